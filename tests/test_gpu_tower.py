@@ -1,0 +1,94 @@
+"""Tower parity (GPU, through the C ABI) vs the fp32 oracle: cosine >= 0.999 and max|a-b|/max|b| <= 1e-2
+(the tolerances BASELINE.json's north_star states), integer artefacts bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import processor as OP, resample as OR, tower as OT
+
+pytestmark = pytest.mark.gpu
+
+
+def _metrics(got, ref):
+    got, ref = got.float().cpu(), ref.float().cpu()
+    cos = torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0).item()
+    maxrel = ((got - ref).abs().max() / ref.abs().max()).item()
+    return cos, maxrel
+
+
+def _fused(sd, cfg, cuda, dtype=torch.float32):
+    from zoomearth_b200 import FusedVisual
+    return FusedVisual(sd, device=cuda, dtype=dtype, depth=cfg["depth"], fullatt=list(cfg["fullatt"]))
+
+
+@pytest.mark.parametrize("grid", [[[1, 8, 8]], [[1, 26, 36], [1, 8, 8], [1, 18, 34], [1, 2, 2]], [[1, 36, 36]]])
+def test_tower_small_depth_vs_oracle(cuda, grid):
+    cfg = OT.small_cfg(depth=3, fullatt=(1,))
+    sd = OT.make_weights(1, cfg)
+    grid = np.array(grid)
+    S = int((grid[:, 1] * grid[:, 2]).sum())
+    pv = torch.randn(S, 1176, generator=torch.Generator().manual_seed(S))
+    fv = _fused(sd, cfg, cuda)
+    out, hidden = fv(pv.to(cuda), torch.from_numpy(grid), return_hidden=True)
+    ref, ref_hidden = OT.forward(sd, pv, grid, cfg, return_hidden=True)
+    ch, mh = _metrics(hidden, ref_hidden)
+    co, mo = _metrics(out, ref)
+    assert ch >= 0.999 and mh <= 1e-2, f"hidden: cos {ch} maxrel {mh}"
+    assert co >= 0.999 and mo <= 1e-2, f"merged: cos {co} maxrel {mo}"
+    # same precision policy on the CPU (bf16 operands, fp32 accumulate / residual) must agree much tighter
+    emu = OT.forward(sd, pv, grid, cfg, emulate_bf16=True)
+    ce, me = _metrics(out, emu)
+    assert me <= 3e-3, f"vs bf16-operand emulation: cos {ce} maxrel {me}"
+
+
+def test_tower_full_depth_vs_oracle(cuda):
+    """All 32 blocks, full attention at 7/15/23/31, one 504x504 zoom crop + one small image."""
+    sd = OT.make_weights(0)
+    grid = np.array([[1, 36, 36], [1, 10, 14]])
+    S = int((grid[:, 1] * grid[:, 2]).sum())
+    pv = torch.randn(S, 1176, generator=torch.Generator().manual_seed(7))
+    fv = _fused(sd, OT.CFG, cuda, dtype=torch.bfloat16)
+    out = fv(pv.to(cuda), torch.from_numpy(grid))
+    assert out.dtype == torch.bfloat16 and out.shape == (S // 4, 2048)
+    ref = OT.forward(sd, pv, grid)
+    cos, maxrel = _metrics(out, ref)
+    assert cos >= 0.999 and maxrel <= 1e-2, f"cos {cos} maxrel {maxrel}"
+
+
+def test_plan_artefacts_bitexact_vs_hf(cuda):
+    """window_index, cu_window_seqlens, cu_seqlens and rotary ids equal the live HF tower's own functions."""
+    from oracle import hf_live
+    from zoomearth_b200 import Plan, _lib
+    cfg = OT.small_cfg(depth=1, fullatt=())
+    m = hf_live.hf_tower(None, cfg)
+    grid = torch.tensor([[1, 70, 70], [1, 26, 36], [1, 64, 92], [1, 4, 200]])
+    p = Plan(_lib.default_cfg(), grid.numpy())
+    w, cu = m.get_window_index(grid)
+    assert np.array_equal(p.window_index, w.numpy())
+    assert p.cu_window_seqlens_raw.tolist() == cu
+    assert p.cu_window_seqlens.tolist() == torch.unique_consecutive(torch.tensor(cu)).tolist()
+    assert np.array_equal(p.pos_ids, OT.rot_pos_ids(grid.numpy()))
+
+
+def test_zoom_step_end_to_end(cuda):
+    """crop -> K1 (bf16, window order) -> tower == oracle crop/resize/patchify -> fp32 oracle tower."""
+    from zoomearth_b200 import FusedImageProcessor, ZoomEncoder
+    cfg = OT.small_cfg(depth=4, fullatt=(3,))
+    sd = OT.make_weights(2, cfg)
+    img = np.random.default_rng(3).integers(0, 256, (1500, 2000, 3), dtype=np.uint8)
+    boxes = [(100, 200, 1300, 1100), (900.5, 700.2, 1100.9, 800.0)]
+    fv = _fused(sd, cfg, cuda)
+    enc = ZoomEncoder(fv, FusedImageProcessor(min_pixels=3136, max_pixels=401408, device=cuda))
+    dev = enc.upload(img)
+    emb, grid, crop = enc.encode([dev], boxes, image_index=[0, 0])
+    rows, grids = [], []
+    for b in boxes:
+        box, pv, g = OP.zoom_step_u8(img, b, 512, 3136, 401408)
+        rows.append(pv)
+        grids.append(g)
+    rgrid = np.concatenate(grids, 0)
+    assert grid.tolist() == rgrid.tolist()
+    ref = OT.forward(sd, torch.from_numpy(np.concatenate(rows, 0)), rgrid, cfg)
+    cos, maxrel = _metrics(emb, ref)
+    assert cos >= 0.999 and maxrel <= 1e-2, f"cos {cos} maxrel {maxrel}"
+    assert enc.last_launches > 0

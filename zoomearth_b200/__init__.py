@@ -1,0 +1,27 @@
+"""zoomearth_b200 - B200-native drop-in for ZoomEarth's per-zoom-step vision path.
+
+crop -> Pillow-exact bicubic smart_resize -> normalize -> patchify (K1) and the Qwen2.5-VL vision tower
+(tcgen05 GEMMs, varlen attention) behind the reference's own surfaces.  Python here is plumbing over the
+C ABI in ``include/zoomvit.h``; the CUDA library is mandatory (no fallback path).
+"""
+from . import _lib, geometry                                    # noqa: F401
+from .geometry import cut_box, extract_bbox, resize_dims, smart_resize   # noqa: F401
+
+
+def __getattr__(name):            # torch-dependent pieces are imported lazily
+    if name == "FusedImageProcessor":
+        from .processor import FusedImageProcessor
+        return FusedImageProcessor
+    if name == "FusedVisual":
+        from .visual import FusedVisual
+        return FusedVisual
+    if name == "ZoomEncoder":
+        from .zoom import ZoomEncoder
+        return ZoomEncoder
+    if name == "install":
+        from .install import install
+        return install
+    if name == "Plan":
+        from .plan import Plan
+        return Plan
+    raise AttributeError(name)

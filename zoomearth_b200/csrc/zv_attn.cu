@@ -1,0 +1,213 @@
+// K3/K4: varlen non-causal attention for the vision tower (HF modeling_qwen2_5_vl.py:207-287).
+// One kernel serves both the 28 windowed layers (segments = windows of <= 64 patches, HF :498-502 with
+// cu_window_seqlens) and the 4 full-attention layers (segments = whole images, cu_seqlens): the host plan
+// turns either segment list into q tiles (q0, q_len, seg_begin, seg_end); a CTA owns one (q tile, head).
+// Flash-style: K/V stream through a cp.async double buffer in 64-row tiles, S = QK^T and O += PV run on
+// mma.sync m16n8k16 (bf16 in, fp32 accumulate), softmax is online in fp32 with exp2.  Rotary embedding is
+// already applied to q,k by the QKV GEMM epilogue (zv_gemm.cu EPI_QKV_ROPE).
+// Layout: qkv (S, 3, heads, 80) bf16, out (S, heads*80) bf16.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+
+#include "zv_common.h"
+#include "zv_gemm.h"
+
+namespace zv {
+namespace {
+
+constexpr int HD = 80;          // head dim
+constexpr int BQ = 64, BKV = 64;
+constexpr int LDS = 88;         // smem row pitch in elements (176 B: conflict-free ldmatrix)
+constexpr int kTileElems = 64 * LDS;
+constexpr int kSmemBytes = 5 * kTileElems * 2;   // Q + 2 x (K, V)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
+  const int n = valid ? 16 : 0;   // src-size 0 => 16 bytes of zeros
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// 64 rows x 80 bf16 from global (row pitch ld elements) into a padded smem tile; rows >= n_valid are zeros.
+__device__ __forceinline__ void load_tile(__nv_bfloat16* s, const __nv_bfloat16* g, int64_t ld, int n_valid) {
+  for (int i = threadIdx.x; i < 64 * 10; i += 128) {
+    const int r = i / 10, c = i % 10;
+    const bool ok = r < n_valid;
+    cp_async16(s + r * LDS + c * 8, g + (int64_t)(ok ? r : 0) * ld + c * 8, ok);
+  }
+}
+
+__global__ void __launch_bounds__(128) attn_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+                                                   const int4* __restrict__ tiles, int heads, float scale_log2) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_raw);
+  __nv_bfloat16* sK = sQ + kTileElems;          // [2][64][LDS]
+  __nv_bfloat16* sV = sK + 2 * kTileElems;      // [2][64][LDS]
+  const int4 tl = tiles[blockIdx.x];
+  const int q0 = tl.x, q_len = tl.y, seg_b = tl.z, seg_e = tl.w;
+  const int head = blockIdx.y;
+  const int hidden = heads * HD;
+  const int64_t ld = 3 * (int64_t)hidden;
+  const __nv_bfloat16* gq = qkv + (int64_t)q0 * ld + head * HD;
+  const __nv_bfloat16* gk = qkv + (int64_t)seg_b * ld + hidden + head * HD;
+  const __nv_bfloat16* gv = gk + hidden;
+  const int kv_len = seg_e - seg_b;
+  const int n_kv = (kv_len + BKV - 1) / BKV;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+
+  load_tile(sQ, gq, ld, q_len);
+  load_tile(sK, gk, ld, min(BKV, kv_len));
+  load_tile(sV, gv, ld, min(BKV, kv_len));
+  cp_async_commit();
+
+  uint32_t qf[5][4];
+  float o[10][4];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+  for (int j = 0; j < n_kv; ++j) {
+    const int buf = j & 1;
+    if (j + 1 < n_kv) {            // prefetch the next K/V tile into the other buffer
+      const int nv = min(BKV, kv_len - (j + 1) * BKV);
+      load_tile(sK + (buf ^ 1) * kTileElems, gk + (int64_t)(j + 1) * BKV * ld, ld, nv);
+      load_tile(sV + (buf ^ 1) * kTileElems, gv + (int64_t)(j + 1) * BKV * ld, ld, nv);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (j == 0) {
+#pragma unroll
+      for (int ks = 0; ks < 5; ++ks) {
+        const int mi = lane >> 3, r = lane & 7;
+        ldsm_x4(qf[ks], sQ + (16 * warp + (mi & 1) * 8 + r) * LDS + 16 * ks + (mi >> 1) * 8);
+      }
+    }
+    const __nv_bfloat16* k = sK + buf * kTileElems;
+    const __nv_bfloat16* v = sV + buf * kTileElems;
+    float s[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+#pragma unroll
+    for (int ks = 0; ks < 5; ++ks) {
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {      // pairs of 8-wide kv tiles
+        uint32_t b[4];
+        const int mi = lane >> 3, r = lane & 7;
+        ldsm_x4(b, k + (16 * np + (mi >> 1) * 8 + r) * LDS + 16 * ks + (mi & 1) * 8);
+        mma_bf16(s[2 * np], qf[ks], b[0], b[1]);
+        mma_bf16(s[2 * np + 1], qf[ks], b[2], b[3]);
+      }
+    }
+    // mask columns beyond the segment, online softmax (rows g and g+8 of this warp's 16)
+    const int kv_base = j * BKV;
+    float mx0 = m0, mx1 = m1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = kv_base + 8 * i + 2 * t;
+      if (c >= kv_len) { s[i][0] = -INFINITY; s[i][2] = -INFINITY; }
+      if (c + 1 >= kv_len) { s[i][1] = -INFINITY; s[i][3] = -INFINITY; }
+      mx0 = fmaxf(mx0, fmaxf(s[i][0], s[i][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[i][2], s[i][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float c0 = exp2f((m0 - mx0) * scale_log2), c1 = exp2f((m1 - mx1) * scale_log2);
+    m0 = mx0; m1 = mx1;
+    const float ms0 = mx0 * scale_log2, ms1 = mx1 * scale_log2;
+    float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s[i][0] = exp2f(s[i][0] * scale_log2 - ms0); s[i][1] = exp2f(s[i][1] * scale_log2 - ms0);
+      s[i][2] = exp2f(s[i][2] * scale_log2 - ms1); s[i][3] = exp2f(s[i][3] * scale_log2 - ms1);
+      rs0 += s[i][0] + s[i][1];
+      rs1 += s[i][2] + s[i][3];
+    }
+    l0 = l0 * c0 + rs0; l1 = l1 * c1 + rs1;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) { o[i][0] *= c0; o[i][1] *= c0; o[i][2] *= c1; o[i][3] *= c1; }
+    // O += P V
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t a[4];
+      a[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+      a[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+      a[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      a[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+      for (int np = 0; np < 5; ++np) {
+        uint32_t b[4];
+        const int mi = lane >> 3, r = lane & 7;
+        ldsm_x4_trans(b, v + (16 * kk + (mi & 1) * 8 + r) * LDS + 8 * (2 * np + (mi >> 1)));
+        mma_bf16(o[2 * np], a, b[0], b[1]);
+        mma_bf16(o[2 * np + 1], a, b[2], b[3]);
+      }
+    }
+    __syncthreads();   // everyone is done with buffer `buf` before iteration j+1 prefetches into it
+  }
+  // finalise: row sums across the quad, normalise, stage through this warp's own Q rows, 16-byte stores
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.f / l0, i1 = 1.f / l1;
+  __nv_bfloat16* so = sQ + 16 * warp * LDS;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    *reinterpret_cast<uint32_t*>(so + g * LDS + 8 * i + 2 * t) = pack_bf16(o[i][0] * i0, o[i][1] * i0);
+    *reinterpret_cast<uint32_t*>(so + (g + 8) * LDS + 8 * i + 2 * t) = pack_bf16(o[i][2] * i1, o[i][3] * i1);
+  }
+  __syncwarp();
+  for (int i = lane; i < 16 * 10; i += 32) {
+    const int r = i / 10, c = i % 10;
+    const int row = 16 * warp + r;
+    if (row < q_len)
+      *reinterpret_cast<uint4*>(out + (int64_t)(q0 + row) * hidden + head * HD + c * 8) =
+          *reinterpret_cast<const uint4*>(so + r * LDS + c * 8);
+  }
+}
+
+}  // namespace
+
+int attention(const void* qkv, void* out, int heads, int head_dim, const int32_t* tiles_dev, int n_tiles, void* stream_) {
+  if (head_dim != HD) return fail(ZV_EINVAL, "attention: only head_dim=80 is built (got %d)", head_dim);
+  if (n_tiles <= 0) return ZV_OK;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return fail(ZV_ECUDA, "attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const float scale_log2 = (float)(1.4426950408889634 / std::sqrt((double)head_dim));
+  dim3 grid((unsigned)n_tiles, (unsigned)heads);
+  attn_kernel<<<grid, 128, kSmemBytes, static_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), reinterpret_cast<const int4*>(tiles_dev),
+      heads, scale_log2);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(ZV_ECUDA, "attention: launch: %s", cudaGetErrorString(e));
+  return ZV_OK;
+}
+
+}  // namespace zv

@@ -1,0 +1,51 @@
+// Shared internals of libzoomvit (not part of the C ABI).
+#pragma once
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <vector>
+
+#include "zoomvit.h"
+
+struct zv_plan;
+namespace zv {
+
+int fail(int code, const char* fmt, ...);   // records the thread-local message, returns code
+void count_launch(int64_t n = 1);
+void reset_launch_count();
+
+// ---- host-side math shared by geometry / preprocess / plan
+struct AxisCoeffs {
+  int32_t in_size = 0, out_size = 0, ksize = 0;
+  std::vector<int32_t> bounds;   // [out][2]
+  std::vector<int32_t> kk;       // [out][ksize]
+};
+int32_t resample_ksize(int32_t in_size, int32_t out_size);
+void resample_coeffs(int32_t in_size, int32_t out_size, AxisCoeffs* out);
+void normalize_lut(const zv_cfg* cfg, float* lut768);
+void plan_device_image(const zv_plan* p, std::vector<uint8_t>* image);
+
+// ---- plan (host tables; device image produced by zv_plan_upload)
+struct PlanDeviceLayout {
+  int64_t off_pos = 0;                     // int32 [S][2]: (h, w) rotary ids, window order
+  int64_t off_rope = 0;                    // float [max_pos][20][2]: (cos, sin) of pos * inv_freq[j]
+  int64_t off_widx = 0;                    // int32 [T]: window position i <-> HF merge-group index
+  int64_t off_win_tiles = 0, off_full_tiles = 0;  // int4 work items (q0, q_len, seg_begin, seg_end)
+  int32_t max_pos = 0;
+  int64_t bytes = 0;
+};
+
+}  // namespace zv
+
+struct zv_plan {
+  zv_cfg cfg;
+  int32_t n_images = 0;
+  int64_t S = 0, T = 0;
+  std::vector<int64_t> grid_thw;
+  std::vector<int64_t> window_index, reverse_index;
+  std::vector<int32_t> cu_window_raw, cu_window, cu_full;
+  std::vector<int32_t> pos_ids;            // [S][2], HF order
+  std::vector<int32_t> win_tiles, full_tiles;   // 4 ints per q tile
+  int32_t n_win_tiles = 0, n_full_tiles = 0;
+  zv::PlanDeviceLayout dev;
+};

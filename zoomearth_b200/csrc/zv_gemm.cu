@@ -1,0 +1,369 @@
+// K2: persistent, warp-specialised tcgen05 GEMM for the tower's contractions
+//   C[M,N] = A[M,K] (bf16, K-major) x B[N,K]^T (bf16, K-major), fp32 accumulation in TMEM,
+// with the epilogues the Qwen2.5-VL vision block needs fused in (HF modeling_qwen2_5_vl.py):
+//   EPI_STORE    plain (+bias) store, fp32 or bf16            patch_embed :113, generic
+//   EPI_QKV_ROPE bias + 2D rotary on q,k heads -> bf16        attn.qkv :226-229 + apply_rotary_pos_emb_vision :156-167
+//   EPI_RESID    X(fp32) += acc + bias                        attn.proj / mlp.down_proj + residual :311-320
+//   EPI_SWIGLU   silu(gate+bg) * (up+bu) -> bf16              mlp :88 (gate/up rows interleaved per 128)
+//   EPI_GELU     gelu_erf(acc + bias) -> bf16                 merger.mlp.0/1 :138-140
+//   EPI_SCATTER  (acc + bias) -> row scatter[row]             merger.mlp.2 + un-reorder :512-513
+//
+// Structure (one CTA per SM, 256 threads): warp 0 = TMA producer (one elected lane), warp 1 = MMA issuer
+// (one elected lane, tcgen05.mma M=128 x N=BN x K=16 from 128B-swizzled smem tiles), warp 2 = TMEM
+// allocator, warps 4-7 = epilogue (tcgen05.ld, one accumulator row per thread).  Three mbarrier pipelines:
+// smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue, two accumulator stages so the epilogue
+// of tile i overlaps the MMAs of tile i+1), and a static persistent tile schedule (n fastest, so CTAs that run
+// together share the A rows in L2 and the whole B matrix stays L2-resident).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <mutex>
+
+#include "zv_common.h"
+#include "zv_gemm.h"
+#include "zv_ptx.cuh"
+
+namespace zv {
+
+using namespace ptx;
+
+namespace {
+
+constexpr int BM = 128, BK = 64, UMMA_K = 16;
+constexpr int kThreads = 256;
+constexpr int kTmemCols = 512;
+
+template <int BN> struct Cfg {
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN > 128) ? 4 : 6;
+  static constexpr int kBarBytes = 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;   // +1024: manual alignment slack
+};
+
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// ---- epilogues: one thread = one accumulator row; `taddr` already carries the warp's lane quarter.
+template <int BN, int EPI>
+__device__ __forceinline__ void epilogue_tile(uint32_t taddr, int m_blk, int n_blk, int row_local, const GemmArgs& g) {
+  const int row = m_blk * BM + row_local;
+  const bool valid = row < g.M;
+  if constexpr (EPI == EPI_STORE || EPI == EPI_GELU || EPI == EPI_SCATTER || EPI == EPI_RESID) {
+    int64_t orow = row;
+    if constexpr (EPI == EPI_SCATTER) orow = valid ? (int64_t)__ldg(g.scatter + row) : 0;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t r[32];
+      __syncwarp();
+      tmem_ld_x32(taddr + c, r);
+      tmem_ld_wait();
+      const int n0 = n_blk * BN + c;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + (g.bias ? __ldg(g.bias + n0 + j) : 0.0f);
+      if constexpr (EPI == EPI_GELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+      }
+      if (!valid) continue;
+      if (EPI == EPI_RESID || g.out_dtype == ZV_F32) {
+        float4* o = reinterpret_cast<float4*>(static_cast<float*>(g.out) + orow * g.ldo + n0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 x = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          if constexpr (EPI == EPI_RESID) {
+            const float4 old = o[j];
+            x.x += old.x; x.y += old.y; x.z += old.z; x.w += old.w;
+          }
+          o[j] = x;
+        }
+      } else {
+        uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(g.out) + orow * g.ldo + n0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          o[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                            pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+      }
+    }
+  } else if constexpr (EPI == EPI_SWIGLU) {
+    static_assert(EPI != EPI_SWIGLU || BN == 256, "SwiGLU tiles hold 128 gate + 128 up columns");
+#pragma unroll 1
+    for (int c = 0; c < 128; c += 32) {
+      uint32_t a[32], b[32];
+      __syncwarp();
+      tmem_ld_x32(taddr + c, a);
+      tmem_ld_x32(taddr + 128 + c, b);
+      tmem_ld_wait();
+      const float* bias = g.bias + (int64_t)n_blk * 256 + c;
+      uint32_t o[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float g0 = __uint_as_float(a[2 * j]) + __ldg(bias + 2 * j), g1 = __uint_as_float(a[2 * j + 1]) + __ldg(bias + 2 * j + 1);
+        const float u0 = __uint_as_float(b[2 * j]) + __ldg(bias + 128 + 2 * j), u1 = __uint_as_float(b[2 * j + 1]) + __ldg(bias + 128 + 2 * j + 1);
+        o[j] = pack_bf16(silu(g0) * u0, silu(g1) * u1);
+      }
+      if (!valid) continue;
+      uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(g.out) + (int64_t)row * g.ldo + n_blk * 128 + c);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+    }
+  } else if constexpr (EPI == EPI_QKV_ROPE) {
+    static_assert(EPI != EPI_QKV_ROPE || BN == 240, "QKV tiles hold three 80-wide heads");
+    int ph = 0, pw = 0;
+    if (valid) { ph = __ldg(g.pos + 2 * row); pw = __ldg(g.pos + 2 * row + 1); }
+    const float2* rope_h = g.rope + (int64_t)ph * 20;
+    const float2* rope_w = g.rope + (int64_t)pw * 20;
+#pragma unroll 1
+    for (int hh = 0; hh < 3; ++hh) {
+      uint32_t r0[32], r1[32], r2[16];
+      __syncwarp();
+      tmem_ld_x32(taddr + hh * 80, r0);
+      tmem_ld_x32(taddr + hh * 80 + 32, r1);
+      tmem_ld_x16(taddr + hh * 80 + 64, r2);
+      tmem_ld_wait();
+      const int n0 = n_blk * 240 + hh * 80;
+      float x[80];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r0[j]) + __ldg(g.bias + n0 + j);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[32 + j] = __uint_as_float(r1[j]) + __ldg(g.bias + n0 + 32 + j);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) x[64 + j] = __uint_as_float(r2[j]) + __ldg(g.bias + n0 + 64 + j);
+      const int head = n_blk * 3 + hh;          // 0..47: q heads, then k heads, then v heads
+      if (head < 2 * g.heads) {
+        // rotate_half pairs (d, d+40); angle index d<20 -> h position, 20<=d<40 -> w position (emb = cat(rot, rot))
+#pragma unroll
+        for (int d = 0; d < 40; ++d) {
+          const float2 cs = d < 20 ? __ldg(rope_h + d) : __ldg(rope_w + (d - 20));
+          const float lo = x[d], hi = x[d + 40];
+          x[d] = lo * cs.x - hi * cs.y;
+          x[d + 40] = hi * cs.x + lo * cs.y;
+        }
+      }
+      if (!valid) continue;
+      uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(g.out) + (int64_t)row * g.ldo + n0);
+#pragma unroll
+      for (int j = 0; j < 10; ++j)
+        dst[j] = make_uint4(pack_bf16(x[8 * j], x[8 * j + 1]), pack_bf16(x[8 * j + 2], x[8 * j + 3]),
+                            pack_bf16(x[8 * j + 4], x[8 * j + 5]), pack_bf16(x[8 * j + 6], x[8 * j + 7]));
+    }
+  }
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc(const __grid_constant__ CUtensorMap tma_a,
+                                                       const __grid_constant__ CUtensorMap tma_b, const GemmArgs g) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + C::kStages;
+  uint64_t* tfull = bars + 2 * C::kStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_blocks = g.N / BN;
+  const int m_blocks = (g.M + BM - 1) / BM;
+  const int num_tiles = m_blocks * n_blocks;
+  const int k_blocks = (g.K + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tma_a);
+    prefetch_tensormap(&tma_b);
+    for (int s = 0; s < C::kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 4); }
+    fence_mbar_init();
+  }
+  if (warp == 2) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(empty + stage, phase ^ 1);
+          uint8_t* sa = smem + stage * C::kStageBytes;
+          mbar_arrive_expect_tx(full + stage, C::kStageBytes);
+          tma_load_2d(sa, &tma_a, full + stage, kb * BK, m_blk * BM);
+          tma_load_2d(sa + C::kABytes, &tma_b, full + stage, kb * BK, n_blk * BN);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(tempty + acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * 256;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(full + stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
+          const uint64_t da = umma_desc_k128(sa), db = umma_desc_k128(sa + C::kABytes);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);   // +32 B per K step, in 16 B units
+          umma_commit(empty + stage);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull + acc);
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(tfull + acc, acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
+      epilogue_tile<BN, EPI>(taddr, m_blk, n_blk, q * 32 + lane, g);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty + acc);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
+}
+
+// ---- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 2-D bf16 tensor (rows, cols) with row pitch `ld` elements; box = 64 columns x box_rows, 128B swizzle, OOB = 0.
+int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(ZV_ECUDA, "gemm: cuTensorMapEncodeTiled is not available from the driver");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * 2) % 16)
+    return fail(ZV_EINVAL, "gemm: operand base/pitch must be 16-byte aligned (base %p, ld %lld)", base, (long long)ld);
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ZV_ECUDA, "gemm: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return ZV_OK;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+template <int BN, int EPI>
+int launch(const GemmArgs& g, const void* a, int64_t lda, const void* b, int64_t ldb, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  if (g.N % BN) return fail(ZV_EINVAL, "gemm: N=%d is not a multiple of the %d-wide tile", g.N, BN);
+  CUtensorMap ta, tb;
+  int rc = make_tmap(&ta, a, g.M, g.K, lda, BM);
+  if (rc) return rc;
+  rc = make_tmap(&tb, b, g.N, g.K, ldb, BN);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) return fail(ZV_ECUDA, "gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int tiles = ((g.M + BM - 1) / BM) * (g.N / BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_tc<BN, EPI><<<grid, kThreads, C::kSmemBytes, stream>>>(ta, tb, g);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(ZV_ECUDA, "gemm: launch: %s", cudaGetErrorString(e));
+  return ZV_OK;
+}
+
+}  // namespace
+
+int gemm(int epi, const GemmArgs& g, const void* a, int64_t lda, const void* b, int64_t ldb, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0) return fail(ZV_EINVAL, "gemm: empty problem %dx%dx%d", g.M, g.N, g.K);
+  switch (epi) {
+    case EPI_STORE:
+      return g.N % 256 == 0 ? launch<256, EPI_STORE>(g, a, lda, b, ldb, stream)
+                            : launch<128, EPI_STORE>(g, a, lda, b, ldb, stream);
+    case EPI_QKV_ROPE: return launch<240, EPI_QKV_ROPE>(g, a, lda, b, ldb, stream);
+    case EPI_RESID: return launch<256, EPI_RESID>(g, a, lda, b, ldb, stream);
+    case EPI_SWIGLU: return launch<256, EPI_SWIGLU>(g, a, lda, b, ldb, stream);
+    case EPI_GELU: return launch<256, EPI_GELU>(g, a, lda, b, ldb, stream);
+    case EPI_SCATTER: return launch<256, EPI_SCATTER>(g, a, lda, b, ldb, stream);
+  }
+  return fail(ZV_EINVAL, "gemm: unknown epilogue %d", epi);
+}
+
+}  // namespace zv
+
+extern "C" int zv_gemm_bf16(const void* a_dev, int64_t lda, const void* b_dev, int64_t ldb, const float* bias_dev,
+                            void* c_dev, int64_t ldc, int32_t c_dtype, int64_t m, int64_t n, int64_t k, void* stream) {
+  zv::reset_launch_count();
+  if (!a_dev || !b_dev || !c_dev) return zv::fail(ZV_EINVAL, "zv_gemm_bf16: null pointer");
+  if (n % 128) return zv::fail(ZV_EINVAL, "zv_gemm_bf16: N must be a multiple of 128");
+  if (c_dtype != ZV_F32 && c_dtype != ZV_BF16) return zv::fail(ZV_EINVAL, "zv_gemm_bf16: bad c_dtype");
+  zv::GemmArgs g{};
+  g.M = (int)m; g.N = (int)n; g.K = (int)k;
+  g.out = c_dev; g.ldo = ldc; g.out_dtype = c_dtype; g.bias = bias_dev;
+  return zv::gemm(zv::EPI_STORE, g, a_dev, lda, b_dev, ldb, stream);
+}
+
+// Epilogue-selectable variant, exposed so unit tests can check every fused epilogue in isolation.
+extern "C" int zv_gemm_ex(int32_t epilogue, const void* a_dev, int64_t lda, const void* b_dev, int64_t ldb,
+                          const float* bias_dev, void* out_dev, int64_t ldo, int32_t out_dtype, int64_t m, int64_t n,
+                          int64_t k, const int32_t* pos_dev, const float* rope_dev, const int32_t* scatter_dev,
+                          int32_t heads, void* stream) {
+  zv::reset_launch_count();
+  if (!a_dev || !b_dev || !out_dev) return zv::fail(ZV_EINVAL, "zv_gemm_ex: null pointer");
+  zv::GemmArgs g{};
+  g.M = (int)m; g.N = (int)n; g.K = (int)k;
+  g.out = out_dev; g.ldo = ldo; g.out_dtype = out_dtype; g.bias = bias_dev;
+  g.pos = pos_dev; g.rope = reinterpret_cast<const float2*>(rope_dev); g.scatter = scatter_dev; g.heads = heads;
+  if (epilogue != zv::EPI_STORE && !bias_dev) return zv::fail(ZV_EINVAL, "zv_gemm_ex: this epilogue needs a bias");
+  if (epilogue == zv::EPI_QKV_ROPE && (!pos_dev || !rope_dev)) return zv::fail(ZV_EINVAL, "zv_gemm_ex: rope tables missing");
+  if (epilogue == zv::EPI_SCATTER && !scatter_dev) return zv::fail(ZV_EINVAL, "zv_gemm_ex: scatter index missing");
+  return zv::gemm(epilogue, g, a_dev, lda, b_dev, ldb, stream);
+}

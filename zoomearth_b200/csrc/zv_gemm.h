@@ -1,0 +1,34 @@
+// Internal interface of the tcgen05 GEMM (zv_gemm.cu) and the other tower kernels.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace zv {
+
+enum GemmEpilogue { EPI_STORE = 0, EPI_QKV_ROPE = 1, EPI_RESID = 2, EPI_SWIGLU = 3, EPI_GELU = 4, EPI_SCATTER = 5 };
+
+struct GemmArgs {
+  int M, N, K;
+  int out_dtype;            // ZV_F32 / ZV_BF16 (EPI_STORE, EPI_SCATTER); others are fixed
+  void* out;
+  int64_t ldo;              // output row pitch in elements
+  const float* bias;        // [N] (EPI_SWIGLU: packed like the weight rows); may be null for EPI_STORE
+  const int32_t* pos;       // EPI_QKV_ROPE: [M][2] (h, w)
+  const float2* rope;       // EPI_QKV_ROPE: [max_pos][20] (cos, sin)
+  const int32_t* scatter;   // EPI_SCATTER: [M] output row of accumulator row i
+  int heads;                // EPI_QKV_ROPE
+};
+
+// C = A[M,K] * B[N,K]^T with the chosen epilogue, enqueued on `stream`.
+int gemm(int epi, const GemmArgs& g, const void* a, int64_t lda, const void* b, int64_t ldb, void* stream);
+
+// fp32 (S, H) -> bf16 (S, H): y = w * (x * rsqrt(mean(x^2) + eps))   (HF Qwen2_5_VLRMSNorm :66-71)
+int rmsnorm(const float* x, const float* w, void* y_bf16, int64_t rows, int hidden, float eps, void* stream);
+// patches in HF order (f32 or bf16) -> bf16 in window order (groups of `unit` rows move together)
+int gather_rows(const void* src, int src_dtype, void* dst_bf16, const int32_t* widx, int64_t n_groups, int unit,
+                int cols, void* stream);
+// varlen non-causal attention over q tiles; qkv (S, 3*H) bf16 with rotary already applied
+int attention(const void* qkv, void* out, int heads, int head_dim, const int32_t* tiles_dev, int n_tiles,
+              void* stream);
+
+}  // namespace zv

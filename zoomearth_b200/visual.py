@@ -1,0 +1,150 @@
+"""FusedVisual - drop-in for ``model.visual`` (HF ``Qwen2_5_VisionTransformerPretrainedModel``).
+
+Same call as the reference makes through the LM forward (HF modeling_qwen2_5_vl.py:1172,
+``self.visual(pixel_values, grid_thw=image_grid_thw)``; reference copy ``qwen2_5vl_monkey_patch.py:93``):
+``forward(hidden_states (S,1176), grid_thw (N,3)) -> (T, out_hidden)`` in ``self.dtype``, HF row order.
+The whole forward (HF :455-518) runs inside ``zv_visual_forward`` on hand-written sm_100a kernels; this module
+only owns the packed weights, a plan cache and a workspace, all as torch tensors (plumbing).
+"""
+import ctypes as C
+from collections import OrderedDict
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib
+from .plan import Plan
+
+_DT = {torch.float32: _lib.ZV_F32, torch.bfloat16: _lib.ZV_BF16}
+
+
+def _vision_cfg_from_hf(config):
+    return dict(depth=config.depth, hidden=config.hidden_size, heads=config.num_heads,
+                inter=config.intermediate_size, out_hidden=config.out_hidden_size, patch=config.patch_size,
+                merge=config.spatial_merge_size, temporal=config.temporal_patch_size, window=config.window_size,
+                fullatt=list(config.fullatt_block_indexes))
+
+
+class FusedVisual(nn.Module):
+    def __init__(self, state_dict, device=None, dtype=torch.bfloat16, return_pooling_output=False, **cfg_overrides):
+        """state_dict: HF names relative to the tower (``visual.`` / ``model.visual.`` prefixes are accepted).
+        ``dtype`` is the dtype of the returned embeddings (what callers read as ``visual.dtype``)."""
+        super().__init__()
+        if not torch.cuda.is_available():
+            raise RuntimeError("FusedVisual needs a CUDA device (sm_100); there is no CPU fallback")
+        self._device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self._dtype = dtype
+        if dtype not in _DT:
+            raise ValueError("FusedVisual returns float32 or bfloat16 embeddings")
+        self.cfg = _lib.default_cfg(**cfg_overrides)
+        self.spatial_merge_size = self.cfg.merge
+        self.patch_size = self.cfg.patch
+        self.spatial_merge_unit = self.cfg.merge ** 2
+        self.return_pooling_output = return_pooling_output
+        self._plans = OrderedDict()
+        self._ws = None
+        self.last_launches = 0
+        self._pack(state_dict)
+
+    @classmethod
+    def from_hf(cls, hf_visual, **kw):
+        """Build from an instantiated HF vision tower (weights are read from its state_dict)."""
+        cfg = _vision_cfg_from_hf(hf_visual.config)
+        kw.setdefault("dtype", torch.bfloat16)
+        return cls(hf_visual.state_dict(), **cfg, **kw)
+
+    def _pack(self, state_dict):
+        lib = _lib.lib()
+        nbytes = _lib.check(lib.zv_weights_bytes(C.byref(self.cfg)))
+        packed = torch.empty(nbytes, dtype=torch.uint8, device=self._device)
+        keep, descs = [], []
+        for name, t in state_dict.items():
+            if not isinstance(t, torch.Tensor) or "inv_freq" in name:
+                continue
+            if t.dtype not in _DT:
+                t = t.float()
+            t = t.detach().to(self._device).contiguous()
+            keep.append(t)
+            d = _lib.ZvTensor()
+            d.name = name.encode()
+            d.data = t.data_ptr()
+            d.dtype = _DT[t.dtype]
+            d.ndim = t.ndim
+            for i, s in enumerate(t.shape):
+                d.shape[i] = s
+            descs.append(d)
+        arr = (_lib.ZvTensor * len(descs))(*descs)
+        stream = torch.cuda.current_stream(self._device).cuda_stream
+        with torch.cuda.device(self._device):
+            _lib.check(lib.zv_weights_pack(C.byref(self.cfg), arr, len(descs), packed.data_ptr(), nbytes, stream))
+            torch.cuda.current_stream(self._device).synchronize()      # sources may be freed after this
+        self.register_buffer("packed_weights", packed, persistent=False)
+
+    # ---- attributes callers read
+    @property
+    def dtype(self):
+        return self._dtype
+
+    @property
+    def device(self):
+        return self._device
+
+    def get_dtype(self):
+        return self._dtype
+
+    def get_device(self):
+        return self._device
+
+    def plan_for(self, grid_thw):
+        g = np.ascontiguousarray(np.asarray(grid_thw.cpu() if isinstance(grid_thw, torch.Tensor) else grid_thw,
+                                            dtype=np.int64).reshape(-1, 3))
+        key = g.tobytes()
+        p = self._plans.get(key)
+        if p is None:
+            p = Plan(self.cfg, g)
+            self._plans[key] = p
+            if len(self._plans) > 64:
+                self._plans.popitem(last=False)
+        else:
+            self._plans.move_to_end(key)
+        return p
+
+    def _workspace(self, nbytes):
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self._device)
+        return self._ws
+
+    @torch.no_grad()
+    def forward(self, hidden_states, grid_thw, window_order=False, return_hidden=False, **kwargs):
+        """hidden_states: (S, 1176) patches, float32/bfloat16, HF row order (or the window-ordered bf16 output of
+        the fused preprocess when ``window_order=True``)."""
+        lib = _lib.lib()
+        plan = self.plan_for(grid_thw)
+        x = hidden_states
+        if x.device != self._device:
+            x = x.to(self._device, non_blocking=True)
+        if x.dtype not in _DT:
+            x = x.float()
+        x = x.contiguous()
+        if x.shape != (plan.num_patches, 1176):
+            raise ValueError(f"pixel_values has shape {tuple(x.shape)}, grid_thw implies ({plan.num_patches}, 1176)")
+        stream = torch.cuda.current_stream(self._device).cuda_stream
+        with torch.cuda.device(self._device):
+            tables = plan.device_tables(self._device, stream)
+            ws = self._workspace(_lib.check(lib.zv_visual_workspace_bytes(C.byref(self.cfg), plan.handle)))
+            out = torch.empty((plan.num_tokens, self.cfg.out_hidden), dtype=self._dtype, device=self._device)
+            hidden = (torch.empty((plan.num_patches, self.cfg.hidden), dtype=torch.float32, device=self._device)
+                      if (return_hidden or self.return_pooling_output) else None)
+            _lib.check(lib.zv_visual_forward(
+                C.byref(self.cfg), self.packed_weights.data_ptr(), plan.handle, tables.data_ptr(), x.data_ptr(),
+                _DT[x.dtype], _lib.ORDER_WINDOW if window_order else _lib.ORDER_HF, out.data_ptr(), _DT[self._dtype],
+                hidden.data_ptr() if hidden is not None else None, ws.data_ptr(), ws.numel(), stream))
+        self.last_launches = lib.zv_last_launch_count()
+        if self.return_pooling_output:
+            from transformers.modeling_outputs import BaseModelOutputWithPooling
+            return BaseModelOutputWithPooling(last_hidden_state=hidden.to(self._dtype), pooler_output=out)
+        if return_hidden:
+            return out, hidden
+        return out
