@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py - vision tokens/s through crop -> patchify -> ViT (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus 1 --steps 3 --warmup 3            # our arm (CUDA, through the C ABI)
+    python bench.py --impl reference --gpus 1 --steps 1      # the reference's CPU path on the host cores
+    torchrun --nproc-per-node N ... bench.py --gpus N ...    # one rank per GPU, weak scaling by image
+
+Workload = BASELINE.json configs[1]: "Global view: 64 synthetic 5000x5000 images downscaled to
+max_pixels=1280*28*28" -> per image 980x980, grid (1,70,70), 4900 patches, 1225 vision tokens.  One step =
+one pass of the hot path over that batch: zv_preprocess (K1, bf16 patches in window order) then
+zv_visual_forward (32-block tower + merger), random-init Qwen2.5-VL-3B vision weights, synthetic pixels.
+
+`value`   : tokens/s with the uint8 images already resident in HBM (device-timed, CUDA events, max over ranks).
+`e2e`     : same metric through the public Python surface with HOST (pinned) uint8 images: H2D of the pixels and
+            D2H of the embeddings inside the timed region.
+`roofline`: all tcgen05 GEMM launches of the timed region (event-timed per launch on the launching stream)
+            against the measured dense bf16 peak; `roofline_k1` / `roofline_attn` give the other kernel classes.
+`cpu_baseline`: the reference's own CPU path (Pillow + HF PIL processor + HF torch tower, fp32) on a bounded
+            sample of the same workload, on this box's host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+IMG = 5000
+MAX_PIXELS = 1280 * 28 * 28
+MIN_PIXELS = 56 * 56
+KCLASS = {"k1_hpass": 0, "k1_vpass": 1, "gemm_store": 2, "gemm_qkv": 3, "gemm_resid": 4, "gemm_swiglu": 5,
+          "gemm_gelu": 6, "gemm_scatter": 7, "attn_window": 8, "attn_full": 9, "rmsnorm": 10, "gather": 11}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def flops_per_step(n_img, S_img):
+    """Algorithmic FLOPs: linear, window attention, full attention.  grid 70x70 per image."""
+    S, T = n_img * S_img, n_img * S_img // 4
+    f_lin = S * 1262940160 + T * 73400320
+    # window attention: 28 layers, sum over windows 4 n^2 1280 ; 70x70 grid -> 35x35 merge groups -> windows of 4x4
+    lh = lw = 35
+    n_w = []
+    for wy in range(0, lh, 4):
+        for wx in range(0, lw, 4):
+            n_w.append(4 * min(4, lh - wy) * min(4, lw - wx))
+    f_win = 28 * n_img * sum(4 * n * n * 1280 for n in n_w)
+    f_full = 4 * n_img * 4 * S_img * S_img * 1280
+    return f_lin, f_win, f_full
+
+
+# ------------------------------------------------------------------------------------------- reference arm (CPU)
+def reference_step(sample_images, seed0=0):
+    """The reference's CPU path on `sample_images` images of the workload: Pillow + HF PIL processor + HF tower."""
+    from PIL import Image
+    from oracle import hf_live, tower as OT
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = hf_live.hf_tower(None, OT.CFG, torch.float32, seed=0)
+    imgs = [np.random.default_rng(seed0 + i).integers(0, 256, (IMG, IMG, 3), dtype=np.uint8) for i in range(sample_images)]
+    t0 = time.perf_counter()
+    tokens = 0
+    for im in imgs:
+        pil = Image.fromarray(im)
+        crop, _ = hf_live.pil_cut_image(im, (0, 0, IMG, IMG))          # global view: the full-image box
+        pv, grid = hf_live.hf_preprocess([crop], MIN_PIXELS, MAX_PIXELS)
+        out = hf_live.hf_tower_forward(model, pv, grid)
+        tokens += out.shape[0]
+        del pil
+    dt = time.perf_counter() - t0
+    return tokens, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = max(1, args.ref_images)
+    best = None
+    for _ in range(max(0, args.warmup if args.warmup < 2 else 1)):
+        reference_step(1)
+    times = []
+    tokens = 0
+    for _ in range(args.steps):
+        tokens, dt = reference_step(sample)
+        times.append(dt)
+    dt = float(np.mean(times))
+    v = tokens / dt
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": "vision tokens/s crop->patchify->ViT", "value": v, "unit": "tokens/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "global view: 5000x5000 uint8 -> max_pixels=1280*28*28 (980x980, 1225 tokens/image), "
+                               "Qwen2.5-VL-3B vision tower random init", "images_per_step": sample},
+        "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": cores, "kind": "reference",
+                         "sample": f"{sample} of the 64 images per step: PIL crop + HF Qwen2VLImageProcessorPil + HF "
+                                   f"Qwen2_5_VisionTransformerPretrainedModel fp32 sdpa, {cores} torch threads"},
+        "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------- our arm (CUDA)
+def run_ours(args):
+    import torch.distributed as dist
+    from zoomearth_b200 import FusedImageProcessor, FusedVisual, ZoomEncoder, _lib
+    from zoomearth_b200.synthetic import random_vision_state_dict
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.lib()
+    n_img = args.images
+    pk = peaks()
+
+    sd = random_vision_state_dict(0, device=dev)
+    visual = FusedVisual(sd, device=dev, dtype=torch.bfloat16)
+    del sd
+    enc = ZoomEncoder(visual, FusedImageProcessor(min_pixels=MIN_PIXELS, max_pixels=MAX_PIXELS, device=dev))
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    images = [torch.randint(0, 256, (IMG, IMG, 3), generator=g, dtype=torch.uint8, device=dev) for _ in range(n_img)]
+    S_img, T_img = 4900, 1225
+    tokens_step = n_img * T_img
+
+    def step():
+        emb, grid, _ = enc.encode(images, None)
+        if world > 1:
+            out = torch.empty((world * emb.shape[0], emb.shape[1]), dtype=emb.dtype, device=dev)
+            dist.all_gather_into_tensor(out, emb)          # C1: gather of the output embeddings (equal shards)
+            return out
+        return emb
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    lib.zv_timing_reset()
+    lib.zv_timing_enable(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    launches = 0
+    for _ in range(args.steps):
+        step()
+        launches += enc.last_launches
+    e1.record()
+    barrier()
+    lib.zv_timing_enable(0)
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    ms_step = ms / args.steps
+    value = world * tokens_step / (ms_step / 1e3)
+
+    # per-kernel-class device time inside the timed region
+    cls = {}
+    for name, cid in KCLASS.items():
+        t, n = C.c_double(), C.c_int64()
+        _lib.check(lib.zv_timing_read(cid, C.byref(t), C.byref(n)))
+        cls[name] = (t.value, n.value)
+    lib.zv_timing_reset()
+    f_lin, f_win, f_full = flops_per_step(n_img, S_img)
+    gemm_ms = sum(cls[k][0] for k in cls if k.startswith("gemm"))
+    gemm_n = sum(cls[k][1] for k in cls if k.startswith("gemm"))
+    gemm_tf = f_lin * args.steps / (gemm_ms / 1e3) / 1e12 if gemm_ms else 0.0
+    k1_ms = cls["k1_hpass"][0] + cls["k1_vpass"][0]
+    k1_bytes = n_img * (IMG * IMG * 3 + S_img * 1176 * 2)
+    k1_gbs = k1_bytes * args.steps / (k1_ms / 1e3) / 1e9 if k1_ms else 0.0
+    attn_ms = cls["attn_window"][0] + cls["attn_full"][0]
+    attn_tf = (f_win + f_full) * args.steps / (attn_ms / 1e3) / 1e12 if attn_ms else 0.0
+    tower_tf = (f_lin + f_win + f_full) * args.steps / ((ms - k1_ms) / 1e3) / 1e12
+
+    # ---- e2e: host (pinned) pixels in, embeddings out to the host, through the public API
+    e2e = None
+    if not args.no_e2e:
+        n_e2e = min(n_img, args.e2e_images)
+        host = [im.cpu().pin_memory() for im in images[:n_e2e]]
+        out_host = torch.empty((n_e2e * T_img, 2048), dtype=torch.bfloat16).pin_memory()
+
+        def step_e2e():
+            dimg = [enc.upload(h) for h in host]                     # H2D of this step's pixels
+            emb, _, _ = enc.encode(dimg, None)
+            out_host.copy_(emb, non_blocking=True)                   # D2H of the step's result
+            torch.cuda.current_stream().synchronize()
+
+        for _ in range(2):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        k_e2e = max(1, args.steps)
+        for _ in range(k_e2e):
+            step_e2e()
+        barrier()
+        dt = (time.perf_counter() - t0) / k_e2e
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = t.item()
+        e2e = {"value": world * n_e2e * T_img / dt, "unit": "tokens/s", "h2d_bytes_per_step": n_e2e * IMG * IMG * 3,
+               "d2h_bytes_per_step": n_e2e * T_img * 2048 * 2, "images_per_step": n_e2e, "ms_per_step": dt * 1e3}
+        del host
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        tokens, dt = reference_step(args.ref_images)
+        cores = torch.get_num_threads()
+        cpu_base = {"value": tokens / dt, "unit": "tokens/s", "cores": cores, "kind": "reference",
+                    "sample": f"{args.ref_images} of the {n_img} images of one step ({tokens} tokens, {dt:.1f} s): PIL crop + "
+                              f"HF Qwen2VLImageProcessorPil + HF vision tower fp32 sdpa on {cores} threads"}
+
+    if rank == 0:
+        line = {
+            "metric": "vision tokens/s crop->patchify->ViT", "value": value, "unit": "tokens/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[1]: global view, 64 synthetic 5000x5000 uint8 images -> "
+                                   "max_pixels=1280*28*28 (980x980, grid 1x70x70, 1225 tokens/image) -> "
+                                   "Qwen2.5-VL-3B vision tower (random init)",
+                       "images_per_step_per_gpu": n_img, "tokens_per_step_per_gpu": tokens_step,
+                       "l2": "inputs larger than L2 (4.8 GB of pixels, 5.5 GB of activations per step)",
+                       "parallelism": f"dp{world} by image, NCCL all-gather of embeddings" if world > 1 else "single GPU"},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": e2e,
+            "roofline": {"bound": "tensor", "kernel": "gemm_tc (tcgen05, all epilogues)", "achieved": gemm_tf,
+                         "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": gemm_tf / pk["tf_sust"],
+                         "frac_of_burst": gemm_tf / pk["tf_burst"], "peak_source": pk["src"] + ", sustained",
+                         "traffic": None, "launches": gemm_n, "ms_total": gemm_ms,
+                         "share_of_step": gemm_ms / ms},
+            "roofline_k1": {"bound": "hbm", "kernel": "k1_hpass + k1_vpass", "achieved": k1_gbs, "peak": pk["hbm"],
+                            "unit": "GB/s", "frac": k1_gbs / pk["hbm"], "ms_total": k1_ms, "share_of_step": k1_ms / ms,
+                            "traffic": None},
+            "roofline_attn": {"bound": "tensor", "kernel": "attn_kernel (mma.sync)", "achieved": attn_tf,
+                              "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": attn_tf / pk["tf_sust"],
+                              "ms_total": attn_ms, "share_of_step": attn_ms / ms},
+            "tower_tflops": tower_tf,
+            "kernel_ms": {k: round(v[0] / args.steps, 3) for k, v in cls.items()},
+            "cpu_baseline": cpu_base,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--images", type=int, default=64, help="images per step per GPU (BASELINE configs[1]: 64)")
+    ap.add_argument("--e2e-images", type=int, default=64)
+    ap.add_argument("--ref-images", type=int, default=1, help="images in the CPU reference sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -147,6 +147,13 @@ ZV_API int zv_visual_forward(const zv_cfg* cfg, const void* weights_dev, const z
 /* Number of kernels the last zv_preprocess / zv_visual_forward call on this thread launched. */
 ZV_API int64_t zv_last_launch_count(void);
 
+/* Optional per-kernel-class device timing (CUDA events on the launching stream around every launch of that
+ * class).  Classes: 0 k1 hpass, 1 k1 vpass, 2 gemm store, 3 gemm qkv+rope, 4 gemm residual, 5 gemm swiglu,
+ * 6 gemm gelu, 7 gemm scatter, 8 attention (window layers), 9 attention (full layers), 10 rmsnorm, 11 gather. */
+ZV_API void zv_timing_enable(int on);
+ZV_API void zv_timing_reset(void);
+ZV_API int zv_timing_read(int kernel_class, double* ms_total, int64_t* count);
+
 /* Standalone GEMM entry (the tower's tcgen05 kernel), exposed for unit tests and roofline runs:
  * C[M,N] = A[M,K] (bf16, row-major, lda elements) * B[N,K]^T (bf16) (+ bias[N] fp32), out fp32 or bf16. */
 ZV_API int zv_gemm_bf16(const void* a_dev, int64_t lda, const void* b_dev, int64_t ldb, const float* bias_dev,

@@ -69,6 +69,9 @@ _PROTOS = {
     "zv_visual_forward": (C.c_int, [_P(ZvCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                     C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "zv_last_launch_count": (C.c_int64, []),
+    "zv_timing_enable": (None, [C.c_int]),
+    "zv_timing_reset": (None, []),
+    "zv_timing_read": (C.c_int, [C.c_int, _P(C.c_double), _P(C.c_int64)]),
     "zv_gemm_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
                                C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]),
     "zv_gemm_ex": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,

@@ -190,7 +190,8 @@ __global__ void __launch_bounds__(128) attn_kernel(const __nv_bfloat16* __restri
 
 }  // namespace
 
-int attention(const void* qkv, void* out, int heads, int head_dim, const int32_t* tiles_dev, int n_tiles, void* stream_) {
+int attention(const void* qkv, void* out, int heads, int head_dim, const int32_t* tiles_dev, int n_tiles, void* stream_,
+              bool full_layer) {
   if (head_dim != HD) return fail(ZV_EINVAL, "attention: only head_dim=80 is built (got %d)", head_dim);
   if (n_tiles <= 0) return ZV_OK;
   static bool attr_set = false;
@@ -201,9 +202,12 @@ int attention(const void* qkv, void* out, int heads, int head_dim, const int32_t
   }
   const float scale_log2 = (float)(1.4426950408889634 / std::sqrt((double)head_dim));
   dim3 grid((unsigned)n_tiles, (unsigned)heads);
-  attn_kernel<<<grid, 128, kSmemBytes, static_cast<cudaStream_t>(stream_)>>>(
-      static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), reinterpret_cast<const int4*>(tiles_dev),
-      heads, scale_log2);
+  {
+    KernelTimer timer(full_layer ? KC_ATTN_FULL : KC_ATTN_WINDOW, stream_);
+    attn_kernel<<<grid, 128, kSmemBytes, static_cast<cudaStream_t>(stream_)>>>(
+        static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), reinterpret_cast<const int4*>(tiles_dev),
+        heads, scale_log2);
+  }
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(ZV_ECUDA, "attention: launch: %s", cudaGetErrorString(e));

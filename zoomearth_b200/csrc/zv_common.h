@@ -14,6 +14,20 @@ int fail(int code, const char* fmt, ...);   // records the thread-local message,
 void count_launch(int64_t n = 1);
 void reset_launch_count();
 
+// Kernel classes for the optional event timing (zv_timing_*): one id per kernel template.
+enum KernelClass { KC_K1_HPASS = 0, KC_K1_VPASS = 1, KC_GEMM_STORE = 2, KC_GEMM_QKV = 3, KC_GEMM_RESID = 4,
+                   KC_GEMM_SWIGLU = 5, KC_GEMM_GELU = 6, KC_GEMM_SCATTER = 7, KC_ATTN_WINDOW = 8, KC_ATTN_FULL = 9,
+                   KC_RMSNORM = 10, KC_GATHER = 11, KC_COUNT = 12 };
+// RAII: records an event pair around the launches issued in its scope when timing is enabled.
+class KernelTimer {
+ public:
+  KernelTimer(int cls, void* stream);
+  ~KernelTimer();
+ private:
+  void* stream_;
+  int idx_;
+};
+
 // ---- host-side math shared by geometry / preprocess / plan
 struct AxisCoeffs {
   int32_t in_size = 0, out_size = 0, ksize = 0;

@@ -312,7 +312,10 @@ int launch(const GemmArgs& g, const void* a, int64_t lda, const void* b, int64_t
   }
   const int tiles = ((g.M + BM - 1) / BM) * (g.N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tc<BN, EPI><<<grid, kThreads, C::kSmemBytes, stream>>>(ta, tb, g);
+  {
+    KernelTimer timer(KC_GEMM_STORE + EPI, stream);
+    gemm_tc<BN, EPI><<<grid, kThreads, C::kSmemBytes, stream>>>(ta, tb, g);
+  }
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(ZV_ECUDA, "gemm: launch: %s", cudaGetErrorString(e));

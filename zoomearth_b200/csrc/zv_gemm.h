@@ -29,6 +29,6 @@ int gather_rows(const void* src, int src_dtype, void* dst_bf16, const int32_t* w
                 int cols, void* stream);
 // varlen non-causal attention over q tiles; qkv (S, 3*H) bf16 with rotary already applied
 int attention(const void* qkv, void* out, int heads, int head_dim, const int32_t* tiles_dev, int n_tiles,
-              void* stream);
+              void* stream, bool full_layer = false);
 
 }  // namespace zv

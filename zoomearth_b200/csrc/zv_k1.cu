@@ -259,7 +259,11 @@ int zv_preprocess(const zv_cfg* cfg, int32_t n, const uint8_t* const* src_dev, c
   const int32_t* dcoef = reinterpret_cast<const int32_t*>(ws + L.off_coef);
   const float* dlut = reinterpret_cast<const float*>(ws + L.off_lut);
   const int wsz = cfg->window / cfg->merge / cfg->patch;
-  k1_hpass<<<(unsigned)hblk, 256, 0, stream>>>(dcrops, n, dcoef, ws);
+  {
+    zv::KernelTimer timer(zv::KC_K1_HPASS, stream);
+    k1_hpass<<<(unsigned)hblk, 256, 0, stream>>>(dcrops, n, dcoef, ws);
+  }
+  zv::KernelTimer timer(zv::KC_K1_VPASS, stream);
   if (out_dtype == ZV_BF16)
     k1_vpass<__nv_bfloat16><<<(unsigned)vblk, 256, 0, stream>>>(dcrops, n, dcoef, ws, dlut,
                                                                  static_cast<__nv_bfloat16*>(out_dev), row_order, wsz);

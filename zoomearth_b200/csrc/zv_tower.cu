@@ -173,8 +173,11 @@ int pack_one(const zv_tensor* t, DstT* dst, int64_t rows, int64_t cols, int64_t 
 
 int rmsnorm(const float* x, const float* w, void* y, int64_t rows, int hidden, float eps, void* stream) {
   if (hidden % 4 || hidden > 1280) return fail(ZV_EINVAL, "rmsnorm: hidden=%d unsupported", hidden);
-  rmsnorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, w, static_cast<__nv_bfloat16*>(y), rows, hidden, eps);
+  {
+    KernelTimer timer(KC_RMSNORM, stream);
+    rmsnorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, w, static_cast<__nv_bfloat16*>(y), rows, hidden, eps);
+  }
   count_launch();
   return ZV_OK;
 }
@@ -184,6 +187,7 @@ int gather_rows(const void* src, int src_dtype, void* dst, const int32_t* widx, 
   const int ge = unit * cols;
   if (ge % 4) return fail(ZV_EINVAL, "gather_rows: group size must be a multiple of 4 elements");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  KernelTimer timer(KC_GATHER, stream);
   if (src_dtype == ZV_F32)
     gather_kernel<float><<<(unsigned)n_groups, 256, 0, s>>>(static_cast<const float*>(src), static_cast<__nv_bfloat16*>(dst), widx, ge);
   else
@@ -352,7 +356,7 @@ int zv_visual_forward(const zv_cfg* cfg, const void* weights_dev, const zv_plan*
     g.M = (int)S; g.N = (int)(3 * H); g.K = (int)H; g.out = BIG; g.ldo = 3 * H; g.out_dtype = ZV_BF16;
     g.bias = reinterpret_cast<const float*>(wb + o.bqkv); g.pos = d_pos; g.rope = d_rope; g.heads = cfg->heads;
     ZV_TRY(gemm(EPI_QKV_ROPE, g, Y, H, wb + o.wqkv, H, stream));
-    ZV_TRY(attention(BIG, Y, cfg->heads, (int)(H / cfg->heads), full ? d_full : d_win, full ? p->n_full_tiles : p->n_win_tiles, stream));
+    ZV_TRY(attention(BIG, Y, cfg->heads, (int)(H / cfg->heads), full ? d_full : d_win, full ? p->n_full_tiles : p->n_win_tiles, stream, full));
     g = GemmArgs{};
     g.M = (int)S; g.N = (int)H; g.K = (int)H; g.out = X; g.ldo = H; g.out_dtype = ZV_F32;
     g.bias = reinterpret_cast<const float*>(wb + o.bo);
