@@ -21,7 +21,7 @@ constexpr int HD = 80;          // head dim
 constexpr int BQ = 64, BKV = 64;
 constexpr int LDS = 88;         // smem row pitch in elements (176 B: conflict-free ldmatrix)
 constexpr int kTileElems = 64 * LDS;
-constexpr int kSmemBytes = 5 * kTileElems * 2;   // Q + 2 x (K, V)
+template <int NW> constexpr int smem_bytes() { return (16 * NW + 4 * 64) * LDS * 2; }   // Q (16*NW rows) + 2 x (K, V)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
@@ -48,20 +48,23 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-// 64 rows x 80 bf16 from global (row pitch ld elements) into a padded smem tile; rows >= n_valid are zeros.
-__device__ __forceinline__ void load_tile(__nv_bfloat16* s, const __nv_bfloat16* g, int64_t ld, int n_valid) {
-  for (int i = threadIdx.x; i < 64 * 10; i += 128) {
+// `rows` x 80 bf16 from global (row pitch ld elements) into a padded smem tile; rows >= n_valid are zeros.
+__device__ __forceinline__ void load_tile(__nv_bfloat16* s, const __nv_bfloat16* g, int64_t ld, int n_valid, int rows) {
+  for (int i = threadIdx.x; i < rows * 10; i += blockDim.x) {
     const int r = i / 10, c = i % 10;
     const bool ok = r < n_valid;
     cp_async16(s + r * LDS + c * 8, g + (int64_t)(ok ? r : 0) * ld + c * 8, ok);
   }
 }
 
-__global__ void __launch_bounds__(128) attn_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+// NW warps per CTA, 16 q rows each: NW = 4 for the window layers (segments <= 64), 8 for the full layers, where
+// the 128-row q tile halves the K/V traffic from L2 per q row.
+template <int NW>
+__global__ void __launch_bounds__(32 * NW) attn_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
                                                    const int4* __restrict__ tiles, int heads, float scale_log2) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_raw);
-  __nv_bfloat16* sK = sQ + kTileElems;          // [2][64][LDS]
+  __nv_bfloat16* sK = sQ + 16 * NW * LDS;       // [2][64][LDS]
   __nv_bfloat16* sV = sK + 2 * kTileElems;      // [2][64][LDS]
   const int4 tl = tiles[blockIdx.x];
   const int q0 = tl.x, q_len = tl.y, seg_b = tl.z, seg_e = tl.w;
@@ -76,9 +79,9 @@ __global__ void __launch_bounds__(128) attn_kernel(const __nv_bfloat16* __restri
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
 
-  load_tile(sQ, gq, ld, q_len);
-  load_tile(sK, gk, ld, min(BKV, kv_len));
-  load_tile(sV, gv, ld, min(BKV, kv_len));
+  load_tile(sQ, gq, ld, q_len, 16 * NW);
+  load_tile(sK, gk, ld, min(BKV, kv_len), BKV);
+  load_tile(sV, gv, ld, min(BKV, kv_len), BKV);
   cp_async_commit();
 
   uint32_t qf[5][4];
@@ -91,8 +94,8 @@ __global__ void __launch_bounds__(128) attn_kernel(const __nv_bfloat16* __restri
     const int buf = j & 1;
     if (j + 1 < n_kv) {            // prefetch the next K/V tile into the other buffer
       const int nv = min(BKV, kv_len - (j + 1) * BKV);
-      load_tile(sK + (buf ^ 1) * kTileElems, gk + (int64_t)(j + 1) * BKV * ld, ld, nv);
-      load_tile(sV + (buf ^ 1) * kTileElems, gv + (int64_t)(j + 1) * BKV * ld, ld, nv);
+      load_tile(sK + (buf ^ 1) * kTileElems, gk + (int64_t)(j + 1) * BKV * ld, ld, nv, BKV);
+      load_tile(sV + (buf ^ 1) * kTileElems, gv + (int64_t)(j + 1) * BKV * ld, ld, nv, BKV);
       cp_async_commit();
       cp_async_wait<1>();
     } else {
@@ -188,26 +191,34 @@ __global__ void __launch_bounds__(128) attn_kernel(const __nv_bfloat16* __restri
   }
 }
 
+template <int NW>
+int launch_attn(const void* qkv, void* out, int heads, const int32_t* tiles_dev, int n_tiles, float scale_log2,
+                void* stream_, int cls) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<NW>());
+    if (e != cudaSuccess) return fail(ZV_ECUDA, "attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)n_tiles, (unsigned)heads);
+  KernelTimer timer(cls, stream_);
+  attn_kernel<NW><<<grid, 32 * NW, smem_bytes<NW>(), static_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), reinterpret_cast<const int4*>(tiles_dev),
+      heads, scale_log2);
+  return ZV_OK;
+}
+
 }  // namespace
 
+// tiles_dev: (q0, q_len, seg_begin, seg_end) work items; q_len <= 64 when !full_layer, <= 128 when full_layer.
 int attention(const void* qkv, void* out, int heads, int head_dim, const int32_t* tiles_dev, int n_tiles, void* stream_,
               bool full_layer) {
   if (head_dim != HD) return fail(ZV_EINVAL, "attention: only head_dim=80 is built (got %d)", head_dim);
   if (n_tiles <= 0) return ZV_OK;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) return fail(ZV_ECUDA, "attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
   const float scale_log2 = (float)(1.4426950408889634 / std::sqrt((double)head_dim));
-  dim3 grid((unsigned)n_tiles, (unsigned)heads);
-  {
-    KernelTimer timer(full_layer ? KC_ATTN_FULL : KC_ATTN_WINDOW, stream_);
-    attn_kernel<<<grid, 128, kSmemBytes, static_cast<cudaStream_t>(stream_)>>>(
-        static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), reinterpret_cast<const int4*>(tiles_dev),
-        heads, scale_log2);
-  }
+  int rc = full_layer ? launch_attn<8>(qkv, out, heads, tiles_dev, n_tiles, scale_log2, stream_, KC_ATTN_FULL)
+                      : launch_attn<4>(qkv, out, heads, tiles_dev, n_tiles, scale_log2, stream_, KC_ATTN_WINDOW);
+  if (rc) return rc;
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(ZV_ECUDA, "attention: launch: %s", cudaGetErrorString(e));

@@ -8,9 +8,9 @@
 //   EPI_GELU     gelu_erf(acc + bias) -> bf16                 merger.mlp.0/1 :138-140
 //   EPI_SCATTER  (acc + bias) -> row scatter[row]             merger.mlp.2 + un-reorder :512-513
 //
-// Structure (one CTA per SM, 256 threads): warp 0 = TMA producer (one elected lane), warp 1 = MMA issuer
+// Structure (one CTA per SM, 384 threads): warp 0 = TMA producer (one elected lane), warp 1 = MMA issuer
 // (one elected lane, tcgen05.mma M=128 x N=BN x K=16 from 128B-swizzled smem tiles), warp 2 = TMEM
-// allocator, warps 4-7 = epilogue (tcgen05.ld, one accumulator row per thread).  Three mbarrier pipelines:
+// allocator, warps 4-11 = epilogue (tcgen05.ld, one accumulator row x half the columns per thread).  Three mbarrier pipelines:
 // smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue, two accumulator stages so the epilogue
 // of tile i overlaps the MMAs of tile i+1), and a static persistent tile schedule (n fastest, so CTAs that run
 // together share the A rows in L2 and the whole B matrix stays L2-resident).
@@ -31,7 +31,7 @@ using namespace ptx;
 namespace {
 
 constexpr int BM = 128, BK = 64, UMMA_K = 16;
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;          // 4 role warps + 8 epilogue warps
 constexpr int kTmemCols = 512;
 
 template <int BN> struct Cfg {
@@ -43,116 +43,168 @@ template <int BN> struct Cfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;   // +1024: manual alignment slack
 };
 
-__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+__device__ __forceinline__ void tmem_ld_x4(uint32_t taddr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
+// 32 consecutive fp32 bias values (warp-uniform address: broadcast loads)
+__device__ __forceinline__ void load_bias32(const float* __restrict__ b, float (&v)[32]) {
+  const float4* p = reinterpret_cast<const float4*>(b);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { const float4 t = __ldg(p + j); v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w; }
+}
 
-// ---- epilogues: one thread = one accumulator row; `taddr` already carries the warp's lane quarter.
-template <int BN, int EPI>
-__device__ __forceinline__ void epilogue_tile(uint32_t taddr, int m_blk, int n_blk, int row_local, const GemmArgs& g) {
+// ---- epilogues.  Eight epilogue warps: lane quarter q = warp & 3 (the TMEM lanes a warp may read), column half
+// h = (warp - 4) >> 2.  One thread = one accumulator row, half of the tile's columns.  `taddr` carries the quarter.
+template <int BN, int EPI, typename WaitFn>
+__device__ __forceinline__ void epilogue_tile(uint32_t taddr, int m_blk, int n_blk, int row_local, int half,
+                                              const GemmArgs& g, WaitFn wait_accumulator) {
   const int row = m_blk * BM + row_local;
   const bool valid = row < g.M;
+  if constexpr (EPI != EPI_RESID) wait_accumulator();
   if constexpr (EPI == EPI_STORE || EPI == EPI_GELU || EPI == EPI_SCATTER || EPI == EPI_RESID) {
+    constexpr int HALF = BN / 2;
     int64_t orow = row;
     if constexpr (EPI == EPI_SCATTER) orow = valid ? (int64_t)__ldg(g.scatter + row) : 0;
+    const int c_begin = half * HALF;
+    float4 xprev[8];
+    if constexpr (EPI == EPI_RESID) {       // residual values of the first chunk: fetched before the accumulator is needed
+      if (valid) {
+        const float4* o = reinterpret_cast<const float4*>(static_cast<const float*>(g.out) + orow * g.ldo + n_blk * BN + c_begin);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xprev[j] = o[j];
+      }
+      wait_accumulator();
+    }
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
+    for (int c = c_begin; c < c_begin + HALF; c += 32) {
       uint32_t r[32];
       __syncwarp();
       tmem_ld_x32(taddr + c, r);
-      tmem_ld_wait();
       const int n0 = n_blk * BN + c;
-      float v[32];
+      float4 xnext[8];
+      if constexpr (EPI == EPI_RESID) {     // prefetch the next chunk's residual while this one is processed
+        if (valid && c + 32 < c_begin + HALF) {
+          const float4* o = reinterpret_cast<const float4*>(static_cast<const float*>(g.out) + orow * g.ldo + n0 + 32);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + (g.bias ? __ldg(g.bias + n0 + j) : 0.0f);
+          for (int j = 0; j < 8; ++j) xnext[j] = o[j];
+        }
+      }
+      float v[32];
+      if (g.bias) load_bias32(g.bias + n0, v);
+      else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(r[j]);
       if constexpr (EPI == EPI_GELU) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
       }
-      if (!valid) continue;
-      if (EPI == EPI_RESID || g.out_dtype == ZV_F32) {
-        float4* o = reinterpret_cast<float4*>(static_cast<float*>(g.out) + orow * g.ldo + n0);
+      if (valid) {
+        if (EPI == EPI_RESID || g.out_dtype == ZV_F32) {
+          float4* o = reinterpret_cast<float4*>(static_cast<float*>(g.out) + orow * g.ldo + n0);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 x = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          if constexpr (EPI == EPI_RESID) {
-            const float4 old = o[j];
-            x.x += old.x; x.y += old.y; x.z += old.z; x.w += old.w;
+          for (int j = 0; j < 8; ++j) {
+            float4 x = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            if constexpr (EPI == EPI_RESID) { x.x += xprev[j].x; x.y += xprev[j].y; x.z += xprev[j].z; x.w += xprev[j].w; }
+            o[j] = x;
           }
-          o[j] = x;
-        }
-      } else {
-        uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(g.out) + orow * g.ldo + n0);
+        } else {
+          uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(g.out) + orow * g.ldo + n0);
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          o[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                            pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+          for (int j = 0; j < 4; ++j)
+            o[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                              pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+        }
+      }
+      if constexpr (EPI == EPI_RESID) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xprev[j] = xnext[j];
       }
     }
   } else if constexpr (EPI == EPI_SWIGLU) {
     static_assert(EPI != EPI_SWIGLU || BN == 256, "SwiGLU tiles hold 128 gate + 128 up columns");
 #pragma unroll 1
-    for (int c = 0; c < 128; c += 32) {
+    for (int c = half * 64; c < half * 64 + 64; c += 32) {
       uint32_t a[32], b[32];
       __syncwarp();
       tmem_ld_x32(taddr + c, a);
       tmem_ld_x32(taddr + 128 + c, b);
+      float bg[32], bu[32];
+      load_bias32(g.bias + (int64_t)n_blk * 256 + c, bg);
+      load_bias32(g.bias + (int64_t)n_blk * 256 + 128 + c, bu);
       tmem_ld_wait();
-      const float* bias = g.bias + (int64_t)n_blk * 256 + c;
       uint32_t o[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const float g0 = __uint_as_float(a[2 * j]) + __ldg(bias + 2 * j), g1 = __uint_as_float(a[2 * j + 1]) + __ldg(bias + 2 * j + 1);
-        const float u0 = __uint_as_float(b[2 * j]) + __ldg(bias + 128 + 2 * j), u1 = __uint_as_float(b[2 * j + 1]) + __ldg(bias + 128 + 2 * j + 1);
+        const float g0 = __uint_as_float(a[2 * j]) + bg[2 * j], g1 = __uint_as_float(a[2 * j + 1]) + bg[2 * j + 1];
+        const float u0 = __uint_as_float(b[2 * j]) + bu[2 * j], u1 = __uint_as_float(b[2 * j + 1]) + bu[2 * j + 1];
         o[j] = pack_bf16(silu(g0) * u0, silu(g1) * u1);
       }
-      if (!valid) continue;
-      uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(g.out) + (int64_t)row * g.ldo + n_blk * 128 + c);
+      if (valid) {
+        uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(g.out) + (int64_t)row * g.ldo + n_blk * 128 + c);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        for (int j = 0; j < 4; ++j) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+      }
     }
   } else if constexpr (EPI == EPI_QKV_ROPE) {
     static_assert(EPI != EPI_QKV_ROPE || BN == 240, "QKV tiles hold three 80-wide heads");
-    int ph = 0, pw = 0;
-    if (valid) { ph = __ldg(g.pos + 2 * row); pw = __ldg(g.pos + 2 * row + 1); }
-    const float2* rope_h = g.rope + (int64_t)ph * 20;
-    const float2* rope_w = g.rope + (int64_t)pw * 20;
+    // Each half owns 20 rotation pairs (d, d+40) of every head: columns [20h, 20h+20) and [40+20h, 40+20h+20).
+    // The angle of pair d is pos_h * f_d for d < 20 and pos_w * f_(d-20) for d >= 20 (emb = cat(rot, rot), HF :485),
+    // so half 0 rotates by the h position and half 1 by the w position.
+    int ps = 0;
+    if (valid) ps = __ldg(g.pos + 2 * row + half);
+    const float2* rope = g.rope + (int64_t)ps * 20;
+    const int d0 = 20 * half;
 #pragma unroll 1
     for (int hh = 0; hh < 3; ++hh) {
-      uint32_t r0[32], r1[32], r2[16];
+      uint32_t lo16[16], lo4[4], hi16[16], hi4[4];
       __syncwarp();
-      tmem_ld_x32(taddr + hh * 80, r0);
-      tmem_ld_x32(taddr + hh * 80 + 32, r1);
-      tmem_ld_x16(taddr + hh * 80 + 64, r2);
+      tmem_ld_x16(taddr + hh * 80 + d0, lo16);
+      tmem_ld_x4(taddr + hh * 80 + d0 + 16, lo4);
+      tmem_ld_x16(taddr + hh * 80 + 40 + d0, hi16);
+      tmem_ld_x4(taddr + hh * 80 + 40 + d0 + 16, hi4);
+      const int n0 = n_blk * 240 + hh * 80 + d0;
+      float lo[20], hi[20];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(g.bias + n0) + j);
+        lo[4 * j] = t.x; lo[4 * j + 1] = t.y; lo[4 * j + 2] = t.z; lo[4 * j + 3] = t.w;
+        const float4 u = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + 40) + j);
+        hi[4 * j] = u.x; hi[4 * j + 1] = u.y; hi[4 * j + 2] = u.z; hi[4 * j + 3] = u.w;
+      }
       tmem_ld_wait();
-      const int n0 = n_blk * 240 + hh * 80;
-      float x[80];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r0[j]) + __ldg(g.bias + n0 + j);
+      for (int j = 0; j < 16; ++j) { lo[j] += __uint_as_float(lo16[j]); hi[j] += __uint_as_float(hi16[j]); }
 #pragma unroll
-      for (int j = 0; j < 32; ++j) x[32 + j] = __uint_as_float(r1[j]) + __ldg(g.bias + n0 + 32 + j);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) x[64 + j] = __uint_as_float(r2[j]) + __ldg(g.bias + n0 + 64 + j);
+      for (int j = 0; j < 4; ++j) { lo[16 + j] += __uint_as_float(lo4[j]); hi[16 + j] += __uint_as_float(hi4[j]); }
       const int head = n_blk * 3 + hh;          // 0..47: q heads, then k heads, then v heads
       if (head < 2 * g.heads) {
-        // rotate_half pairs (d, d+40); angle index d<20 -> h position, 20<=d<40 -> w position (emb = cat(rot, rot))
 #pragma unroll
-        for (int d = 0; d < 40; ++d) {
-          const float2 cs = d < 20 ? __ldg(rope_h + d) : __ldg(rope_w + (d - 20));
-          const float lo = x[d], hi = x[d + 40];
-          x[d] = lo * cs.x - hi * cs.y;
-          x[d + 40] = hi * cs.x + lo * cs.y;
+        for (int d = 0; d < 20; ++d) {
+          const float2 cs = __ldg(rope + d);
+          const float l = lo[d], h = hi[d];
+          lo[d] = l * cs.x - h * cs.y;           // x*cos + rotate_half(x)*sin, rotate_half = (-x[40:], x[:40])
+          hi[d] = h * cs.x + l * cs.y;
         }
       }
-      if (!valid) continue;
-      uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(g.out) + (int64_t)row * g.ldo + n0);
+      if (valid) {
+        __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(g.out) + (int64_t)row * g.ldo + n0;   // 8-byte aligned
 #pragma unroll
-      for (int j = 0; j < 10; ++j)
-        dst[j] = make_uint4(pack_bf16(x[8 * j], x[8 * j + 1]), pack_bf16(x[8 * j + 2], x[8 * j + 3]),
-                            pack_bf16(x[8 * j + 4], x[8 * j + 5]), pack_bf16(x[8 * j + 6], x[8 * j + 7]));
+        for (int j = 0; j < 5; ++j) {
+          *reinterpret_cast<uint2*>(dst + 4 * j) = make_uint2(pack_bf16(lo[4 * j], lo[4 * j + 1]), pack_bf16(lo[4 * j + 2], lo[4 * j + 3]));
+          *reinterpret_cast<uint2*>(dst + 40 + 4 * j) = make_uint2(pack_bf16(hi[4 * j], hi[4 * j + 1]), pack_bf16(hi[4 * j + 2], hi[4 * j + 3]));
+        }
+      }
     }
   }
 }
@@ -180,7 +232,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc(const __grid_constant__ C
     prefetch_tensormap(&tma_a);
     prefetch_tensormap(&tma_b);
     for (int s = 0; s < C::kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 8); }
     fence_mbar_init();
   }
   if (warp == 2) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
@@ -230,16 +282,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc(const __grid_constant__ C
       }
     }
   } else if (warp >= 4) {
-    const int q = warp & 3;
+    const int q = warp & 3, half = (warp - 4) >> 2;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(tfull + acc, acc_phase);
-      tc_fence_after();
       const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
-      epilogue_tile<BN, EPI>(taddr, m_blk, n_blk, q * 32 + lane, g);
+      epilogue_tile<BN, EPI>(taddr, m_blk, n_blk, q * 32 + lane, half, g, [&] {
+        mbar_wait(tfull + acc, acc_phase);
+        tc_fence_after();
+      });
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty + acc);

@@ -304,17 +304,17 @@ int zv_plan_create(const zv_cfg* cfg, int32_t n, const int64_t* grid, zv_plan** 
   for (int64_t i = 0; i < p->T; ++i) p->reverse_index[p->window_index[i]] = i;
 
   // attention work items: q tiles of <= 64 rows inside one segment: (q0, q_len, seg_begin, seg_end)
-  auto tiles = [](const std::vector<int32_t>& cu, std::vector<int32_t>* out_tiles) {
+  auto tiles = [](const std::vector<int32_t>& cu, int32_t bq, std::vector<int32_t>* out_tiles) {
     for (size_t s = 0; s + 1 < cu.size(); ++s)
-      for (int32_t q0 = cu[s]; q0 < cu[s + 1]; q0 += 64) {
+      for (int32_t q0 = cu[s]; q0 < cu[s + 1]; q0 += bq) {
         out_tiles->push_back(q0);
-        out_tiles->push_back(std::min(64, cu[s + 1] - q0));
+        out_tiles->push_back(std::min(bq, cu[s + 1] - q0));
         out_tiles->push_back(cu[s]);
         out_tiles->push_back(cu[s + 1]);
       }
   };
-  tiles(p->cu_window, &p->win_tiles);
-  tiles(p->cu_full, &p->full_tiles);
+  tiles(p->cu_window, 64, &p->win_tiles);      // windows hold <= 64 patches: one 64-row q tile each
+  tiles(p->cu_full, 128, &p->full_tiles);      // whole-image segments: 128-row q tiles (zv_attn.cu, 8 warps)
   p->n_win_tiles = (int32_t)(p->win_tiles.size() / 4);
   p->n_full_tiles = (int32_t)(p->full_tiles.size() / 4);
 

@@ -399,16 +399,20 @@ int zv_attention(const void* qkv_dev, void* out_dev, int32_t heads, int32_t head
   int rc = check_device("zv_attention");
   if (rc) return rc;
   std::vector<int32_t> tiles;
+  int32_t longest = 0;
+  for (int32_t s = 0; s < n_seg; ++s) longest = std::max(longest, cu_host[s + 1] - cu_host[s]);
+  const bool full = longest > 64;                 // same choice the tower makes: 128-row q tiles for long segments
+  const int32_t bq = full ? 128 : 64;
   for (int32_t s = 0; s < n_seg; ++s)
-    for (int32_t q0 = cu_host[s]; q0 < cu_host[s + 1]; q0 += 64) {
-      tiles.push_back(q0); tiles.push_back(std::min(64, cu_host[s + 1] - q0));
+    for (int32_t q0 = cu_host[s]; q0 < cu_host[s + 1]; q0 += bq) {
+      tiles.push_back(q0); tiles.push_back(std::min(bq, cu_host[s + 1] - q0));
       tiles.push_back(cu_host[s]); tiles.push_back(cu_host[s + 1]);
     }
   const int64_t need = (int64_t)tiles.size() * 4;
   if (work_bytes < need) return fail(ZV_ENOMEM, "zv_attention: work buffer %lld B < required %lld B", (long long)work_bytes, (long long)need);
   cudaError_t e = cudaMemcpyAsync(work_dev, tiles.data(), (size_t)need, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return fail(ZV_ECUDA, "zv_attention: %s", cudaGetErrorString(e));
-  return attention(qkv_dev, out_dev, heads, head_dim, static_cast<const int32_t*>(work_dev), (int)(tiles.size() / 4), stream);
+  return attention(qkv_dev, out_dev, heads, head_dim, static_cast<const int32_t*>(work_dev), (int)(tiles.size() / 4), stream, full);
 }
 
 }  // extern "C"
