@@ -46,7 +46,7 @@ typedef enum zv_err {
   ZV_EARCH = -7          /* device is not sm_100 */
 } zv_err;
 
-enum { ZV_F32 = 0, ZV_BF16 = 1 };          /* element types at the boundary */
+enum { ZV_F32 = 0, ZV_BF16 = 1, ZV_F16 = 2 };   /* element types at the boundary */
 enum { ZV_ORDER_HF = 0, ZV_ORDER_WINDOW = 1 }; /* patch row order: HF merge-group raster, or tower window order */
 
 /* Processor + model constants (defaults = Qwen2.5-VL-3B vision config + OPENAI_CLIP statistics). */
@@ -62,7 +62,7 @@ typedef struct zv_cfg {
   int32_t inter;        /* 3420 */
   int32_t out_hidden;   /* 2048 */
   int32_t fullatt_mask_lo; /* bit l set = block l uses full attention (blocks 0..31) */
-  int32_t reserved;
+  int32_t op_dtype;     /* GEMM / attention operand type: 0 or ZV_BF16 = bf16 (default), ZV_F16 = fp16 */
   int64_t min_pixels;   /* 3136 */
   int64_t max_pixels;   /* per call site */
   double  rescale;      /* 1/255 */
@@ -164,11 +164,11 @@ ZV_API int zv_gemm_bf16(const void* a_dev, int64_t lda, const void* b_dev, int64
 ZV_API int zv_gemm_ex(int32_t epilogue, const void* a_dev, int64_t lda, const void* b_dev, int64_t ldb,
                       const float* bias_dev, void* out_dev, int64_t ldo, int32_t out_dtype, int64_t m, int64_t n,
                       int64_t k, const int32_t* pos_dev, const float* rope_dev, const int32_t* scatter_dev,
-                      int32_t heads, void* stream);
+                      int32_t heads, int32_t op_dtype /* ZV_BF16 or ZV_F16 operands */, void* stream);
 /* Standalone varlen attention (rotated q,k already in qkv): qkv (S, 3*hidden) bf16 -> out (S, hidden) bf16. */
 ZV_API int zv_attention(const void* qkv_dev, void* out_dev, int32_t heads, int32_t head_dim,
                         const int32_t* cu_seqlens_host, int32_t n_seg, void* work_dev, int64_t work_bytes,
-                        void* stream);
+                        int32_t dtype /* ZV_BF16 or ZV_F16 */, void* stream);
 
 #ifdef __cplusplus
 }

@@ -17,14 +17,17 @@ def _mk(m, n, k, dev, seed=0, scale=1.0):
     return a, b, bias
 
 
+_ZT = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+
+
 def _run(lib, epi, a, b, bias, out, m, n, k, pos=None, rope=None, scatter=None, heads=16, lda=None, ldb=None):
     from zoomearth_b200 import _lib
     stream = torch.cuda.current_stream().cuda_stream
-    dt = _lib.ZV_BF16 if out.dtype == torch.bfloat16 else _lib.ZV_F32
+    dt = _ZT[out.dtype]
     _lib.check(lib.zv_gemm_ex(epi, a.data_ptr(), lda or a.stride(0), b.data_ptr(), ldb or b.stride(0),
                               None if bias is None else bias.data_ptr(), out.data_ptr(), out.stride(0), dt, m, n, k,
                               None if pos is None else pos.data_ptr(), None if rope is None else rope.data_ptr(),
-                              None if scatter is None else scatter.data_ptr(), heads, stream))
+                              None if scatter is None else scatter.data_ptr(), heads, _ZT[a.dtype], stream))
     torch.cuda.synchronize()
 
 
@@ -115,3 +118,14 @@ def test_gemm_qkv_rope(cuda, lib):
         return t * emb.cos() + r * emb.sin()
     ref = torch.stack([rope_fn(y[:, 0]), rope_fn(y[:, 1]), y[:, 2]], 1).reshape(m, n)
     _close(out, ref, 6e-3)
+
+
+def test_gemm_fp16_operands(cuda, lib):
+    m, n, k = 300, 512, 1280
+    g = torch.Generator().manual_seed(12)
+    a = torch.randn(m, k, generator=g).to(torch.float16).to(cuda)
+    b = (torch.randn(n, k, generator=g) * 0.05).to(torch.float16).to(cuda)
+    bias = torch.randn(n, generator=g).to(cuda)
+    out = torch.zeros((m, n), dtype=torch.float16, device=cuda)
+    _run(lib, 0, a, b, bias, out, m, n, k)
+    _close(out, a.float() @ b.float().t() + bias, 1.5e-3)

@@ -65,6 +65,15 @@ def test_k1_bf16_window_order_matches_oracle_cast(cuda):
     assert torch.equal(pv.cpu(), ref_w)
 
 
+def test_k1_fp16_output(cuda):
+    from zoomearth_b200 import FusedImageProcessor
+    img = _img(6, 600, 600)
+    fp = FusedImageProcessor(min_pixels=3136, max_pixels=200704, device=cuda)
+    pv, grid, _ = fp.preprocess_crops([torch.from_numpy(img).to(cuda)], None, torch.float16)
+    ref, _ = _oracle_crop(img, (0, 0, 600, 600), 3136, 200704)
+    assert torch.equal(pv.cpu(), torch.from_numpy(ref).to(torch.float16))
+
+
 def test_k1_ragged_batch_and_cut_image(cuda):
     """A ragged batch through the reference's cut_image rule (min 512) equals the per-crop oracle."""
     from zoomearth_b200 import FusedImageProcessor

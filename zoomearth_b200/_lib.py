@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libzoomvit.so")
 
-ZV_F32, ZV_BF16 = 0, 1
+ZV_F32, ZV_BF16, ZV_F16 = 0, 1, 2
 ORDER_HF, ORDER_WINDOW = 0, 1
 ZV_EINVAL, ZV_EINVAL_ASPECT, ZV_EINVAL_BOX, ZV_ENOMEM, ZV_ECUDA, ZV_ENODEV, ZV_EARCH = -1, -2, -3, -4, -5, -6, -7
 
@@ -18,7 +18,7 @@ class ZvCfg(C.Structure):
     _fields_ = [
         ("patch", C.c_int32), ("merge", C.c_int32), ("temporal", C.c_int32), ("window", C.c_int32),
         ("min_size", C.c_int32), ("depth", C.c_int32), ("hidden", C.c_int32), ("heads", C.c_int32),
-        ("inter", C.c_int32), ("out_hidden", C.c_int32), ("fullatt_mask_lo", C.c_int32), ("reserved", C.c_int32),
+        ("inter", C.c_int32), ("out_hidden", C.c_int32), ("fullatt_mask_lo", C.c_int32), ("op_dtype", C.c_int32),
         ("min_pixels", C.c_int64), ("max_pixels", C.c_int64), ("rescale", C.c_double),
         ("mean", C.c_float * 3), ("std", C.c_float * 3), ("eps", C.c_float), ("reserved_f", C.c_float),
     ]
@@ -76,9 +76,9 @@ _PROTOS = {
                                C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]),
     "zv_gemm_ex": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
                              C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
-                             C.c_void_p]),
+                             C.c_int32, C.c_void_p]),
     "zv_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
-                               C.c_int64, C.c_void_p]),
+                               C.c_int64, C.c_int32, C.c_void_p]),
 }
 EXPORTS = tuple(_PROTOS)
 _lib = None

@@ -7,6 +7,7 @@
 // already applied to q,k by the QKV GEMM epilogue (zv_gemm.cu EPI_QKV_ROPE).
 // Layout: qkv (S, 3, heads, 80) bf16, out (S, heads*80) bf16.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -38,12 +39,20 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* p) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
 }
-__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+template <bool F16>
+__device__ __forceinline__ void mma_16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if constexpr (F16)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_16(float a, float b) {
+  if constexpr (F16) { __half2 v = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&v); }
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
@@ -59,7 +68,7 @@ __device__ __forceinline__ void load_tile(__nv_bfloat16* s, const __nv_bfloat16*
 
 // NW warps per CTA, 16 q rows each: NW = 4 for the window layers (segments <= 64), 8 for the full layers, where
 // the 128-row q tile halves the K/V traffic from L2 per q row.
-template <int NW>
+template <int NW, bool F16>
 __global__ void __launch_bounds__(32 * NW) attn_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
                                                    const int4* __restrict__ tiles, int heads, float scale_log2) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -121,8 +130,8 @@ __global__ void __launch_bounds__(32 * NW) attn_kernel(const __nv_bfloat16* __re
         uint32_t b[4];
         const int mi = lane >> 3, r = lane & 7;
         ldsm_x4(b, k + (16 * np + (mi >> 1) * 8 + r) * LDS + 16 * ks + (mi & 1) * 8);
-        mma_bf16(s[2 * np], qf[ks], b[0], b[1]);
-        mma_bf16(s[2 * np + 1], qf[ks], b[2], b[3]);
+        mma_16<F16>(s[2 * np], qf[ks], b[0], b[1]);
+        mma_16<F16>(s[2 * np + 1], qf[ks], b[2], b[3]);
       }
     }
     // mask columns beyond the segment, online softmax (rows g and g+8 of this warp's 16)
@@ -156,17 +165,17 @@ __global__ void __launch_bounds__(32 * NW) attn_kernel(const __nv_bfloat16* __re
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
       uint32_t a[4];
-      a[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
-      a[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
-      a[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-      a[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+      a[0] = pack_16<F16>(s[2 * kk][0], s[2 * kk][1]);
+      a[1] = pack_16<F16>(s[2 * kk][2], s[2 * kk][3]);
+      a[2] = pack_16<F16>(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      a[3] = pack_16<F16>(s[2 * kk + 1][2], s[2 * kk + 1][3]);
 #pragma unroll
       for (int np = 0; np < 5; ++np) {
         uint32_t b[4];
         const int mi = lane >> 3, r = lane & 7;
         ldsm_x4_trans(b, v + (16 * kk + (mi & 1) * 8 + r) * LDS + 8 * (2 * np + (mi >> 1)));
-        mma_bf16(o[2 * np], a, b[0], b[1]);
-        mma_bf16(o[2 * np + 1], a, b[2], b[3]);
+        mma_16<F16>(o[2 * np], a, b[0], b[1]);
+        mma_16<F16>(o[2 * np + 1], a, b[2], b[3]);
       }
     }
     __syncthreads();   // everyone is done with buffer `buf` before iteration j+1 prefetches into it
@@ -178,8 +187,8 @@ __global__ void __launch_bounds__(32 * NW) attn_kernel(const __nv_bfloat16* __re
   __nv_bfloat16* so = sQ + 16 * warp * LDS;
 #pragma unroll
   for (int i = 0; i < 10; ++i) {
-    *reinterpret_cast<uint32_t*>(so + g * LDS + 8 * i + 2 * t) = pack_bf16(o[i][0] * i0, o[i][1] * i0);
-    *reinterpret_cast<uint32_t*>(so + (g + 8) * LDS + 8 * i + 2 * t) = pack_bf16(o[i][2] * i1, o[i][3] * i1);
+    *reinterpret_cast<uint32_t*>(so + g * LDS + 8 * i + 2 * t) = pack_16<F16>(o[i][0] * i0, o[i][1] * i0);
+    *reinterpret_cast<uint32_t*>(so + (g + 8) * LDS + 8 * i + 2 * t) = pack_16<F16>(o[i][2] * i1, o[i][3] * i1);
   }
   __syncwarp();
   for (int i = lane; i < 16 * 10; i += 32) {
@@ -191,18 +200,18 @@ __global__ void __launch_bounds__(32 * NW) attn_kernel(const __nv_bfloat16* __re
   }
 }
 
-template <int NW>
+template <int NW, bool F16>
 int launch_attn(const void* qkv, void* out, int heads, const int32_t* tiles_dev, int n_tiles, float scale_log2,
                 void* stream_, int cls) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<NW>());
+    cudaError_t e = cudaFuncSetAttribute(attn_kernel<NW, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<NW>());
     if (e != cudaSuccess) return fail(ZV_ECUDA, "attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
   dim3 grid((unsigned)n_tiles, (unsigned)heads);
   KernelTimer timer(cls, stream_);
-  attn_kernel<NW><<<grid, 32 * NW, smem_bytes<NW>(), static_cast<cudaStream_t>(stream_)>>>(
+  attn_kernel<NW, F16><<<grid, 32 * NW, smem_bytes<NW>(), static_cast<cudaStream_t>(stream_)>>>(
       static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), reinterpret_cast<const int4*>(tiles_dev),
       heads, scale_log2);
   return ZV_OK;
@@ -212,12 +221,17 @@ int launch_attn(const void* qkv, void* out, int heads, const int32_t* tiles_dev,
 
 // tiles_dev: (q0, q_len, seg_begin, seg_end) work items; q_len <= 64 when !full_layer, <= 128 when full_layer.
 int attention(const void* qkv, void* out, int heads, int head_dim, const int32_t* tiles_dev, int n_tiles, void* stream_,
-              bool full_layer) {
+              bool full_layer, bool f16) {
   if (head_dim != HD) return fail(ZV_EINVAL, "attention: only head_dim=80 is built (got %d)", head_dim);
   if (n_tiles <= 0) return ZV_OK;
   const float scale_log2 = (float)(1.4426950408889634 / std::sqrt((double)head_dim));
-  int rc = full_layer ? launch_attn<8>(qkv, out, heads, tiles_dev, n_tiles, scale_log2, stream_, KC_ATTN_FULL)
-                      : launch_attn<4>(qkv, out, heads, tiles_dev, n_tiles, scale_log2, stream_, KC_ATTN_WINDOW);
+  int rc;
+  if (f16)
+    rc = full_layer ? launch_attn<8, true>(qkv, out, heads, tiles_dev, n_tiles, scale_log2, stream_, KC_ATTN_FULL)
+                    : launch_attn<4, true>(qkv, out, heads, tiles_dev, n_tiles, scale_log2, stream_, KC_ATTN_WINDOW);
+  else
+    rc = full_layer ? launch_attn<8, false>(qkv, out, heads, tiles_dev, n_tiles, scale_log2, stream_, KC_ATTN_FULL)
+                    : launch_attn<4, false>(qkv, out, heads, tiles_dev, n_tiles, scale_log2, stream_, KC_ATTN_WINDOW);
   if (rc) return rc;
   count_launch();
   cudaError_t e = cudaGetLastError();

@@ -16,6 +16,7 @@
 // together share the A rows in L2 and the whole B matrix stays L2-resident).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <mutex>
@@ -45,13 +46,16 @@ template <int BN> struct Cfg {
 
 __device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+// two fp32 -> packed 16-bit pair, bf16 or fp16 (warp-uniform choice)
+__device__ __forceinline__ uint32_t pack2(float a, float b, bool f16) {
+  if (f16) { __half2 v = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&v); }
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ void tmem_ld_x4(uint32_t taddr, uint32_t (&r)[4]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr) : "memory");
 }
 // 32 consecutive fp32 bias values (warp-uniform address: broadcast loads)
 __device__ __forceinline__ void load_bias32(const float* __restrict__ b, float (&v)[32]) {
@@ -67,6 +71,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int m_blk, int n_b
                                               const GemmArgs& g, WaitFn wait_accumulator) {
   const int row = m_blk * BM + row_local;
   const bool valid = row < g.M;
+  const bool of16 = g.out_dtype == ZV_F16;
   if constexpr (EPI != EPI_RESID) wait_accumulator();
   if constexpr (EPI == EPI_STORE || EPI == EPI_GELU || EPI == EPI_SCATTER || EPI == EPI_RESID) {
     constexpr int HALF = BN / 2;
@@ -122,8 +127,8 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int m_blk, int n_b
           uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(g.out) + orow * g.ldo + n0);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            o[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                              pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+            o[j] = make_uint4(pack2(v[8 * j], v[8 * j + 1], of16), pack2(v[8 * j + 2], v[8 * j + 3], of16),
+                              pack2(v[8 * j + 4], v[8 * j + 5], of16), pack2(v[8 * j + 6], v[8 * j + 7], of16));
         }
       }
       if constexpr (EPI == EPI_RESID) {
@@ -148,7 +153,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int m_blk, int n_b
       for (int j = 0; j < 16; ++j) {
         const float g0 = __uint_as_float(a[2 * j]) + bg[2 * j], g1 = __uint_as_float(a[2 * j + 1]) + bg[2 * j + 1];
         const float u0 = __uint_as_float(b[2 * j]) + bu[2 * j], u1 = __uint_as_float(b[2 * j + 1]) + bu[2 * j + 1];
-        o[j] = pack_bf16(silu(g0) * u0, silu(g1) * u1);
+        o[j] = pack2(silu(g0) * u0, silu(g1) * u1, of16);
       }
       if (valid) {
         uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(g.out) + (int64_t)row * g.ldo + n_blk * 128 + c);
@@ -158,51 +163,96 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int m_blk, int n_b
     }
   } else if constexpr (EPI == EPI_QKV_ROPE) {
     static_assert(EPI != EPI_QKV_ROPE || BN == 240, "QKV tiles hold three 80-wide heads");
-    // Each half owns 20 rotation pairs (d, d+40) of every head: columns [20h, 20h+20) and [40+20h, 40+20h+20).
-    // The angle of pair d is pos_h * f_d for d < 20 and pos_w * f_(d-20) for d >= 20 (emb = cat(rot, rot), HF :485),
-    // so half 0 rotates by the h position and half 1 by the w position.
-    int ps = 0;
-    if (valid) ps = __ldg(g.pos + 2 * row + half);
-    const float2* rope = g.rope + (int64_t)ps * 20;
-    const int d0 = 20 * half;
+    // The two halves split the 40 rotation pairs (d, d+40) of every head 24 : 16, so that every store stays a
+    // 16-byte store: half 0 owns columns [0,24) and [40,64), half 1 owns [24,40) and [64,80).
+    // Angle of pair d: pos_h * f_d for d < 20, pos_w * f_(d-20) for d >= 20 (emb = cat(rot, rot), HF :485).
+    int ph = 0, pw = 0;
+    if (valid) { ph = __ldg(g.pos + 2 * row); pw = __ldg(g.pos + 2 * row + 1); }
+    const float2* rope_h = g.rope + (int64_t)ph * 20;
+    const float2* rope_w = g.rope + (int64_t)pw * 20;
+    const bool rot_heads_possible = n_blk * 3 < 2 * g.heads;
+    if (half == 0) {
+      constexpr int NP = 24;
 #pragma unroll 1
-    for (int hh = 0; hh < 3; ++hh) {
-      uint32_t lo16[16], lo4[4], hi16[16], hi4[4];
-      __syncwarp();
-      tmem_ld_x16(taddr + hh * 80 + d0, lo16);
-      tmem_ld_x4(taddr + hh * 80 + d0 + 16, lo4);
-      tmem_ld_x16(taddr + hh * 80 + 40 + d0, hi16);
-      tmem_ld_x4(taddr + hh * 80 + 40 + d0 + 16, hi4);
-      const int n0 = n_blk * 240 + hh * 80 + d0;
-      float lo[20], hi[20];
+      for (int hh = 0; hh < 3; ++hh) {
+        uint32_t l16[16], l8[8], h16[16], h8[8];
+        __syncwarp();
+        tmem_ld_x16(taddr + hh * 80, l16);
+        tmem_ld_x8(taddr + hh * 80 + 16, l8);
+        tmem_ld_x16(taddr + hh * 80 + 40, h16);
+        tmem_ld_x8(taddr + hh * 80 + 56, h8);
+        const int n0 = n_blk * 240 + hh * 80;
+        float lo[NP], hi[NP];
 #pragma unroll
-      for (int j = 0; j < 5; ++j) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(g.bias + n0) + j);
-        lo[4 * j] = t.x; lo[4 * j + 1] = t.y; lo[4 * j + 2] = t.z; lo[4 * j + 3] = t.w;
-        const float4 u = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + 40) + j);
-        hi[4 * j] = u.x; hi[4 * j + 1] = u.y; hi[4 * j + 2] = u.z; hi[4 * j + 3] = u.w;
-      }
-      tmem_ld_wait();
+        for (int j = 0; j < NP / 4; ++j) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(g.bias + n0) + j);
+          lo[4 * j] = t.x; lo[4 * j + 1] = t.y; lo[4 * j + 2] = t.z; lo[4 * j + 3] = t.w;
+          const float4 u = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + 40) + j);
+          hi[4 * j] = u.x; hi[4 * j + 1] = u.y; hi[4 * j + 2] = u.z; hi[4 * j + 3] = u.w;
+        }
+        tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 16; ++j) { lo[j] += __uint_as_float(lo16[j]); hi[j] += __uint_as_float(hi16[j]); }
+        for (int j = 0; j < 16; ++j) { lo[j] += __uint_as_float(l16[j]); hi[j] += __uint_as_float(h16[j]); }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { lo[16 + j] += __uint_as_float(lo4[j]); hi[16 + j] += __uint_as_float(hi4[j]); }
-      const int head = n_blk * 3 + hh;          // 0..47: q heads, then k heads, then v heads
-      if (head < 2 * g.heads) {
+        for (int j = 0; j < 8; ++j) { lo[16 + j] += __uint_as_float(l8[j]); hi[16 + j] += __uint_as_float(h8[j]); }
+        if (rot_heads_possible && n_blk * 3 + hh < 2 * g.heads) {
 #pragma unroll
-        for (int d = 0; d < 20; ++d) {
-          const float2 cs = __ldg(rope + d);
-          const float l = lo[d], h = hi[d];
-          lo[d] = l * cs.x - h * cs.y;           // x*cos + rotate_half(x)*sin, rotate_half = (-x[40:], x[:40])
-          hi[d] = h * cs.x + l * cs.y;
+          for (int d = 0; d < NP; ++d) {
+            const float2 cs = d < 20 ? __ldg(rope_h + d) : __ldg(rope_w + (d - 20));
+            const float l = lo[d], h = hi[d];
+            lo[d] = l * cs.x - h * cs.y;         // x*cos + rotate_half(x)*sin, rotate_half = (-x[40:], x[:40])
+            hi[d] = h * cs.x + l * cs.y;
+          }
+        }
+        if (valid) {
+          __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(g.out) + (int64_t)row * g.ldo + n0;
+#pragma unroll
+          for (int j = 0; j < NP / 8; ++j) {
+            *reinterpret_cast<uint4*>(dst + 8 * j) = make_uint4(pack2(lo[8 * j], lo[8 * j + 1], of16), pack2(lo[8 * j + 2], lo[8 * j + 3], of16),
+                                                                pack2(lo[8 * j + 4], lo[8 * j + 5], of16), pack2(lo[8 * j + 6], lo[8 * j + 7], of16));
+            *reinterpret_cast<uint4*>(dst + 40 + 8 * j) = make_uint4(pack2(hi[8 * j], hi[8 * j + 1], of16), pack2(hi[8 * j + 2], hi[8 * j + 3], of16),
+                                                                     pack2(hi[8 * j + 4], hi[8 * j + 5], of16), pack2(hi[8 * j + 6], hi[8 * j + 7], of16));
+          }
         }
       }
-      if (valid) {
-        __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(g.out) + (int64_t)row * g.ldo + n0;   // 8-byte aligned
+    } else {
+      constexpr int NP = 16;
+#pragma unroll 1
+      for (int hh = 0; hh < 3; ++hh) {
+        uint32_t l16[16], h16[16];
+        __syncwarp();
+        tmem_ld_x16(taddr + hh * 80 + 24, l16);
+        tmem_ld_x16(taddr + hh * 80 + 64, h16);
+        const int n0 = n_blk * 240 + hh * 80 + 24;
+        float lo[NP], hi[NP];
 #pragma unroll
-        for (int j = 0; j < 5; ++j) {
-          *reinterpret_cast<uint2*>(dst + 4 * j) = make_uint2(pack_bf16(lo[4 * j], lo[4 * j + 1]), pack_bf16(lo[4 * j + 2], lo[4 * j + 3]));
-          *reinterpret_cast<uint2*>(dst + 40 + 4 * j) = make_uint2(pack_bf16(hi[4 * j], hi[4 * j + 1]), pack_bf16(hi[4 * j + 2], hi[4 * j + 3]));
+        for (int j = 0; j < NP / 4; ++j) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(g.bias + n0) + j);
+          lo[4 * j] = t.x; lo[4 * j + 1] = t.y; lo[4 * j + 2] = t.z; lo[4 * j + 3] = t.w;
+          const float4 u = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + 40) + j);
+          hi[4 * j] = u.x; hi[4 * j + 1] = u.y; hi[4 * j + 2] = u.z; hi[4 * j + 3] = u.w;
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { lo[j] += __uint_as_float(l16[j]); hi[j] += __uint_as_float(h16[j]); }
+        if (rot_heads_possible && n_blk * 3 + hh < 2 * g.heads) {
+#pragma unroll
+          for (int d = 0; d < NP; ++d) {
+            const float2 cs = __ldg(rope_w + (d + 4));       // pair index 24 + d -> w angle index 4 + d
+            const float l = lo[d], h = hi[d];
+            lo[d] = l * cs.x - h * cs.y;
+            hi[d] = h * cs.x + l * cs.y;
+          }
+        }
+        if (valid) {
+          __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(g.out) + (int64_t)row * g.ldo + n0;
+#pragma unroll
+          for (int j = 0; j < NP / 8; ++j) {
+            *reinterpret_cast<uint4*>(dst + 8 * j) = make_uint4(pack2(lo[8 * j], lo[8 * j + 1], of16), pack2(lo[8 * j + 2], lo[8 * j + 3], of16),
+                                                                pack2(lo[8 * j + 4], lo[8 * j + 5], of16), pack2(lo[8 * j + 6], lo[8 * j + 7], of16));
+            *reinterpret_cast<uint4*>(dst + 40 + 8 * j) = make_uint4(pack2(hi[8 * j], hi[8 * j + 1], of16), pack2(hi[8 * j + 2], hi[8 * j + 3], of16),
+                                                                     pack2(hi[8 * j + 4], hi[8 * j + 5], of16), pack2(hi[8 * j + 6], hi[8 * j + 7], of16));
+          }
         }
       }
     }
@@ -258,7 +308,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc(const __grid_constant__ C
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      const uint32_t idesc = umma_idesc_16bit(BM, BN, g.op_f16 != 0);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -322,7 +372,7 @@ EncodeTiledFn encode_fn() {
 }
 
 // 2-D bf16 tensor (rows, cols) with row pitch `ld` elements; box = 64 columns x box_rows, 128B swizzle, OOB = 0.
-int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool f16) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(ZV_ECUDA, "gemm: cuTensorMapEncodeTiled is not available from the driver");
   if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * 2) % 16)
@@ -331,7 +381,7 @@ int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
   cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = fn(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(ZV_ECUDA, "gemm: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -353,9 +403,9 @@ int launch(const GemmArgs& g, const void* a, int64_t lda, const void* b, int64_t
   using C = Cfg<BN>;
   if (g.N % BN) return fail(ZV_EINVAL, "gemm: N=%d is not a multiple of the %d-wide tile", g.N, BN);
   CUtensorMap ta, tb;
-  int rc = make_tmap(&ta, a, g.M, g.K, lda, BM);
+  int rc = make_tmap(&ta, a, g.M, g.K, lda, BM, g.op_f16 != 0);
   if (rc) return rc;
-  rc = make_tmap(&tb, b, g.N, g.K, ldb, BN);
+  rc = make_tmap(&tb, b, g.N, g.K, ldb, BN, g.op_f16 != 0);
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
@@ -411,13 +461,14 @@ extern "C" int zv_gemm_bf16(const void* a_dev, int64_t lda, const void* b_dev, i
 extern "C" int zv_gemm_ex(int32_t epilogue, const void* a_dev, int64_t lda, const void* b_dev, int64_t ldb,
                           const float* bias_dev, void* out_dev, int64_t ldo, int32_t out_dtype, int64_t m, int64_t n,
                           int64_t k, const int32_t* pos_dev, const float* rope_dev, const int32_t* scatter_dev,
-                          int32_t heads, void* stream) {
+                          int32_t heads, int32_t op_dtype, void* stream) {
   zv::reset_launch_count();
   if (!a_dev || !b_dev || !out_dev) return zv::fail(ZV_EINVAL, "zv_gemm_ex: null pointer");
   zv::GemmArgs g{};
   g.M = (int)m; g.N = (int)n; g.K = (int)k;
   g.out = out_dev; g.ldo = ldo; g.out_dtype = out_dtype; g.bias = bias_dev;
   g.pos = pos_dev; g.rope = reinterpret_cast<const float2*>(rope_dev); g.scatter = scatter_dev; g.heads = heads;
+  g.op_f16 = op_dtype == ZV_F16;
   if (epilogue != zv::EPI_STORE && !bias_dev) return zv::fail(ZV_EINVAL, "zv_gemm_ex: this epilogue needs a bias");
   if (epilogue == zv::EPI_QKV_ROPE && (!pos_dev || !rope_dev)) return zv::fail(ZV_EINVAL, "zv_gemm_ex: rope tables missing");
   if (epilogue == zv::EPI_SCATTER && !scatter_dev) return zv::fail(ZV_EINVAL, "zv_gemm_ex: scatter index missing");

@@ -9,7 +9,8 @@ enum GemmEpilogue { EPI_STORE = 0, EPI_QKV_ROPE = 1, EPI_RESID = 2, EPI_SWIGLU =
 
 struct GemmArgs {
   int M, N, K;
-  int out_dtype;            // ZV_F32 / ZV_BF16 (EPI_STORE, EPI_SCATTER); others are fixed
+  int out_dtype;            // ZV_F32 / ZV_BF16 / ZV_F16 element type of `out` (EPI_RESID is always fp32)
+  int op_f16;               // operands A, B are fp16 (else bf16)
   void* out;
   int64_t ldo;              // output row pitch in elements
   const float* bias;        // [N] (EPI_SWIGLU: packed like the weight rows); may be null for EPI_STORE
@@ -23,12 +24,12 @@ struct GemmArgs {
 int gemm(int epi, const GemmArgs& g, const void* a, int64_t lda, const void* b, int64_t ldb, void* stream);
 
 // fp32 (S, H) -> bf16 (S, H): y = w * (x * rsqrt(mean(x^2) + eps))   (HF Qwen2_5_VLRMSNorm :66-71)
-int rmsnorm(const float* x, const float* w, void* y_bf16, int64_t rows, int hidden, float eps, void* stream);
+int rmsnorm(const float* x, const float* w, void* y, int y_f16, int64_t rows, int hidden, float eps, void* stream);
 // patches in HF order (f32 or bf16) -> bf16 in window order (groups of `unit` rows move together)
-int gather_rows(const void* src, int src_dtype, void* dst_bf16, const int32_t* widx, int64_t n_groups, int unit,
+int gather_rows(const void* src, int src_dtype, void* dst, int dst_f16, const int32_t* widx, int64_t n_groups, int unit,
                 int cols, void* stream);
 // varlen non-causal attention over q tiles; qkv (S, 3*H) bf16 with rotary already applied
 int attention(const void* qkv, void* out, int heads, int head_dim, const int32_t* tiles_dev, int n_tiles,
-              void* stream, bool full_layer = false);
+              void* stream, bool full_layer = false, bool f16 = false);
 
 }  // namespace zv

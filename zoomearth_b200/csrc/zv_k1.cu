@@ -12,11 +12,13 @@
 // Integer arithmetic only: int32 accumulators, 22-bit fixed-point taps computed on the host in fp64
 // (zv_host.cpp) - results are bit-identical to Pillow.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
 #include <cstring>
 #include <map>
+#include <type_traits>
 #include <vector>
 
 #include "zv_common.h"
@@ -124,7 +126,9 @@ __global__ void __launch_bounds__(256) k1_vpass(const K1Crop* __restrict__ crops
     const int j = (yl / 14) * 2 + (xl / 14);
     const int e = j * kPatchElems + ch * 392 + (yl % 14) * 14 + (xl % 14);
     OutT o;
-    if constexpr (sizeof(OutT) == 2) o = __float2bfloat16_rn(v); else o = v;
+    if constexpr (std::is_same<OutT, __nv_bfloat16>::value) o = __float2bfloat16_rn(v);
+    else if constexpr (std::is_same<OutT, __half>::value) o = __float2half_rn(v);
+    else o = v;
     stage[e] = o;            // temporal frame 0
     stage[e + 196] = o;      // temporal frame 1 = the repeated frame (HF :189-193)
   }
@@ -213,7 +217,7 @@ int zv_preprocess(const zv_cfg* cfg, int32_t n, const uint8_t* const* src_dev, c
     return zv::fail(ZV_EINVAL, "zv_preprocess: null argument");
   if (cfg->patch != 14 || cfg->merge != 2 || cfg->temporal != 2)
     return zv::fail(ZV_EINVAL, "zv_preprocess: only patch=14, merge=2, temporal=2 is built");
-  if (out_dtype != ZV_F32 && out_dtype != ZV_BF16) return zv::fail(ZV_EINVAL, "zv_preprocess: bad out_dtype");
+  if (out_dtype != ZV_F32 && out_dtype != ZV_BF16 && out_dtype != ZV_F16) return zv::fail(ZV_EINVAL, "zv_preprocess: bad out_dtype");
   if (row_order != ZV_ORDER_HF && row_order != ZV_ORDER_WINDOW) return zv::fail(ZV_EINVAL, "zv_preprocess: bad row_order");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return zv::fail(ZV_ENODEV, "zv_preprocess: no CUDA device");
@@ -267,6 +271,8 @@ int zv_preprocess(const zv_cfg* cfg, int32_t n, const uint8_t* const* src_dev, c
   if (out_dtype == ZV_BF16)
     k1_vpass<__nv_bfloat16><<<(unsigned)vblk, 256, 0, stream>>>(dcrops, n, dcoef, ws, dlut,
                                                                  static_cast<__nv_bfloat16*>(out_dev), row_order, wsz);
+  else if (out_dtype == ZV_F16)
+    k1_vpass<__half><<<(unsigned)vblk, 256, 0, stream>>>(dcrops, n, dcoef, ws, dlut, static_cast<__half*>(out_dev), row_order, wsz);
   else
     k1_vpass<float><<<(unsigned)vblk, 256, 0, stream>>>(dcrops, n, dcoef, ws, dlut, static_cast<float*>(out_dev),
                                                          row_order, wsz);

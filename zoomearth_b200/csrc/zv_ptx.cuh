@@ -124,10 +124,11 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// Instruction descriptor, kind::f16: D fp32 (bits 4-5 = 1), A,B bf16 (bits 7-9, 10-12 = 1), both K-major,
+// Instruction descriptor, kind::f16: D fp32 (bits 4-5 = 1), A,B bf16 or fp16 (bits 7-9, 10-12), both K-major,
 // N >> 3 in [17,23), M >> 4 in [24,29).
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+__host__ __device__ constexpr uint32_t umma_idesc_16bit(int m, int n, bool f16) {
+  const uint32_t fmt = f16 ? 0u : 1u;     // F16 = 0, BF16 = 1
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 }  // namespace ptx

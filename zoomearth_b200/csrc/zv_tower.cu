@@ -13,12 +13,14 @@
 //                            X += H Wd^T + b                          EPI_RESID
 // Merger (HF :133-146):      Z = rmsnorm(X) viewed (T, 4H); G = gelu(Z W1^T + b); out[widx[i]] = G W2^T + b.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <cmath>
 #include <cstring>
 #include <map>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "zv_common.h"
@@ -29,13 +31,19 @@ namespace {
 
 constexpr int kPatchK = 1176;
 
+__device__ __forceinline__ uint32_t pack2(float a, float b, bool f16) {
+  if (f16) { __half2 v = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&v); }
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
 inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 inline int ipad(const zv_cfg* c) { return (c->inter + 127) / 128 * 128; }
 
 // ------------------------------------------------------------------------------------------------ small kernels
 // One warp per row.  y = w * (x * rsqrt(mean(x^2) + eps)), fp32 math, bf16 out.
 __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                      __nv_bfloat16* __restrict__ y, int64_t rows, int hidden, float eps) {
+                                                      uint16_t* __restrict__ y, bool f16, int64_t rows, int hidden, float eps) {
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -61,27 +69,24 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ 
     const int idx = lane + 32 * i;
     if (idx < nv) {
       const float4 g = __ldg(wr + idx);
-      __nv_bfloat162 a = __floats2bfloat162_rn(g.x * (v[i].x * r), g.y * (v[i].y * r));
-      __nv_bfloat162 b = __floats2bfloat162_rn(g.z * (v[i].z * r), g.w * (v[i].w * r));
-      yr[idx] = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+      yr[idx] = make_uint2(pack2(g.x * (v[i].x * r), g.y * (v[i].y * r), f16), pack2(g.z * (v[i].z * r), g.w * (v[i].w * r), f16));
     }
   }
 }
 
-// dst group i (unit rows x cols, bf16) <- src group widx[i] (f32 or bf16).  One block per group.
+// dst group i (unit rows x cols, 16-bit operand type) <- src group widx[i] (f32, or already the operand type).
 template <typename SrcT>
-__global__ void __launch_bounds__(256) gather_kernel(const SrcT* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+__global__ void __launch_bounds__(256) gather_kernel(const SrcT* __restrict__ src, uint16_t* __restrict__ dst, bool f16,
                                                      const int32_t* __restrict__ widx, int group_elems) {
   const int64_t gi = blockIdx.x;
   const SrcT* s = src + (int64_t)widx[gi] * group_elems;
-  __nv_bfloat16* d = dst + gi * group_elems;
+  uint16_t* d = dst + gi * group_elems;
   for (int i = threadIdx.x * 4; i < group_elems; i += blockDim.x * 4) {
     float f[4];
     if constexpr (sizeof(SrcT) == 4) {
       const float4 t = *reinterpret_cast<const float4*>(s + i);
       f[0] = t.x; f[1] = t.y; f[2] = t.z; f[3] = t.w;
-      __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]), b = __floats2bfloat162_rn(f[2], f[3]);
-      *reinterpret_cast<uint2*>(d + i) = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+      *reinterpret_cast<uint2*>(d + i) = make_uint2(pack2(f[0], f[1], f16), pack2(f[2], f[3], f16));
     } else {
       *reinterpret_cast<uint2*>(d + i) = *reinterpret_cast<const uint2*>(s + i);
     }
@@ -100,8 +105,12 @@ __global__ void pack_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst
   if (mode == 1) dr = (r / 128) * 256 + r % 128;
   if (mode == 2) dr = (r / 128) * 256 + 128 + r % 128;
   float v;
-  if constexpr (sizeof(SrcT) == 4) v = src[i]; else v = __bfloat162float(src[i]);
-  if constexpr (sizeof(DstT) == 4) dst[dr * dst_ld + c] = v; else dst[dr * dst_ld + c] = __float2bfloat16_rn(v);
+  if constexpr (std::is_same<SrcT, float>::value) v = src[i];
+  else if constexpr (std::is_same<SrcT, __half>::value) v = __half2float(src[i]);
+  else v = __bfloat162float(src[i]);
+  if constexpr (std::is_same<DstT, float>::value) dst[dr * dst_ld + c] = v;
+  else if constexpr (std::is_same<DstT, __half>::value) dst[dr * dst_ld + c] = __float2half_rn(v);
+  else dst[dr * dst_ld + c] = __float2bfloat16_rn(v);
 }
 
 // ------------------------------------------------------------------------------------------------ weight layout
@@ -163,6 +172,8 @@ int pack_one(const zv_tensor* t, DstT* dst, int64_t rows, int64_t cols, int64_t 
     pack_kernel<float, DstT><<<blocks, 256, 0, s>>>(static_cast<const float*>(t->data), dst, rows, cols, dst_ld, mode);
   else if (t->dtype == ZV_BF16)
     pack_kernel<__nv_bfloat16, DstT><<<blocks, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(t->data), dst, rows, cols, dst_ld, mode);
+  else if (t->dtype == ZV_F16)
+    pack_kernel<__half, DstT><<<blocks, 256, 0, s>>>(static_cast<const __half*>(t->data), dst, rows, cols, dst_ld, mode);
   else
     return fail(ZV_EINVAL, "zv_weights_pack: %s has unsupported dtype %d", t->name, t->dtype);
   count_launch();
@@ -171,27 +182,27 @@ int pack_one(const zv_tensor* t, DstT* dst, int64_t rows, int64_t cols, int64_t 
 
 }  // namespace
 
-int rmsnorm(const float* x, const float* w, void* y, int64_t rows, int hidden, float eps, void* stream) {
+int rmsnorm(const float* x, const float* w, void* y, int y_f16, int64_t rows, int hidden, float eps, void* stream) {
   if (hidden % 4 || hidden > 1280) return fail(ZV_EINVAL, "rmsnorm: hidden=%d unsupported", hidden);
   {
     KernelTimer timer(KC_RMSNORM, stream);
     rmsnorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, w, static_cast<__nv_bfloat16*>(y), rows, hidden, eps);
+        x, w, static_cast<uint16_t*>(y), y_f16 != 0, rows, hidden, eps);
   }
   count_launch();
   return ZV_OK;
 }
 
-int gather_rows(const void* src, int src_dtype, void* dst, const int32_t* widx, int64_t n_groups, int unit, int cols,
-                void* stream) {
+int gather_rows(const void* src, int src_dtype, void* dst, int dst_f16, const int32_t* widx, int64_t n_groups, int unit,
+                int cols, void* stream) {
   const int ge = unit * cols;
   if (ge % 4) return fail(ZV_EINVAL, "gather_rows: group size must be a multiple of 4 elements");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   KernelTimer timer(KC_GATHER, stream);
   if (src_dtype == ZV_F32)
-    gather_kernel<float><<<(unsigned)n_groups, 256, 0, s>>>(static_cast<const float*>(src), static_cast<__nv_bfloat16*>(dst), widx, ge);
-  else
-    gather_kernel<__nv_bfloat16><<<(unsigned)n_groups, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), widx, ge);
+    gather_kernel<float><<<(unsigned)n_groups, 256, 0, s>>>(static_cast<const float*>(src), static_cast<uint16_t*>(dst), dst_f16 != 0, widx, ge);
+  else   // already the 16-bit operand type: plain row move
+    gather_kernel<uint16_t><<<(unsigned)n_groups, 256, 0, s>>>(static_cast<const uint16_t*>(src), static_cast<uint16_t*>(dst), dst_f16 != 0, widx, ge);
   count_launch();
   return ZV_OK;
 }
@@ -244,11 +255,15 @@ int zv_weights_pack(const zv_cfg* cfg, const zv_tensor* tensors, int32_t n, void
   if (e != cudaSuccess) return fail(ZV_ECUDA, "zv_weights_pack: memset: %s", cudaGetErrorString(e));
   uint8_t* base = static_cast<uint8_t*>(packed_dev);
   const int64_t H = cfg->hidden, I = cfg->inter, IP = ipad(cfg), O = cfg->out_hidden;
+  const bool f16 = cfg->op_dtype == ZV_F16;
 #define ZV_PACK(NAME, TYPE, OFF, ROWS, COLS, LD, MODE)                                                     \
   do {                                                                                                      \
     const zv_tensor* t_ = get(NAME);                                                                        \
     if (!t_) return fail(ZV_EINVAL, "zv_weights_pack: missing tensor %s", std::string(NAME).c_str());      \
-    rc = pack_one<TYPE>(t_, reinterpret_cast<TYPE*>(base + (OFF)), ROWS, COLS, LD, MODE, s);                \
+    if (std::is_same<TYPE, __nv_bfloat16>::value && f16)                                                    \
+      rc = pack_one<__half>(t_, reinterpret_cast<__half*>(base + (OFF)), ROWS, COLS, LD, MODE, s);          \
+    else                                                                                                    \
+      rc = pack_one<TYPE>(t_, reinterpret_cast<TYPE*>(base + (OFF)), ROWS, COLS, LD, MODE, s);              \
     if (rc) return rc;                                                                                      \
   } while (0)
   ZV_PACK("patch_embed.proj.weight", __nv_bfloat16, L.wpe, H, kPatchK, kPatchK, 0);
@@ -312,8 +327,10 @@ int zv_visual_forward(const zv_cfg* cfg, const void* weights_dev, const zv_plan*
   if (rc) return rc;
   if (!weights_dev || !p || !plan_dev || !patches_dev || !merged_out_dev || !workspace_dev)
     return fail(ZV_EINVAL, "zv_visual_forward: null argument");
-  if ((in_dtype != ZV_F32 && in_dtype != ZV_BF16) || (out_dtype != ZV_F32 && out_dtype != ZV_BF16))
-    return fail(ZV_EINVAL, "zv_visual_forward: bad dtype");
+  const int op = cfg->op_dtype == ZV_F16 ? ZV_F16 : ZV_BF16;
+  const int f16 = op == ZV_F16;
+  if ((in_dtype != ZV_F32 && in_dtype != op) || (out_dtype != ZV_F32 && out_dtype != ZV_BF16 && out_dtype != ZV_F16))
+    return fail(ZV_EINVAL, "zv_visual_forward: bad dtype (16-bit patches must be the operand type %s)", f16 ? "fp16" : "bf16");
   rc = check_device("zv_visual_forward");
   if (rc) return rc;
   const int64_t S = p->S, T = p->T, H = cfg->hidden, IP = ipad(cfg), O = cfg->out_hidden;
@@ -338,35 +355,44 @@ int zv_visual_forward(const zv_cfg* cfg, const void* weights_dev, const zv_plan*
   // patches -> bf16, window order
   const void* P = patches_dev;
   if (in_order == ZV_ORDER_HF) {
-    ZV_TRY(gather_rows(patches_dev, in_dtype, ws + W.p, d_widx, T, cfg->merge * cfg->merge, kPatchK, stream));
+    ZV_TRY(gather_rows(patches_dev, in_dtype, ws + W.p, f16, d_widx, T, cfg->merge * cfg->merge, kPatchK, stream));
     P = ws + W.p;
   } else if (in_dtype == ZV_F32) {
-    return fail(ZV_EINVAL, "zv_visual_forward: window-ordered input must be bf16 (the fused zv_preprocess output)");
+    return fail(ZV_EINVAL, "zv_visual_forward: window-ordered input must be the 16-bit operand type (the fused zv_preprocess output)");
   }
   // patch embed (HF :113): X = P Wpe^T, fp32
   GemmArgs g{};
+  g.op_f16 = f16;
   g.M = (int)S; g.N = (int)H; g.K = kPatchK; g.out = X; g.ldo = H; g.out_dtype = ZV_F32; g.bias = nullptr;
   ZV_TRY(gemm(EPI_STORE, g, P, kPatchK, wb + L.wpe, kPatchK, stream));
 
   for (int l = 0; l < cfg->depth; ++l) {
     const LayerOff& o = L.layers[l];
     const bool full = (cfg->fullatt_mask_lo >> l) & 1;
-    ZV_TRY(rmsnorm(X, reinterpret_cast<const float*>(wb + o.n1), Y, S, (int)H, cfg->eps, stream));
+    ZV_TRY(rmsnorm(X, reinterpret_cast<const float*>(wb + o.n1), Y, f16, S, (int)H, cfg->eps, stream));
     g = GemmArgs{};
-    g.M = (int)S; g.N = (int)(3 * H); g.K = (int)H; g.out = BIG; g.ldo = 3 * H; g.out_dtype = ZV_BF16;
+  g.op_f16 = f16;
+    g.op_f16 = f16;
+    g.M = (int)S; g.N = (int)(3 * H); g.K = (int)H; g.out = BIG; g.ldo = 3 * H; g.out_dtype = op;
     g.bias = reinterpret_cast<const float*>(wb + o.bqkv); g.pos = d_pos; g.rope = d_rope; g.heads = cfg->heads;
     ZV_TRY(gemm(EPI_QKV_ROPE, g, Y, H, wb + o.wqkv, H, stream));
-    ZV_TRY(attention(BIG, Y, cfg->heads, (int)(H / cfg->heads), full ? d_full : d_win, full ? p->n_full_tiles : p->n_win_tiles, stream, full));
+    ZV_TRY(attention(BIG, Y, cfg->heads, (int)(H / cfg->heads), full ? d_full : d_win, full ? p->n_full_tiles : p->n_win_tiles, stream, full, f16 != 0));
     g = GemmArgs{};
+  g.op_f16 = f16;
+    g.op_f16 = f16;
     g.M = (int)S; g.N = (int)H; g.K = (int)H; g.out = X; g.ldo = H; g.out_dtype = ZV_F32;
     g.bias = reinterpret_cast<const float*>(wb + o.bo);
     ZV_TRY(gemm(EPI_RESID, g, Y, H, wb + o.wo, H, stream));
-    ZV_TRY(rmsnorm(X, reinterpret_cast<const float*>(wb + o.n2), Y, S, (int)H, cfg->eps, stream));
+    ZV_TRY(rmsnorm(X, reinterpret_cast<const float*>(wb + o.n2), Y, f16, S, (int)H, cfg->eps, stream));
     g = GemmArgs{};
-    g.M = (int)S; g.N = (int)(2 * IP); g.K = (int)H; g.out = BIG; g.ldo = IP; g.out_dtype = ZV_BF16;
+  g.op_f16 = f16;
+    g.op_f16 = f16;
+    g.M = (int)S; g.N = (int)(2 * IP); g.K = (int)H; g.out = BIG; g.ldo = IP; g.out_dtype = op;
     g.bias = reinterpret_cast<const float*>(wb + o.bgu);
     ZV_TRY(gemm(EPI_SWIGLU, g, Y, H, wb + o.wgu, H, stream));
     g = GemmArgs{};
+  g.op_f16 = f16;
+    g.op_f16 = f16;
     g.M = (int)S; g.N = (int)H; g.K = (int)IP; g.out = X; g.ldo = H; g.out_dtype = ZV_F32;
     g.bias = reinterpret_cast<const float*>(wb + o.bd);
     ZV_TRY(gemm(EPI_RESID, g, BIG, IP, wb + o.wd, IP, stream));
@@ -376,12 +402,14 @@ int zv_visual_forward(const zv_cfg* cfg, const void* weights_dev, const zv_plan*
     if (e != cudaSuccess) return fail(ZV_ECUDA, "zv_visual_forward: hidden copy: %s", cudaGetErrorString(e));
   }
   // merger (HF :133-146) + un-reorder (HF :512-513)
-  ZV_TRY(rmsnorm(X, reinterpret_cast<const float*>(wb + L.ln_q), Y, S, (int)H, cfg->eps, stream));
+  ZV_TRY(rmsnorm(X, reinterpret_cast<const float*>(wb + L.ln_q), Y, f16, S, (int)H, cfg->eps, stream));
   g = GemmArgs{};
-  g.M = (int)T; g.N = (int)(4 * H); g.K = (int)(4 * H); g.out = BIG; g.ldo = 4 * H; g.out_dtype = ZV_BF16;
+  g.op_f16 = f16;
+  g.M = (int)T; g.N = (int)(4 * H); g.K = (int)(4 * H); g.out = BIG; g.ldo = 4 * H; g.out_dtype = op;
   g.bias = reinterpret_cast<const float*>(wb + L.b1);
   ZV_TRY(gemm(EPI_GELU, g, Y, 4 * H, wb + L.w1, 4 * H, stream));
   g = GemmArgs{};
+  g.op_f16 = f16;
   g.M = (int)T; g.N = (int)O; g.K = (int)(4 * H); g.out = merged_out_dev; g.ldo = O; g.out_dtype = out_dtype;
   g.bias = reinterpret_cast<const float*>(wb + L.b2); g.scatter = d_widx;
   ZV_TRY(gemm(EPI_SCATTER, g, BIG, 4 * H, wb + L.w2, 4 * H, stream));
@@ -393,7 +421,7 @@ int zv_visual_forward(const zv_cfg* cfg, const void* weights_dev, const zv_plan*
 }
 
 int zv_attention(const void* qkv_dev, void* out_dev, int32_t heads, int32_t head_dim, const int32_t* cu_host,
-                 int32_t n_seg, void* work_dev, int64_t work_bytes, void* stream) {
+                 int32_t n_seg, void* work_dev, int64_t work_bytes, int32_t dtype, void* stream) {
   reset_launch_count();
   if (!qkv_dev || !out_dev || !cu_host || n_seg <= 0 || !work_dev) return fail(ZV_EINVAL, "zv_attention: bad argument");
   int rc = check_device("zv_attention");
@@ -412,7 +440,7 @@ int zv_attention(const void* qkv_dev, void* out_dev, int32_t heads, int32_t head
   if (work_bytes < need) return fail(ZV_ENOMEM, "zv_attention: work buffer %lld B < required %lld B", (long long)work_bytes, (long long)need);
   cudaError_t e = cudaMemcpyAsync(work_dev, tiles.data(), (size_t)need, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return fail(ZV_ECUDA, "zv_attention: %s", cudaGetErrorString(e));
-  return attention(qkv_dev, out_dev, heads, head_dim, static_cast<const int32_t*>(work_dev), (int)(tiles.size() / 4), stream, full);
+  return attention(qkv_dev, out_dev, heads, head_dim, static_cast<const int32_t*>(work_dev), (int)(tiles.size() / 4), stream, full, dtype == ZV_F16);
 }
 
 }  // extern "C"

@@ -173,7 +173,7 @@ class FusedImageProcessor:
         with torch.cuda.device(device):
             _lib.check(lib.zv_preprocess(
                 C.byref(cfg), n, ptrs, img_hw.ctypes.data, pitch.ctypes.data, crop.ctypes.data, rhw.ctypes.data, None,
-                out.data_ptr(), _lib.ZV_BF16 if out_dtype == torch.bfloat16 else _lib.ZV_F32,
+                out.data_ptr(), {torch.float32: _lib.ZV_F32, torch.bfloat16: _lib.ZV_BF16, torch.float16: _lib.ZV_F16}[out_dtype],
                 _lib.ORDER_WINDOW if window_order else _lib.ORDER_HF, ws.data_ptr(), ws.numel(), stream))
         self.last_launches = lib.zv_last_launch_count()
         return out, torch.from_numpy(grid), crop

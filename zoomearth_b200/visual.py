@@ -16,7 +16,7 @@ from torch import nn
 from . import _lib
 from .plan import Plan
 
-_DT = {torch.float32: _lib.ZV_F32, torch.bfloat16: _lib.ZV_BF16}
+_DT = {torch.float32: _lib.ZV_F32, torch.bfloat16: _lib.ZV_BF16, torch.float16: _lib.ZV_F16}
 
 
 def _vision_cfg_from_hf(config):
@@ -27,17 +27,26 @@ def _vision_cfg_from_hf(config):
 
 
 class FusedVisual(nn.Module):
-    def __init__(self, state_dict, device=None, dtype=torch.bfloat16, return_pooling_output=False, **cfg_overrides):
+    def __init__(self, state_dict, device=None, dtype=torch.bfloat16, operand_dtype=None,
+                 return_pooling_output=False, **cfg_overrides):
         """state_dict: HF names relative to the tower (``visual.`` / ``model.visual.`` prefixes are accepted).
-        ``dtype`` is the dtype of the returned embeddings (what callers read as ``visual.dtype``)."""
+        ``dtype`` is the dtype of the returned embeddings (what callers read as ``visual.dtype``).
+        ``operand_dtype`` is the 16-bit type of the GEMM / attention operands: bfloat16 (default) or float16 (the
+        dtype the reference's eval loop loads the model in, src/eval/infer.py:149; 8x smaller rounding error).
+        Default: float16 when ``dtype`` is float16, else bfloat16.  Accumulation and the residual stream are fp32."""
         super().__init__()
         if not torch.cuda.is_available():
             raise RuntimeError("FusedVisual needs a CUDA device (sm_100); there is no CPU fallback")
         self._device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self._dtype = dtype
         if dtype not in _DT:
-            raise ValueError("FusedVisual returns float32 or bfloat16 embeddings")
-        self.cfg = _lib.default_cfg(**cfg_overrides)
+            raise ValueError("FusedVisual returns float32, bfloat16 or float16 embeddings")
+        if operand_dtype is None:
+            operand_dtype = torch.float16 if dtype == torch.float16 else torch.bfloat16
+        if operand_dtype not in (torch.bfloat16, torch.float16):
+            raise ValueError("operand_dtype must be torch.bfloat16 or torch.float16")
+        self.operand_dtype = operand_dtype
+        self.cfg = _lib.default_cfg(op_dtype=_DT[operand_dtype], **cfg_overrides)
         self.spatial_merge_size = self.cfg.merge
         self.patch_size = self.cfg.patch
         self.spatial_merge_unit = self.cfg.merge ** 2
@@ -53,6 +62,7 @@ class FusedVisual(nn.Module):
         cfg = _vision_cfg_from_hf(hf_visual.config)
         kw.setdefault("dtype", torch.bfloat16)
         return cls(hf_visual.state_dict(), **cfg, **kw)
+
 
     def _pack(self, state_dict):
         lib = _lib.lib()
@@ -125,7 +135,9 @@ class FusedVisual(nn.Module):
         x = hidden_states
         if x.device != self._device:
             x = x.to(self._device, non_blocking=True)
-        if x.dtype not in _DT:
+        if x.dtype not in _DT or (x.dtype != torch.float32 and x.dtype != self.operand_dtype):
+            if window_order:
+                raise ValueError(f"window-ordered patches must be {self.operand_dtype} (the fused preprocess output)")
             x = x.float()
         x = x.contiguous()
         if x.shape != (plan.num_patches, 1176):

@@ -34,7 +34,7 @@ class ZoomEncoder:
         """images_dev: resident images; boxes (n, 4) in image pixels (None = global view of every image).
         Returns (embeddings (T, out_hidden), image_grid_thw (n, 3), crop boxes (n, 4))."""
         pv, grid, crop = self.processor.preprocess_crops(
-            images_dev, boxes, out_dtype=torch.bfloat16, window_order=True, image_index=image_index,
+            images_dev, boxes, out_dtype=self.visual.operand_dtype, window_order=True, image_index=image_index,
             apply_cut_image=apply_cut_image and boxes is not None)
         k1 = self.processor.last_launches
         emb = self.visual(pv, grid, window_order=True)
