@@ -16,7 +16,7 @@ def test_attention_vs_sdpa(cuda, lib, segs, dtype):
     qkv = torch.randn(S, 3, heads, hd, generator=g).to(dtype).to(cuda)
     out = torch.full((S, heads * hd), float("nan"), dtype=dtype, device=cuda)
     cu = np.concatenate([[0], np.cumsum(segs)]).astype(np.int32)
-    work = torch.empty(16 * (S // 64 + len(segs) + 1) * 4, dtype=torch.uint8, device=cuda)
+    work = torch.empty(16 * (S // 64 + len(segs) + 1) * 4 + 4096 + (S + 8) * heads * hd * 2, dtype=torch.uint8, device=cuda)
     _lib.check(lib.zv_attention(qkv.data_ptr(), out.data_ptr(), heads, hd, cu.ctypes.data, len(segs), work.data_ptr(),
                                 work.numel(), 2 if dtype == torch.float16 else 1, torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()

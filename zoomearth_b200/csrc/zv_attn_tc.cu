@@ -1,0 +1,316 @@
+// K4: tcgen05 flash attention for the full-attention layers (whole-image segments; HF modeling_qwen2_5_vl.py
+// :207-287 with cu_seqlens, blocks 7/15/23/31).  One CTA = one 128-row q tile of one head; K/V stream through a
+// 3-stage TMA ring in 64-row tiles.
+//   S_j = Q K_j^T   tcgen05.mma M=128 N=64, K = 80 = 4 x 16 (128B-swizzled [rows][64] block) + 16 (32B-swizzled
+//                   [rows][16] block), accumulator in TMEM (two S buffers: QK_{j+1} is issued while tile j is in softmax)
+//   softmax         four warps, one thread per q row: tcgen05.ld of the row, online max/sum in fp32 with exp2,
+//                   P_j rounded to 16 bit and written to shared memory in the 128B-swizzled K-major layout
+//   O_j = P_j V_j   tcgen05.mma M=128 N=80 K=64 from P (smem) and V^T (smem, kv contiguous: V is pre-transposed per
+//                   head by transpose_v so that the B operand is K-major); O_j is read back from TMEM and folded into
+//                   the fp32 register accumulator with the rescale factor of its tile.
+// Warp roles (192 threads): warp 0 = TMA producer + TMEM allocator, warp 1 = MMA issuer, warps 2-5 = softmax
+// (TMEM lane quarters 2,3,0,1).  Rotary is already applied to q,k by the QKV GEMM epilogue.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+
+#include "zv_common.h"
+#include "zv_gemm.h"
+#include "zv_ptx.cuh"
+
+namespace zv {
+using namespace ptx;
+namespace {
+
+constexpr int HD = 80, BQ = 128, BKV = 64, STAGES = 3;
+constexpr int kQ64 = BQ * 64 * 2, kQ16 = BQ * 16 * 2;                   // 16384, 4096
+constexpr int kK64 = BKV * 64 * 2, kK16 = BKV * 16 * 2, kVt = HD * BKV * 2;   // 8192, 2048, 10240
+constexpr int kStage = kK64 + kK16 + kVt;                                // 20480
+constexpr int kP = BQ * BKV * 2;                                         // 16384
+constexpr int kOffQ16 = kQ64, kOffStage = kQ64 + kQ16, kOffP = kOffStage + STAGES * kStage, kOffBar = kOffP + kP;
+constexpr int kSmem = kOffBar + 256 + 1024;
+constexpr int kTmemCols = 256;                                           // S0 [0,64) S1 [64,128) O [128,208)
+constexpr int kThreads = 192;
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint32_t pack2(float a, float b, bool f16) {
+  if (f16) { __half2 v = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&v); }
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+struct AttnArgs {
+  void* out;
+  const int4* tiles;
+  int heads, hidden, f16;
+  float scale_log2;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qk64,
+                                                              const __grid_constant__ CUtensorMap tm_qk16,
+                                                              const __grid_constant__ CUtensorMap tm_vt, const AttnArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* q_full = bars;             // 1
+  uint64_t* k_full = bars + 1;         // STAGES
+  uint64_t* v_full = bars + 4;
+  uint64_t* k_empty = bars + 7;
+  uint64_t* v_empty = bars + 10;
+  uint64_t* s_full = bars + 13;        // 2
+  uint64_t* s_empty = bars + 15;       // 2
+  uint64_t* p_full = bars + 17;
+  uint64_t* pv_done = bars + 18;
+  uint64_t* o_empty = bars + 19;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+  const int4 tl = a.tiles[blockIdx.x];
+  const int q0 = tl.x, q_len = tl.y, seg_b = tl.z, seg_e = tl.w;
+  const int head = blockIdx.y;
+  const int kv_len = seg_e - seg_b;
+  const int n_kv = (kv_len + BKV - 1) / BKV;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tm_qk64); prefetch_tensormap(&tm_qk16); prefetch_tensormap(&tm_vt);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(k_full + s, 1); mbar_init(v_full + s, 1); mbar_init(k_empty + s, 1); mbar_init(v_empty + s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(s_full + b, 1); mbar_init(s_empty + b, 4); }
+    mbar_init(p_full, 4); mbar_init(pv_done, 1); mbar_init(o_empty, 4);
+    fence_mbar_init();
+  }
+  if (warp == 0) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // ---- TMA producer: Q once, then the K / V^T ring
+      const int colq = head * HD, colk = a.hidden + head * HD;
+      mbar_arrive_expect_tx(q_full, kQ64 + kQ16);
+      tma_load_2d(smem, &tm_qk64, q_full, colq, q0);
+      tma_load_2d(smem + kQ64 / 2, &tm_qk64, q_full, colq, q0 + 64);
+      tma_load_2d(smem + kOffQ16, &tm_qk16, q_full, colq + 64, q0);
+      tma_load_2d(smem + kOffQ16 + kQ16 / 2, &tm_qk16, q_full, colq + 64, q0 + 64);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j % STAGES;
+        const uint32_t ph = (j / STAGES) & 1;
+        uint8_t* sk = smem + kOffStage + st * kStage;
+        const int row = seg_b + j * BKV;
+        mbar_wait(k_empty + st, ph ^ 1);
+        mbar_arrive_expect_tx(k_full + st, kK64 + kK16);
+        tma_load_2d(sk, &tm_qk64, k_full + st, colk, row);
+        tma_load_2d(sk + kK64, &tm_qk16, k_full + st, colk + 64, row);
+        mbar_wait(v_empty + st, ph ^ 1);
+        mbar_arrive_expect_tx(v_full + st, kVt);
+        tma_load_2d(sk + kK64 + kK16, &tm_vt, v_full + st, row, head * HD);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // ---- MMA issuer
+      const uint32_t idesc_qk = umma_idesc_16bit(BQ, BKV, a.f16 != 0);
+      const uint32_t idesc_pv = umma_idesc_16bit(BQ, HD, a.f16 != 0);
+      const uint32_t sq = smem_u32(smem), sq16 = smem_u32(smem + kOffQ16), sp = smem_u32(smem + kOffP);
+      auto issue_qk = [&](int t) {
+        const int st = t % STAGES;
+        const uint32_t sk = smem_u32(smem + kOffStage + st * kStage);
+        mbar_wait(k_full + st, (t / STAGES) & 1);
+        mbar_wait(s_empty + (t & 1), ((t >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem + (t & 1) * 64;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_bf16(d, umma_desc(sq, 1024, 2) + 2 * ks, umma_desc(sk, 1024, 2) + 2 * ks, idesc_qk, ks != 0);
+        umma_bf16(d, umma_desc(sq16, 256, 6), umma_desc(sk + kK64, 256, 6), idesc_qk, 1);
+        umma_commit(k_empty + st);
+        umma_commit(s_full + (t & 1));
+      };
+      mbar_wait(q_full, 0);
+      issue_qk(0);
+      for (int j = 0; j < n_kv; ++j) {
+        if (j + 1 < n_kv) issue_qk(j + 1);
+        const int st = j % STAGES;
+        const uint32_t sv = smem_u32(smem + kOffStage + st * kStage + kK64 + kK16);
+        mbar_wait(v_full + st, (j / STAGES) & 1);
+        mbar_wait(p_full, j & 1);
+        if (j > 0) mbar_wait(o_empty, (j - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_bf16(tmem + 128, umma_desc(sp, 1024, 2) + 2 * ks, umma_desc(sv, 1024, 2) + 2 * ks, idesc_pv, ks != 0);
+        umma_commit(v_empty + st);
+        umma_commit(pv_done);
+      }
+    }
+  } else {
+    // ---- softmax warps: thread = q row
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const bool f16 = a.f16 != 0;
+    const float sl2 = a.scale_log2;
+    float m = -INFINITY, l = 0.f, corr_pending = 0.f;
+    float o[HD];
+#pragma unroll
+    for (int i = 0; i < HD; ++i) o[i] = 0.f;
+    uint8_t* prow = smem + kOffP + row * 128;
+
+    auto fold_o = [&](float corr) {          // o = o * corr + O_tile (read back from TMEM)
+      uint32_t t0[32], t1[32], t2[16];
+      tmem_ld_x32(tmem + lane_addr + 128, t0);
+      tmem_ld_x32(tmem + lane_addr + 160, t1);
+      tmem_ld_x16(tmem + lane_addr + 192, t2);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) { o[i] = o[i] * corr + __uint_as_float(t0[i]); o[32 + i] = o[32 + i] * corr + __uint_as_float(t1[i]); }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) o[64 + i] = o[64 + i] * corr + __uint_as_float(t2[i]);
+    };
+
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(s_full + (j & 1), (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t r0[32], r1[32];
+      tmem_ld_x32(tmem + lane_addr + (j & 1) * 64, r0);
+      tmem_ld_x32(tmem + lane_addr + (j & 1) * 64 + 32, r1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty + (j & 1));
+      float s[64];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) { s[i] = __uint_as_float(r0[i]); s[32 + i] = __uint_as_float(r1[i]); }
+      const int valid = kv_len - j * BKV;          // columns >= valid belong to the next segment / padding
+      if (valid < BKV) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) if (i >= valid) s[i] = -INFINITY;
+      }
+      float mx = m;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) mx = fmaxf(mx, s[i]);
+      const float corr = exp2f((m - mx) * sl2);
+      const float ms = mx * sl2;
+      m = mx;
+      float rs = 0.f;
+      uint32_t pk[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float p0 = exp2f(s[2 * i] * sl2 - ms), p1 = exp2f(s[2 * i + 1] * sl2 - ms);
+        rs += p0 + p1;
+        pk[i] = pack2(p0, p1, f16);
+      }
+      l = l * corr + rs;
+      if (j > 0) {                                  // O_{j-1} is complete: fold it in, which also frees P and O
+        mbar_wait(pv_done, (j - 1) & 1);
+        tc_fence_after();
+        fold_o(corr_pending);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(o_empty);
+      }
+      corr_pending = corr;
+      // P row -> shared memory, K-major 128B swizzle: 16-byte chunk c of row r lives at chunk (c ^ (r & 7))
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    mbar_wait(pv_done, (n_kv - 1) & 1);
+    tc_fence_after();
+    fold_o(corr_pending);
+    tc_fence_before();
+    if (row < q_len) {
+      const float inv = 1.f / l;
+      uint16_t* dst = static_cast<uint16_t*>(a.out) + (int64_t)(q0 + row) * a.hidden + head * HD;
+#pragma unroll
+      for (int c = 0; c < 10; ++c)
+        *reinterpret_cast<uint4*>(dst + 8 * c) =
+            make_uint4(pack2(o[8 * c] * inv, o[8 * c + 1] * inv, f16), pack2(o[8 * c + 2] * inv, o[8 * c + 3] * inv, f16),
+                       pack2(o[8 * c + 4] * inv, o[8 * c + 5] * inv, f16), pack2(o[8 * c + 6] * inv, o[8 * c + 7] * inv, f16));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, kTmemCols); }
+}
+
+// V heads of qkv (S, 3*hidden), columns [2*hidden, 3*hidden) -> vt [hidden][s_pad] (32x32 tiles through smem)
+__global__ void __launch_bounds__(256) transpose_v_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ vt,
+                                                          int64_t S, int64_t s_pad, int hidden) {
+  __shared__ uint16_t tile[32][34];
+  const int64_t s0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t srow = s0 + r;
+    tile[r][tx] = (srow < S) ? qkv[srow * 3 * hidden + 2 * hidden + c0 + tx] : (uint16_t)0;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t scol = s0 + tx;
+    if (scol < s_pad) vt[(int64_t)(c0 + r) * s_pad + scol] = tile[tx][r];
+  }
+}
+
+}  // namespace
+
+int transpose_v(const void* qkv, void* vt, int64_t S, int64_t s_pad, int heads, int head_dim, void* stream) {
+  const int hidden = heads * head_dim;
+  if (hidden % 32) return fail(ZV_EINVAL, "transpose_v: hidden must be a multiple of 32");
+  dim3 grid((unsigned)((s_pad + 31) / 32), (unsigned)(hidden / 32));
+  KernelTimer timer(KC_ATTN_FULL, stream);
+  transpose_v_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint16_t*>(qkv),
+                                                                          static_cast<uint16_t*>(vt), S, s_pad, hidden);
+  count_launch();
+  return ZV_OK;
+}
+
+int attention_tc(const void* qkv, const void* vt, int64_t s_pad, void* out, int64_t S, int heads, int head_dim,
+                 const int32_t* tiles_dev, int n_tiles, void* stream_, bool f16) {
+  if (head_dim != HD) return fail(ZV_EINVAL, "attention_tc: only head_dim=80 is built (got %d)", head_dim);
+  if (n_tiles <= 0) return ZV_OK;
+  const int hidden = heads * head_dim;
+  CUtensorMap t64, t16, tvt;
+  int rc = make_tmap_2d(&t64, qkv, S, 3 * hidden, 3 * hidden, 64, 64, 128, f16);
+  if (rc) return rc;
+  rc = make_tmap_2d(&t16, qkv, S, 3 * hidden, 3 * hidden, 16, 64, 32, f16);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tvt, vt, hidden, S, s_pad, 64, HD, 128, f16);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (e != cudaSuccess) return fail(ZV_ECUDA, "attention_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  AttnArgs a{};
+  a.out = out; a.tiles = reinterpret_cast<const int4*>(tiles_dev); a.heads = heads; a.hidden = hidden; a.f16 = f16;
+  a.scale_log2 = (float)(1.4426950408889634 / std::sqrt((double)head_dim));
+  dim3 grid((unsigned)n_tiles, (unsigned)heads);
+  {
+    KernelTimer timer(KC_ATTN_FULL, stream_);
+    attn_tc_kernel<<<grid, kThreads, kSmem, static_cast<cudaStream_t>(stream_)>>>(t64, t16, tvt, a);
+  }
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(ZV_ECUDA, "attention_tc: launch: %s", cudaGetErrorString(e));
+  return ZV_OK;
+}
+
+}  // namespace zv

@@ -358,6 +358,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+}  // namespace
+int make_tmap_2d(void* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
+                 int swizzle_bytes, bool f16);
+namespace {
+
 EncodeTiledFn encode_fn() {
   static EncodeTiledFn fn = nullptr;
   static std::once_flag once;
@@ -371,21 +376,8 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// 2-D bf16 tensor (rows, cols) with row pitch `ld` elements; box = 64 columns x box_rows, 128B swizzle, OOB = 0.
 int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool f16) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return fail(ZV_ECUDA, "gemm: cuTensorMapEncodeTiled is not available from the driver");
-  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * 2) % 16)
-    return fail(ZV_EINVAL, "gemm: operand base/pitch must be 16-byte aligned (base %p, ld %lld)", base, (long long)ld);
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(ZV_ECUDA, "gemm: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-  return ZV_OK;
+  return make_tmap_2d(tm, base, rows, cols, ld, BK, box_rows, 128, f16);
 }
 
 int num_sms() {
@@ -426,6 +418,28 @@ int launch(const GemmArgs& g, const void* a, int64_t lda, const void* b, int64_t
 }
 
 }  // namespace
+
+// 2-D 16-bit tensor (rows, cols), row pitch `ld` elements; box = box_cols x box_rows; swizzle 128 or 32 bytes; OOB = 0.
+int make_tmap_2d(void* tm_, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
+                 int swizzle_bytes, bool f16) {
+  CUtensorMap* tm = static_cast<CUtensorMap*>(tm_);
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(ZV_ECUDA, "tma: cuTensorMapEncodeTiled is not available from the driver");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * 2) % 16)
+    return fail(ZV_EINVAL, "tma: operand base/pitch must be 16-byte aligned (base %p, ld %lld)", base, (long long)ld);
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base),
+                  dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ZV_ECUDA, "tma: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return ZV_OK;
+}
 
 int gemm(int epi, const GemmArgs& g, const void* a, int64_t lda, const void* b, int64_t ldb, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);

@@ -23,6 +23,16 @@ struct GemmArgs {
 // C = A[M,K] * B[N,K]^T with the chosen epilogue, enqueued on `stream`.
 int gemm(int epi, const GemmArgs& g, const void* a, int64_t lda, const void* b, int64_t ldb, void* stream);
 
+// cuTensorMapEncodeTiled wrapper (tm points at a CUtensorMap): 16-bit 2-D tensor, box_cols x box_rows box.
+int make_tmap_2d(void* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
+                 int swizzle_bytes, bool f16);
+// tcgen05 flash attention for long segments (zv_attn_tc.cu): qkv (S, 3*H) 16-bit with rotary applied, vt = V
+// transposed per head [(heads*80)][s_pad]; tiles (q0, q_len, seg_begin, seg_end) with q_len <= 128.
+int attention_tc(const void* qkv, const void* vt, int64_t s_pad, void* out, int64_t S, int heads, int head_dim,
+                 const int32_t* tiles_dev, int n_tiles, void* stream, bool f16);
+// V heads of qkv -> vt [(heads*head_dim)][s_pad] (s_pad = S rounded up to 8)
+int transpose_v(const void* qkv, void* vt, int64_t S, int64_t s_pad, int heads, int head_dim, void* stream);
+
 // fp32 (S, H) -> bf16 (S, H): y = w * (x * rsqrt(mean(x^2) + eps))   (HF Qwen2_5_VLRMSNorm :66-71)
 int rmsnorm(const float* x, const float* w, void* y, int y_f16, int64_t rows, int hidden, float eps, void* stream);
 // patches in HF order (f32 or bf16) -> bf16 in window order (groups of `unit` rows move together)
