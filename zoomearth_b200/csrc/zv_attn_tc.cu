@@ -5,9 +5,10 @@
 //                   [rows][16] block), accumulator in TMEM (two S buffers: QK_{j+1} is issued while tile j is in softmax)
 //   softmax         four warps, one thread per q row: tcgen05.ld of the row, online max/sum in fp32 with exp2,
 //                   P_j rounded to 16 bit and written to shared memory in the 128B-swizzled K-major layout
-//   O_j = P_j V_j   tcgen05.mma M=128 N=80 K=64 from P (smem) and V^T (smem, kv contiguous: V is pre-transposed per
-//                   head by transpose_v so that the B operand is K-major); O_j is read back from TMEM and folded into
-//                   the fp32 register accumulator with the rescale factor of its tile.
+//   O += P_j V_j    tcgen05.mma M=128 N=80 K=64 from P (smem) and V^T (smem, kv contiguous: V is pre-transposed per
+//                   head by transpose_v so that the B operand is K-major); O stays in TMEM for the whole segment and
+//                   is rescaled lazily (only when the row max grows by more than 2^8).  Two CTAs fit per SM, so one
+//                   CTA's softmax overlaps the other's MMAs.
 // Warp roles (192 threads): warp 0 = TMA producer + TMEM allocator, warp 1 = MMA issuer, warps 2-5 = softmax
 // (TMEM lane quarters 2,3,0,1).  Rotary is already applied to q,k by the QKV GEMM epilogue.
 #include <cuda.h>
@@ -43,6 +44,15 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t sbo_b
   d |= (uint64_t)layout << 61;
   return d;
 }
+__device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ uint32_t pack2(float a, float b, bool f16) {
   if (f16) { __half2 v = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&v); }
@@ -57,7 +67,7 @@ struct AttnArgs {
   float scale_log2;
 };
 
-__global__ void __launch_bounds__(kThreads, 1) attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qk64,
+__global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qk64,
                                                               const __grid_constant__ CUtensorMap tm_qk16,
                                                               const __grid_constant__ CUtensorMap tm_vt, const AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -72,14 +82,15 @@ __global__ void __launch_bounds__(kThreads, 1) attn_tc_kernel(const __grid_const
   uint64_t* s_empty = bars + 15;       // 2
   uint64_t* p_full = bars + 17;
   uint64_t* pv_done = bars + 18;
-  uint64_t* o_empty = bars + 19;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int4 tl = a.tiles[blockIdx.x];
   const int q0 = tl.x, q_len = tl.y, seg_b = tl.z, seg_e = tl.w;
   const int head = blockIdx.y;
-  const int kv_len = seg_e - seg_b;
-  const int n_kv = (kv_len + BKV - 1) / BKV;
+  // K/V tiles start at the segment start rounded down to 8 rows: the V^T tile's inner TMA coordinate must be
+  // 16-byte aligned.  Columns before seg_b (first tile) and from seg_e on (last tile) are masked in the softmax.
+  const int kv_base = seg_b & ~7;
+  const int n_kv = (seg_e - kv_base + BKV - 1) / BKV;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -87,7 +98,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_tc_kernel(const __grid_const
     mbar_init(q_full, 1);
     for (int s = 0; s < STAGES; ++s) { mbar_init(k_full + s, 1); mbar_init(v_full + s, 1); mbar_init(k_empty + s, 1); mbar_init(v_empty + s, 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(s_full + b, 1); mbar_init(s_empty + b, 4); }
-    mbar_init(p_full, 4); mbar_init(pv_done, 1); mbar_init(o_empty, 4);
+    mbar_init(p_full, 4); mbar_init(pv_done, 1);
     fence_mbar_init();
   }
   if (warp == 0) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
@@ -109,7 +120,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_tc_kernel(const __grid_const
         const int st = j % STAGES;
         const uint32_t ph = (j / STAGES) & 1;
         uint8_t* sk = smem + kOffStage + st * kStage;
-        const int row = seg_b + j * BKV;
+        const int row = kv_base + j * BKV;
         mbar_wait(k_empty + st, ph ^ 1);
         mbar_arrive_expect_tx(k_full + st, kK64 + kK16);
         tma_load_2d(sk, &tm_qk64, k_full + st, colk, row);
@@ -147,39 +158,26 @@ __global__ void __launch_bounds__(kThreads, 1) attn_tc_kernel(const __grid_const
         const uint32_t sv = smem_u32(smem + kOffStage + st * kStage + kK64 + kK16);
         mbar_wait(v_full + st, (j / STAGES) & 1);
         mbar_wait(p_full, j & 1);
-        if (j > 0) mbar_wait(o_empty, (j - 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
-          umma_bf16(tmem + 128, umma_desc(sp, 1024, 2) + 2 * ks, umma_desc(sv, 1024, 2) + 2 * ks, idesc_pv, ks != 0);
+          umma_bf16(tmem + 128, umma_desc(sp, 1024, 2) + 2 * ks, umma_desc(sv, 1024, 2) + 2 * ks, idesc_pv, (j | ks) != 0);
         umma_commit(v_empty + st);
         umma_commit(pv_done);
       }
     }
   } else {
-    // ---- softmax warps: thread = q row
+    // ---- softmax warps: thread = q row.  O accumulates in TMEM across KV tiles; it is rescaled (tcgen05.ld ->
+    // multiply -> tcgen05.st) only when the running row max grew by more than 2^8 since the scale in use was chosen
+    // ("lazy rescale": P may then exceed 1 by at most 2^8, harmless in fp32 sums and 16-bit P), so the common tile
+    // costs one TMEM row load, 64 exp2 and one 128-byte row store per thread.
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const bool f16 = a.f16 != 0;
     const float sl2 = a.scale_log2;
-    float m = -INFINITY, l = 0.f, corr_pending = 0.f;
-    float o[HD];
-#pragma unroll
-    for (int i = 0; i < HD; ++i) o[i] = 0.f;
+    float m_used = -INFINITY, l = 0.f;      // scale in use (raw score units) and the row sum in that scale
     uint8_t* prow = smem + kOffP + row * 128;
-
-    auto fold_o = [&](float corr) {          // o = o * corr + O_tile (read back from TMEM)
-      uint32_t t0[32], t1[32], t2[16];
-      tmem_ld_x32(tmem + lane_addr + 128, t0);
-      tmem_ld_x32(tmem + lane_addr + 160, t1);
-      tmem_ld_x16(tmem + lane_addr + 192, t2);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) { o[i] = o[i] * corr + __uint_as_float(t0[i]); o[32 + i] = o[32 + i] * corr + __uint_as_float(t1[i]); }
-#pragma unroll
-      for (int i = 0; i < 16; ++i) o[64 + i] = o[64 + i] * corr + __uint_as_float(t2[i]);
-    };
 
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(s_full + (j & 1), (j >> 1) & 1);
@@ -194,17 +192,35 @@ __global__ void __launch_bounds__(kThreads, 1) attn_tc_kernel(const __grid_const
       float s[64];
 #pragma unroll
       for (int i = 0; i < 32; ++i) { s[i] = __uint_as_float(r0[i]); s[32 + i] = __uint_as_float(r1[i]); }
-      const int valid = kv_len - j * BKV;          // columns >= valid belong to the next segment / padding
-      if (valid < BKV) {
+      const int lo = seg_b - (kv_base + j * BKV), hi = seg_e - (kv_base + j * BKV);   // valid columns: [lo, hi)
+      if (lo > 0 || hi < BKV) {
 #pragma unroll
-        for (int i = 0; i < 64; ++i) if (i >= valid) s[i] = -INFINITY;
+        for (int i = 0; i < 64; ++i) if (i < lo || i >= hi) s[i] = -INFINITY;
       }
-      float mx = m;
+      float mx = s[0];
 #pragma unroll
-      for (int i = 0; i < 64; ++i) mx = fmaxf(mx, s[i]);
-      const float corr = exp2f((m - mx) * sl2);
-      const float ms = mx * sl2;
-      m = mx;
+      for (int i = 1; i < 64; ++i) mx = fmaxf(mx, s[i]);
+      const bool grow = (mx - m_used) * sl2 > 8.0f;          // true on the first tile (m_used = -inf)
+      float factor = 1.0f;
+      if (grow) { factor = exp2f((m_used - mx) * sl2); m_used = mx; l *= factor; }
+      if (j > 0) {
+        mbar_wait(pv_done, (j - 1) & 1);                     // P buffer free, O_{j-1} accumulated
+        if (__any_sync(0xffffffffu, grow)) {
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < 80; c += 16) {
+            uint32_t t[16];
+            tmem_ld_x16(tmem + lane_addr + 128 + c, t);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * factor);
+            tmem_st_x16(tmem + lane_addr + 128 + c, t);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+        }
+      }
+      const float ms = m_used * sl2;
       float rs = 0.f;
       uint32_t pk[32];
 #pragma unroll
@@ -213,16 +229,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_tc_kernel(const __grid_const
         rs += p0 + p1;
         pk[i] = pack2(p0, p1, f16);
       }
-      l = l * corr + rs;
-      if (j > 0) {                                  // O_{j-1} is complete: fold it in, which also frees P and O
-        mbar_wait(pv_done, (j - 1) & 1);
-        tc_fence_after();
-        fold_o(corr_pending);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(o_empty);
-      }
-      corr_pending = corr;
+      l += rs;
       // P row -> shared memory, K-major 128B swizzle: 16-byte chunk c of row r lives at chunk (c ^ (r & 7))
 #pragma unroll
       for (int c = 0; c < 8; ++c)
@@ -233,17 +240,24 @@ __global__ void __launch_bounds__(kThreads, 1) attn_tc_kernel(const __grid_const
     }
     mbar_wait(pv_done, (n_kv - 1) & 1);
     tc_fence_after();
-    fold_o(corr_pending);
-    tc_fence_before();
-    if (row < q_len) {
-      const float inv = 1.f / l;
-      uint16_t* dst = static_cast<uint16_t*>(a.out) + (int64_t)(q0 + row) * a.hidden + head * HD;
+    const float inv = 1.f / l;
+    uint16_t* dst = static_cast<uint16_t*>(a.out) + (int64_t)(q0 + row) * a.hidden + head * HD;
 #pragma unroll
-      for (int c = 0; c < 10; ++c)
-        *reinterpret_cast<uint4*>(dst + 8 * c) =
-            make_uint4(pack2(o[8 * c] * inv, o[8 * c + 1] * inv, f16), pack2(o[8 * c + 2] * inv, o[8 * c + 3] * inv, f16),
-                       pack2(o[8 * c + 4] * inv, o[8 * c + 5] * inv, f16), pack2(o[8 * c + 6] * inv, o[8 * c + 7] * inv, f16));
+    for (int c = 0; c < 80; c += 16) {
+      uint32_t t[16];
+      tmem_ld_x16(tmem + lane_addr + 128 + c, t);
+      tmem_ld_wait();
+      if (row < q_len) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          *reinterpret_cast<uint4*>(dst + c + 8 * h) =
+              make_uint4(pack2(__uint_as_float(t[8 * h]) * inv, __uint_as_float(t[8 * h + 1]) * inv, f16),
+                         pack2(__uint_as_float(t[8 * h + 2]) * inv, __uint_as_float(t[8 * h + 3]) * inv, f16),
+                         pack2(__uint_as_float(t[8 * h + 4]) * inv, __uint_as_float(t[8 * h + 5]) * inv, f16),
+                         pack2(__uint_as_float(t[8 * h + 6]) * inv, __uint_as_float(t[8 * h + 7]) * inv, f16));
+      }
     }
+    tc_fence_before();
   }
   tc_fence_before();
   __syncthreads();
