@@ -8,14 +8,28 @@
 //   patchify                     HF models/qwen2_vl/image_processing_pil_qwen2_vl.py:186-214
 //
 // The two resample passes cannot be merged (the intermediate is rounded to uint8), so the data flow is
-//   source u8 (HWC) --hpass--> tmp u8 (rows the vertical pass needs, HWC) --vpass+LUT+permute--> patches.
-// Integer arithmetic only: int32 accumulators, 22-bit fixed-point taps computed on the host in fp64
-// (zv_host.cpp) - results are bit-identical to Pillow.
+//   source u8 (HWC) --hpass--> tmp u8 (only the rows the vertical pass needs) --vpass+LUT+permute--> patches.
+// Integer arithmetic only, bit-identical to Pillow: 22-bit fixed-point taps computed on the host in fp64
+// (zv_host.cpp), int32 sums.
+//
+// Fast path (taps <= 37 per axis, 4-byte aligned image rows): the work is instruction-bound on the integer pipes
+// (4 multiply-adds per source byte), so both passes run on dp4a.  Each 23-bit tap is split into three byte limbs
+// (k = l0 + 256 l1 + 65536 l2, l2 signed); the host emits, per output index, a word-aligned tap window whose limb
+// bytes are packed four taps to a word, so one dp4a does four taps of one limb and no per-thread realignment of the
+// pixels is needed:
+//   hpass_fast  a CTA stages 8 source rows x the span of 128 output columns into shared memory, de-interleaved to
+//               R/G/B planes (coalesced word loads, byte permutes); a thread owns one output column with its limb
+//               words in registers, runs 4 rows x 3 channels, and writes tmp packed 4 rows to a word.
+//   vpass_fast  tmp's row-quad words are directly dp4a operands along y; a warp owns output rows with their limb words
+//               in registers and sweeps the columns coalesced; the CTA assembles two merge groups' patch rows in shared
+//               memory and streams them out with 16-byte stores.
+// Everything else (huge downscales, unaligned pitches) takes the plain per-tap kernels k1_hpass / k1_vpass.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <type_traits>
@@ -27,6 +41,9 @@ namespace {
 
 constexpr int kPrecisionBits = 22;
 constexpr int kPatchElems = 1176;   // 3 * 2 * 14 * 14
+constexpr int kMaxNW = 10;          // fast path: taps <= 4 * kMaxNW - 3 = 37
+constexpr int kHRows = 8;           // hpass_fast: source rows per CTA (two row quads)
+constexpr int kHCols = 128;         // hpass_fast: output columns per CTA
 
 struct K1Crop {
   const uint8_t* src;      // image base (device)
@@ -38,31 +55,63 @@ struct K1Crop {
   int32_t cw, ch;          // crop extent
   int32_t ow, oh;          // resized extent (multiples of 28)
   int32_t ksh, ksv;        // taps per output column / row
-  int32_t ybox0, nrows;    // crop rows [ybox0, ybox0 + nrows) feed the vertical pass
-  int32_t off_bh, off_kh, off_bv, off_kv;  // int32 offsets into the coefficient area
-  int32_t hblk0, vblk0;    // first block of this crop in the hpass / vpass grids
+  int32_t ybox0, nrows;    // crop rows [ybox0, ybox0 + nrows) feed the vertical pass (fast path: ybox0 % 4 == 0)
+  int32_t off_bh, off_kh, off_bv, off_kv;  // int32 offsets into the coefficient area (bounds, taps)
+  int32_t off_lh, off_lv;  // int32 offsets of the dp4a limb tables (fast path)
+  int32_t nwh, nwv;        // words per tap window (fast path), 0 = generic path
   int32_t lh, lw;          // merge-group grid (gh/2, gw/2)
+  int32_t fast;            // 1: tmp is row-quad packed (fast path), 0: plain rows
   int32_t pad_;
 };
 
-__device__ __forceinline__ int find_crop(const K1Crop* crops, int n, int blk, bool vpass) {
+// Block -> (crop, local block) through the launch's own prefix array (crops of one kernel class only).
+__device__ __forceinline__ int find_slot(const int32_t* __restrict__ blk0, int n, int blk) {
   int lo = 0, hi = n - 1;
   while (lo < hi) {
-    int mid = (lo + hi + 1) >> 1;
-    int b0 = vpass ? crops[mid].vblk0 : crops[mid].hblk0;
-    if (b0 <= blk) lo = mid; else hi = mid - 1;
+    const int mid = (lo + hi + 1) >> 1;
+    if (blk0[mid] <= blk) lo = mid; else hi = mid - 1;
   }
   return lo;
 }
 
 __device__ __forceinline__ int clip8(int v) { return min(255, max(0, v)); }
+__device__ __forceinline__ int dp4a_uu(uint32_t a, uint32_t b, int c) {
+  int d;
+  asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {   // a unsigned bytes, b signed bytes
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+// sum_t px_t * k_t from the three limb sums, rounded and clipped like Pillow's 8bpc passes
+__device__ __forceinline__ int finish8(int a0, int a1, int a2) {
+  return clip8((a0 + (a1 << 8) + (a2 << 16) + (1 << (kPrecisionBits - 1))) >> kPrecisionBits);
+}
 
+// Position of merge group (my, mx) in the tower's window order (closed form of argsort(window_index),
+// HF modeling_qwen2_5_vl.py:411-451): windows of ws x ws merge groups, row-major over windows, row-major inside.
+__device__ __forceinline__ int window_pos(int my, int mx, int lh, int lw, int ws) {
+  const int wy = my / ws, wx = mx / ws;
+  const int bh = min(ws, lh - wy * ws), bw = min(ws, lw - wx * ws);
+  return wy * ws * lw + wx * ws * bh + (my - wy * ws) * bw + (mx - wx * ws);
+}
+
+template <typename OutT> __device__ __forceinline__ OutT to_out(float v) {
+  if constexpr (std::is_same<OutT, __nv_bfloat16>::value) return __float2bfloat16_rn(v);
+  else if constexpr (std::is_same<OutT, __half>::value) return __float2half_rn(v);
+  else return v;
+}
+
+// ------------------------------------------------------------------------------------------------ generic path
 // Horizontal pass.  One thread = one (tmp row, output column), all 3 channels.
-__global__ void __launch_bounds__(256) k1_hpass(const K1Crop* __restrict__ crops, int n_crops,
-                                                const int32_t* __restrict__ coef, uint8_t* __restrict__ tmp_base) {
-  const int ci = find_crop(crops, n_crops, blockIdx.x, false);
-  const K1Crop c = crops[ci];
-  const int64_t item = (int64_t)(blockIdx.x - c.hblk0) * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) k1_hpass(const K1Crop* __restrict__ crops, const int32_t* __restrict__ ids,
+                                                const int32_t* __restrict__ blk0, int n_cls,
+                                                const int32_t* __restrict__ coef, uint8_t* __restrict__ ws) {
+  const int slot = find_slot(blk0, n_cls, blockIdx.x);
+  const K1Crop c = crops[ids[slot]];
+  const int64_t item = (int64_t)(blockIdx.x - blk0[slot]) * blockDim.x + threadIdx.x;
   if (item >= (int64_t)c.nrows * c.ow) return;
   const int r = (int)(item / c.ow), xx = (int)(item % c.ow);
   const int y_img = c.y0 + c.ybox0 + r;
@@ -82,36 +131,28 @@ __global__ void __launch_bounds__(256) k1_hpass(const K1Crop* __restrict__ crops
       }
     }
   }
-  uint8_t* o = tmp_base + c.tmp_off + ((int64_t)r * c.ow + xx) * 3;
+  uint8_t* o = ws + c.tmp_off + ((int64_t)r * c.ow + xx) * 3;
   o[0] = (uint8_t)clip8(a0 >> kPrecisionBits);
   o[1] = (uint8_t)clip8(a1 >> kPrecisionBits);
   o[2] = (uint8_t)clip8(a2 >> kPrecisionBits);
 }
 
-// Position of merge group (my, mx) in the tower's window order (closed form of argsort(window_index),
-// HF modeling_qwen2_5_vl.py:411-451): windows of ws x ws merge groups, row-major over windows, row-major inside.
-__device__ __forceinline__ int window_pos(int my, int mx, int lh, int lw, int ws) {
-  const int wy = my / ws, wx = mx / ws;
-  const int bh = min(ws, lh - wy * ws), bw = min(ws, lw - wx * ws);
-  return wy * ws * lw + wx * ws * bh + (my - wy * ws) * bw + (mx - wx * ws);
-}
-
-// Vertical pass + LUT normalise + patchify.  One block = one 2x2 merge group (28 x 28 pixels, 4 patch rows);
-// the block assembles the four 1176-element rows in shared memory and streams them out with 16-byte stores.
+// Vertical pass + LUT normalise + patchify.  One block = one 2x2 merge group (28 x 28 pixels, 4 patch rows).
 template <typename OutT>
-__global__ void __launch_bounds__(256) k1_vpass(const K1Crop* __restrict__ crops, int n_crops,
-                                                const int32_t* __restrict__ coef,
-                                                const uint8_t* __restrict__ tmp_base, const float* __restrict__ lut,
-                                                OutT* __restrict__ out, int row_order, int ws) {
+__global__ void __launch_bounds__(256) k1_vpass(const K1Crop* __restrict__ crops, const int32_t* __restrict__ ids,
+                                                const int32_t* __restrict__ blk0, int n_cls,
+                                                const int32_t* __restrict__ coef, const uint8_t* __restrict__ ws,
+                                                const float* __restrict__ lut, OutT* __restrict__ out, int row_order,
+                                                int wsz) {
   __shared__ __align__(16) OutT stage[4 * kPatchElems];
   __shared__ float s_lut[768];
-  const int ci = find_crop(crops, n_crops, blockIdx.x, true);
-  const K1Crop c = crops[ci];
-  const int g = blockIdx.x - c.vblk0;           // merge group, raster order inside the crop
+  const int slot = find_slot(blk0, n_cls, blockIdx.x);
+  const K1Crop c = crops[ids[slot]];
+  const int g = blockIdx.x - blk0[slot];        // merge group, raster order inside the crop
   const int my = g / c.lw, mx = g % c.lw;
   for (int i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i] = lut[i];
   __syncthreads();
-  const uint8_t* __restrict__ tmp = tmp_base + c.tmp_off;
+  const uint8_t* __restrict__ tmp = ws + c.tmp_off;
   const int64_t tpitch = (int64_t)c.ow * 3;
   for (int item = threadIdx.x; item < 28 * 84; item += blockDim.x) {
     const int yl = item / 84, col = item % 84;             // col = xl * 3 + ch
@@ -125,29 +166,185 @@ __global__ void __launch_bounds__(256) k1_vpass(const K1Crop* __restrict__ crops
     const float v = s_lut[ch * 256 + clip8(acc >> kPrecisionBits)];
     const int j = (yl / 14) * 2 + (xl / 14);
     const int e = j * kPatchElems + ch * 392 + (yl % 14) * 14 + (xl % 14);
-    OutT o;
-    if constexpr (std::is_same<OutT, __nv_bfloat16>::value) o = __float2bfloat16_rn(v);
-    else if constexpr (std::is_same<OutT, __half>::value) o = __float2half_rn(v);
-    else o = v;
+    const OutT o = to_out<OutT>(v);
     stage[e] = o;            // temporal frame 0
     stage[e + 196] = o;      // temporal frame 1 = the repeated frame (HF :189-193)
   }
   __syncthreads();
-  const int pos = row_order == ZV_ORDER_WINDOW ? window_pos(my, mx, c.lh, c.lw, ws) : g;
+  const int pos = row_order == ZV_ORDER_WINDOW ? window_pos(my, mx, c.lh, c.lw, wsz) : g;
   uint4* dst = reinterpret_cast<uint4*>(out + (c.out_row0 + 4 * (int64_t)pos) * kPatchElems);
   const uint4* srcv = reinterpret_cast<const uint4*>(stage);
   constexpr int kVec = 4 * kPatchElems * (int)sizeof(OutT) / 16;
   for (int i = threadIdx.x; i < kVec; i += blockDim.x) dst[i] = srcv[i];
 }
 
-inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+// ------------------------------------------------------------------------------------------------ fast path
+// Limb table of one axis: per output index, (1 + 3 NW) ints: first word of the tap window (in 4-sample words from the
+// axis origin), then NW words of limb 0, NW of limb 1, NW of limb 2 (signed bytes); taps outside the window are 0.
 
+// Horizontal pass on dp4a.  Block = (8 tmp rows) x (128 output columns) of one crop.
+template <int NW>
+__global__ void __launch_bounds__(256) k1_hpass_fast(const K1Crop* __restrict__ crops, const int32_t* __restrict__ ids,
+                                                     const int32_t* __restrict__ blk0, int n_cls,
+                                                     const int32_t* __restrict__ coef, uint8_t* __restrict__ ws,
+                                                     int seg_words_max) {
+  extern __shared__ uint32_t planes[];            // [8 rows][3 planes][seg_words_max]
+  const int slot = find_slot(blk0, n_cls, blockIdx.x);
+  const K1Crop c = crops[ids[slot]];
+  const int local = blockIdx.x - blk0[slot];
+  const int chunks = (c.ow + kHCols - 1) / kHCols;
+  const int strip = local / chunks, chunk = local % chunks;
+  const int xx0 = chunk * kHCols, xx1 = min(c.ow, xx0 + kHCols);
+  const int32_t* __restrict__ lt = coef + c.off_lh;
+  constexpr int kStride = 1 + 3 * NW;
+  const int w_first = lt[(int64_t)xx0 * kStride];                       // window starts are monotone in xx
+  const int seg_words = min(seg_words_max, lt[(int64_t)(xx1 - 1) * kStride] + NW - w_first);
+  const int r0 = strip * kHRows;                                         // first tmp row of the strip
+
+  // ---- stage: 8 rows x seg_words pixel quads, interleaved RGB -> planes, zero outside the image
+  const uintptr_t img_lo = reinterpret_cast<uintptr_t>(c.src);
+  const uintptr_t img_hi = img_lo + (uintptr_t)c.src_h * (uintptr_t)c.pitch;
+  for (int i = threadIdx.x; i < kHRows * seg_words; i += blockDim.x) {
+    const int row = i / seg_words, wq = i - row * seg_words;
+    const int y_img = c.y0 + c.ybox0 + r0 + row;
+    const int x_img = c.x0 + (w_first + wq) * 4;                         // image x of the quad's first pixel
+    uint32_t R = 0, G = 0, B = 0;
+    if (y_img >= 0 && y_img < c.src_h && x_img + 3 >= 0 && x_img < c.src_w) {
+      const int64_t off = (int64_t)y_img * c.pitch + 3 * (int64_t)x_img;  // may be negative (box left of the image)
+      const int64_t base = off & ~(int64_t)3;
+      const uint32_t sh = (uint32_t)(off & 3) * 8;
+      uint32_t w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int64_t a = base + 4 * k;
+        w[k] = (a >= 0 && (uintptr_t)(a + 4) <= img_hi - img_lo) ? __ldg(reinterpret_cast<const uint32_t*>(c.src + a)) : 0u;
+      }
+      const uint32_t v0 = __funnelshift_r(w[0], w[1], sh), v1 = __funnelshift_r(w[1], w[2], sh),
+                     v2 = __funnelshift_r(w[2], w[3], sh);
+      R = __byte_perm(__byte_perm(v0, v1, 0x0630), v2, 0x5210);
+      G = __byte_perm(__byte_perm(v0, v1, 0x0741), v2, 0x6210);
+      B = __byte_perm(__byte_perm(v0, v1, 0x0052), v2, 0x7410);
+      if (x_img < 0 || x_img + 3 >= c.src_w) {                           // quad straddles the image edge
+        uint32_t m = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (x_img + j >= 0 && x_img + j < c.src_w) m |= 0xFFu << (8 * j);
+        R &= m; G &= m; B &= m;
+      }
+    }
+    uint32_t* p = planes + (row * 3) * seg_words_max + wq;
+    p[0] = R; p[seg_words_max] = G; p[2 * seg_words_max] = B;
+  }
+  __syncthreads();
+
+  // ---- compute: thread = (output column, row quad)
+  const int xx = xx0 + (threadIdx.x & (kHCols - 1));
+  const int quad = threadIdx.x >> 7;                                     // 0, 1
+  const int nq = (c.nrows + 3) >> 2;
+  const int q = (r0 >> 2) + quad;
+  if (xx >= xx1 || q >= nq) return;
+  const int32_t* __restrict__ e = lt + (int64_t)xx * kStride;
+  const int w0 = __ldg(e) - w_first;
+  uint32_t l0[NW], l1[NW], l2[NW];
+#pragma unroll
+  for (int k = 0; k < NW; ++k) { l0[k] = __ldg(e + 1 + k); l1[k] = __ldg(e + 1 + NW + k); l2[k] = __ldg(e + 1 + 2 * NW + k); }
+  uint32_t* __restrict__ tmp4 = reinterpret_cast<uint32_t*>(ws + c.tmp_off) + ((int64_t)q * c.ow + xx) * 3;
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    uint32_t packed = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const uint32_t* __restrict__ p = planes + ((quad * 4 + r) * 3 + ch) * seg_words_max + w0;
+      int a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll
+      for (int k = 0; k < NW; ++k) {
+        const uint32_t v = p[k];
+        a0 = dp4a_uu(v, l0[k], a0);
+        a1 = dp4a_uu(v, l1[k], a1);
+        a2 = dp4a_us(v, l2[k], a2);
+      }
+      packed |= (uint32_t)finish8(a0, a1, a2) << (8 * r);
+    }
+    tmp4[ch] = packed;                              // rows 4q..4q+3 of (xx, ch)
+  }
+}
+
+// Vertical pass on dp4a + LUT + patchify.  Block = one merge-group row x two merge groups (28 rows x 56 pixels).
+template <int NW, typename OutT>
+__global__ void __launch_bounds__(256) k1_vpass_fast(const K1Crop* __restrict__ crops, const int32_t* __restrict__ ids,
+                                                     const int32_t* __restrict__ blk0, int n_cls,
+                                                     const int32_t* __restrict__ coef, const uint8_t* __restrict__ ws,
+                                                     const float* __restrict__ lut, OutT* __restrict__ out,
+                                                     int row_order, int wsz) {
+  __shared__ __align__(16) OutT stage[2 * 4 * kPatchElems];
+  __shared__ float s_lut[768];
+  const int slot = find_slot(blk0, n_cls, blockIdx.x);
+  const K1Crop c = crops[ids[slot]];
+  const int local = blockIdx.x - blk0[slot];
+  const int pairs = (c.lw + 1) >> 1;
+  const int my = local / pairs, mx0 = (local % pairs) * 2;
+  const int ngroups = min(2, c.lw - mx0);
+  const int ncols = ngroups * 84;                                        // (pixel, channel) columns of this block
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i] = lut[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t* __restrict__ tmp4 = reinterpret_cast<const uint32_t*>(ws + c.tmp_off) + mx0 * 84;
+  const int64_t qpitch = (int64_t)c.ow * 3;                              // words per row quad
+  constexpr int kStride = 1 + 3 * NW;
+  const int q_origin = c.ybox0 >> 2;                                     // tmp quads are counted from ybox0 (multiple of 4)
+  for (int yl = warp; yl < 28; yl += 8) {
+    const int yy = my * 28 + yl;
+    const int32_t* __restrict__ e = coef + c.off_lv + (int64_t)yy * kStride;
+    const int q0 = __ldg(e) - q_origin;
+    uint32_t l0[NW], l1[NW], l2[NW];
+#pragma unroll
+    for (int k = 0; k < NW; ++k) { l0[k] = __ldg(e + 1 + k); l1[k] = __ldg(e + 1 + NW + k); l2[k] = __ldg(e + 1 + 2 * NW + k); }
+    const uint32_t* __restrict__ base = tmp4 + (int64_t)q0 * qpitch;
+    for (int col = lane; col < ncols; col += 32) {
+      int a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll
+      for (int k = 0; k < NW; ++k) {
+        const uint32_t v = __ldg(base + (int64_t)k * qpitch + col);
+        a0 = dp4a_uu(v, l0[k], a0);
+        a1 = dp4a_uu(v, l1[k], a1);
+        a2 = dp4a_us(v, l2[k], a2);
+      }
+      const int xl = col / 3, ch = col - xl * 3;                         // xl in [0, 56)
+      const float v = s_lut[ch * 256 + finish8(a0, a1, a2)];
+      const int grp = xl / 28, xg = xl - grp * 28;
+      const int j = (yl / 14) * 2 + (xg / 14);
+      const int el = (grp * 4 + j) * kPatchElems + ch * 392 + (yl % 14) * 14 + (xg % 14);
+      const OutT o = to_out<OutT>(v);
+      stage[el] = o;
+      stage[el + 196] = o;
+    }
+  }
+  __syncthreads();
+  constexpr int kVec = 4 * kPatchElems * (int)sizeof(OutT) / 16;
+  for (int gi = 0; gi < ngroups; ++gi) {
+    const int mx = mx0 + gi;
+    const int pos = row_order == ZV_ORDER_WINDOW ? window_pos(my, mx, c.lh, c.lw, wsz) : my * c.lw + mx;
+    uint4* dst = reinterpret_cast<uint4*>(out + (c.out_row0 + 4 * (int64_t)pos) * kPatchElems);
+    const uint4* srcv = reinterpret_cast<const uint4*>(stage + gi * 4 * kPatchElems);
+    for (int i = threadIdx.x; i < kVec; i += blockDim.x) dst[i] = srcv[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+inline int nw_class(int ksize) {                   // words per tap window (<= 3 samples of misalignment + ksize taps)
+  const int need = (ksize + 3 + 3) / 4;
+  for (int c : {2, 3, 4, 5, 7, 10}) if (need <= c) return c;
+  return 0;
+}
+
+struct AxisTables { int32_t off_bounds = 0, off_kk = 0, off_limbs = 0, ksize = 0, nw = 0, seg_words = 0; };
 struct Layout {
-  int64_t off_desc = 0, off_lut = 0, off_coef = 0, off_tmp = 0, bytes = 0;
+  int64_t off_desc = 0, off_lut = 0, off_coef = 0, off_lists = 0, off_tmp = 0, bytes = 0;
   std::vector<int64_t> tmp_off;              // per crop, relative to off_tmp
   std::vector<int32_t> ybox0, nrows;
-  std::map<std::pair<int32_t, int32_t>, std::pair<int32_t, int32_t>> coef_at;  // (in,out) -> (bounds off, kk off)
+  std::map<std::pair<int32_t, int32_t>, AxisTables> axis;   // (in, out) -> table offsets
   std::vector<int32_t> coef;                 // concatenated int32 tables
+  int64_t list_ints = 0;
 };
 
 // Workspace layout shared by zv_preprocess_workspace_bytes and zv_preprocess.
@@ -162,16 +359,47 @@ int build_layout(int32_t n, const int32_t* crop_box, const int32_t* resized_hw, 
                       i, cw, ch, ow, oh);
     const std::pair<int32_t, int32_t> keys[2] = {{cw, ow}, {ch, oh}};
     for (const auto& key : keys) {
-      if (L->coef_at.count(key)) continue;
-      const int32_t ks = zv::resample_ksize(key.first, key.second);
-      L->coef_at[key] = {(int32_t)coef_ints, (int32_t)(coef_ints + 2 * (int64_t)key.second)};
+      if (L->axis.count(key)) continue;
+      AxisTables t;
+      t.ksize = zv::resample_ksize(key.first, key.second);
+      t.nw = nw_class(t.ksize);
+      t.off_bounds = (int32_t)coef_ints;
+      t.off_kk = (int32_t)(coef_ints + 2 * (int64_t)key.second);
+      t.off_limbs = (int32_t)(coef_ints + 2 * (int64_t)key.second + (int64_t)key.second * t.ksize);
+      const int64_t ints = 2 * (int64_t)key.second + (int64_t)key.second * t.ksize + (int64_t)key.second * (1 + 3 * t.nw);
       if (fill) {
         zv::AxisCoeffs ac;
         zv::resample_coeffs(key.first, key.second, &ac);
         L->coef.insert(L->coef.end(), ac.bounds.begin(), ac.bounds.end());
         L->coef.insert(L->coef.end(), ac.kk.begin(), ac.kk.end());
+        // dp4a limb table: the window starts at the first tap rounded down to 4 samples
+        std::vector<int32_t> w0(key.second);
+        for (int32_t o = 0; o < key.second; ++o) {
+          const int32_t xmin = ac.bounds[2 * o], cnt = ac.bounds[2 * o + 1];
+          const int32_t a = xmin & ~3;
+          w0[o] = a >> 2;
+          L->coef.push_back(a >> 2);
+          for (int limb = 0; limb < 3; ++limb)
+            for (int w = 0; w < t.nw; ++w) {
+              uint32_t word = 0;
+              for (int b = 0; b < 4; ++b) {
+                const int32_t tap = a + 4 * w + b - xmin;
+                const int32_t k = (tap >= 0 && tap < cnt) ? ac.kk[(size_t)o * ac.ksize + tap] : 0;
+                const uint32_t byte = limb == 0 ? (uint32_t)(k & 255) : limb == 1 ? (uint32_t)((k >> 8) & 255)
+                                                                                  : (uint32_t)((k >> 16) & 255);
+                word |= byte << (8 * b);
+              }
+              L->coef.push_back((int32_t)word);
+            }
+        }
+        // widest source span (in words) any 128-column chunk of this axis needs
+        for (int32_t o0 = 0; o0 < key.second; o0 += kHCols) {
+          const int32_t o1 = std::min(key.second, o0 + kHCols) - 1;
+          t.seg_words = std::max(t.seg_words, w0[o1] + t.nw - w0[o0]);
+        }
       }
-      coef_ints += 2 * (int64_t)key.second + (int64_t)key.second * ks;
+      L->axis[key] = t;
+      coef_ints += ints;
       if (coef_ints > INT32_MAX) return zv::fail(ZV_EINVAL, "zv_preprocess: coefficient tables exceed 2^31 entries");
     }
     // rows of the crop the vertical pass reads: [first tap of row 0, last tap of the last row]
@@ -186,15 +414,41 @@ int build_layout(int32_t n, const int32_t* crop_box, const int32_t* resized_hw, 
     L->ybox0[i] = y_first;
     L->nrows[i] = y_last - y_first;
     L->tmp_off[i] = tmp_bytes;
-    tmp_bytes += align_up((int64_t)L->nrows[i] * ow * 3, 256);
+    // fast path: 4 rows per word, quads counted from ybox0 rounded down to 4, spare quads for zero-tap window padding
+    const int64_t quads = (int64_t)((y_last + 3) / 4 - y_first / 4) + kMaxNW + 1;
+    tmp_bytes += align_up(std::max<int64_t>((int64_t)L->nrows[i] * ow * 3, quads * ow * 3 * 4), 256);
   }
   int64_t off = 0;
   L->off_desc = off; off = align_up(off + (int64_t)n * sizeof(K1Crop), 256);
   L->off_lut = off; off = align_up(off + 768 * sizeof(float), 256);
   L->off_coef = off; off = align_up(off + coef_ints * (int64_t)sizeof(int32_t), 256);
+  L->list_ints = 4 * ((int64_t)n + 16);      // per pass: crop ids + block prefix of every kernel class
+  L->off_lists = off; off = align_up(off + L->list_ints * (int64_t)sizeof(int32_t), 256);
   L->off_tmp = off; off += tmp_bytes;
   L->bytes = off;
   return ZV_OK;
+}
+
+template <int NW>
+void launch_hfast(unsigned blocks, int smem, cudaStream_t s, const K1Crop* d, const int32_t* ids, const int32_t* blk0,
+                  int ncls, const int32_t* coef, uint8_t* ws, int seg_words) {
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(k1_hpass_fast<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+  k1_hpass_fast<NW><<<blocks, 256, smem, s>>>(d, ids, blk0, ncls, coef, ws, seg_words);
+}
+template <typename OutT>
+void launch_vpass(int nw, unsigned blocks, cudaStream_t s, const K1Crop* d, const int32_t* ids, const int32_t* blk0, int ncls,
+                  const int32_t* coef, const uint8_t* ws, const float* lut, void* out_, int row_order, int wsz) {
+  OutT* out = static_cast<OutT*>(out_);
+  switch (nw) {
+    case 0: k1_vpass<OutT><<<blocks, 256, 0, s>>>(d, ids, blk0, ncls, coef, ws, lut, out, row_order, wsz); break;
+    case 2: k1_vpass_fast<2, OutT><<<blocks, 256, 0, s>>>(d, ids, blk0, ncls, coef, ws, lut, out, row_order, wsz); break;
+    case 3: k1_vpass_fast<3, OutT><<<blocks, 256, 0, s>>>(d, ids, blk0, ncls, coef, ws, lut, out, row_order, wsz); break;
+    case 4: k1_vpass_fast<4, OutT><<<blocks, 256, 0, s>>>(d, ids, blk0, ncls, coef, ws, lut, out, row_order, wsz); break;
+    case 5: k1_vpass_fast<5, OutT><<<blocks, 256, 0, s>>>(d, ids, blk0, ncls, coef, ws, lut, out, row_order, wsz); break;
+    case 7: k1_vpass_fast<7, OutT><<<blocks, 256, 0, s>>>(d, ids, blk0, ncls, coef, ws, lut, out, row_order, wsz); break;
+    default: k1_vpass_fast<10, OutT><<<blocks, 256, 0, s>>>(d, ids, blk0, ncls, coef, ws, lut, out, row_order, wsz); break;
+  }
 }
 
 }  // namespace
@@ -228,10 +482,12 @@ int zv_preprocess(const zv_cfg* cfg, int32_t n, const uint8_t* const* src_dev, c
   if (workspace_bytes < L.bytes)
     return zv::fail(ZV_ENOMEM, "zv_preprocess: workspace %lld B < required %lld B", (long long)workspace_bytes, (long long)L.bytes);
 
-  // host image of [descriptors | LUT | coefficient tables]
+  // host image of [descriptors | LUT | coefficient tables | launch lists]
   std::vector<uint8_t> host((size_t)L.off_tmp, 0);
   K1Crop* d = reinterpret_cast<K1Crop*>(host.data() + L.off_desc);
-  int64_t hblk = 0, vblk = 0, row = 0;
+  const bool generic_only = std::getenv("ZV_K1_GENERIC") != nullptr;    // debug: force the per-tap kernels
+  std::vector<int32_t> seg_h(n, 0);
+  int64_t row = 0;
   for (int32_t i = 0; i < n; ++i) {
     K1Crop& c = d[i];
     c.src = src_dev[i]; c.pitch = src_pitch[i];
@@ -240,43 +496,105 @@ int zv_preprocess(const zv_cfg* cfg, int32_t n, const uint8_t* const* src_dev, c
     c.cw = crop_box[4 * i + 2] - c.x0; c.ch = crop_box[4 * i + 3] - c.y0;
     c.oh = resized_hw[2 * i]; c.ow = resized_hw[2 * i + 1];
     if (!c.src || c.pitch < 3 * (int64_t)c.src_w) return zv::fail(ZV_EINVAL, "zv_preprocess: image %d has a null pointer or short pitch", i);
-    c.ksh = zv::resample_ksize(c.cw, c.ow); c.ksv = zv::resample_ksize(c.ch, c.oh);
-    const auto h = L.coef_at[{c.cw, c.ow}], v = L.coef_at[{c.ch, c.oh}];
-    c.off_bh = h.first; c.off_kh = h.second; c.off_bv = v.first; c.off_kv = v.second;
+    const AxisTables& h = L.axis[{c.cw, c.ow}];
+    const AxisTables& v = L.axis[{c.ch, c.oh}];
+    c.ksh = h.ksize; c.ksv = v.ksize;
+    c.off_bh = h.off_bounds; c.off_kh = h.off_kk; c.off_bv = v.off_bounds; c.off_kv = v.off_kk;
+    c.off_lh = h.off_limbs; c.off_lv = v.off_limbs;
+    const bool aligned = (reinterpret_cast<uintptr_t>(c.src) & 3) == 0 && (c.pitch & 3) == 0;
+    c.fast = (!generic_only && aligned && h.nw > 0 && v.nw > 0 && kHRows * 3 * h.seg_words * 4 <= 200 * 1024) ? 1 : 0;
+    c.nwh = c.fast ? h.nw : 0; c.nwv = c.fast ? v.nw : 0;
+    seg_h[i] = h.seg_words;
     c.ybox0 = L.ybox0[i]; c.nrows = L.nrows[i];
+    if (c.fast) {                       // row quads are counted from ybox0 rounded down to 4
+      const int32_t al = c.ybox0 & ~3;
+      c.nrows += c.ybox0 - al; c.ybox0 = al;
+    }
     c.tmp_off = L.off_tmp + L.tmp_off[i];
     c.lh = c.oh / 28; c.lw = c.ow / 28;
     c.out_row0 = row_off ? row_off[i] : row;
     row += (int64_t)(c.oh / 14) * (c.ow / 14);
-    c.hblk0 = (int32_t)hblk; c.vblk0 = (int32_t)vblk;
-    hblk += ((int64_t)c.nrows * c.ow + 255) / 256;
-    vblk += (int64_t)c.lh * c.lw;
-    if (hblk > INT32_MAX || vblk > INT32_MAX) return zv::fail(ZV_EINVAL, "zv_preprocess: batch too large for one launch");
   }
   zv::normalize_lut(cfg, reinterpret_cast<float*>(host.data() + L.off_lut));
   std::memcpy(host.data() + L.off_coef, L.coef.data(), L.coef.size() * sizeof(int32_t));
+
+  // launch lists: crops grouped by kernel class, each class with its own block prefix
+  struct Launch { int nw; int32_t ids_off, blk_off, count; int64_t blocks; int seg_words; };
+  std::vector<Launch> hl, vl;
+  int32_t* lists = reinterpret_cast<int32_t*>(host.data() + L.off_lists);
+  int64_t cur = 0;
+  auto build = [&](bool vpass, std::vector<Launch>* outl) -> int {
+    for (int nw : {0, 2, 3, 4, 5, 7, 10}) {
+      std::vector<int32_t> ids;
+      for (int32_t i = 0; i < n; ++i) if ((vpass ? d[i].nwv : d[i].nwh) == nw) ids.push_back(i);
+      if (ids.empty()) continue;
+      Launch l{};
+      l.nw = nw; l.count = (int32_t)ids.size();
+      if (cur + 2 * (int64_t)ids.size() > L.list_ints) return zv::fail(ZV_EINVAL, "zv_preprocess: launch lists overflow");
+      l.ids_off = (int32_t)cur;
+      for (int32_t id : ids) lists[cur++] = id;
+      l.blk_off = (int32_t)cur;
+      int64_t blocks = 0;
+      for (int32_t id : ids) {
+        const K1Crop& c = d[id];
+        lists[cur++] = (int32_t)blocks;
+        if (vpass) blocks += nw == 0 ? (int64_t)c.lh * c.lw : (int64_t)c.lh * ((c.lw + 1) / 2);
+        else if (nw == 0) blocks += ((int64_t)c.nrows * c.ow + 255) / 256;
+        else {
+          blocks += (((int64_t)c.nrows + kHRows - 1) / kHRows) * ((c.ow + kHCols - 1) / kHCols);
+          l.seg_words = std::max(l.seg_words, seg_h[id]);
+        }
+        if (blocks > INT32_MAX) return zv::fail(ZV_EINVAL, "zv_preprocess: batch too large for one launch");
+      }
+      l.blocks = blocks;
+      outl->push_back(l);
+    }
+    return ZV_OK;
+  };
+  rc = build(false, &hl);
+  if (rc) return rc;
+  rc = build(true, &vl);
+  if (rc) return rc;
 
   uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
   cudaError_t e = cudaMemcpyAsync(ws, host.data(), host.size(), cudaMemcpyHostToDevice, stream);
   if (e != cudaSuccess) return zv::fail(ZV_ECUDA, "zv_preprocess: table upload: %s", cudaGetErrorString(e));
   const K1Crop* dcrops = reinterpret_cast<const K1Crop*>(ws + L.off_desc);
   const int32_t* dcoef = reinterpret_cast<const int32_t*>(ws + L.off_coef);
+  const int32_t* dlists = reinterpret_cast<const int32_t*>(ws + L.off_lists);
   const float* dlut = reinterpret_cast<const float*>(ws + L.off_lut);
   const int wsz = cfg->window / cfg->merge / cfg->patch;
   {
     zv::KernelTimer timer(zv::KC_K1_HPASS, stream);
-    k1_hpass<<<(unsigned)hblk, 256, 0, stream>>>(dcrops, n, dcoef, ws);
+    for (const Launch& l : hl) {
+      const int32_t* ids = dlists + l.ids_off;
+      const int32_t* blk0 = dlists + l.blk_off;
+      const int smem = kHRows * 3 * l.seg_words * 4;
+      const unsigned nb = (unsigned)l.blocks;
+      switch (l.nw) {
+        case 0: k1_hpass<<<nb, 256, 0, stream>>>(dcrops, ids, blk0, l.count, dcoef, ws); break;
+        case 2: launch_hfast<2>(nb, smem, stream, dcrops, ids, blk0, l.count, dcoef, ws, l.seg_words); break;
+        case 3: launch_hfast<3>(nb, smem, stream, dcrops, ids, blk0, l.count, dcoef, ws, l.seg_words); break;
+        case 4: launch_hfast<4>(nb, smem, stream, dcrops, ids, blk0, l.count, dcoef, ws, l.seg_words); break;
+        case 5: launch_hfast<5>(nb, smem, stream, dcrops, ids, blk0, l.count, dcoef, ws, l.seg_words); break;
+        case 7: launch_hfast<7>(nb, smem, stream, dcrops, ids, blk0, l.count, dcoef, ws, l.seg_words); break;
+        default: launch_hfast<10>(nb, smem, stream, dcrops, ids, blk0, l.count, dcoef, ws, l.seg_words); break;
+      }
+      zv::count_launch();
+    }
   }
-  zv::KernelTimer timer(zv::KC_K1_VPASS, stream);
-  if (out_dtype == ZV_BF16)
-    k1_vpass<__nv_bfloat16><<<(unsigned)vblk, 256, 0, stream>>>(dcrops, n, dcoef, ws, dlut,
-                                                                 static_cast<__nv_bfloat16*>(out_dev), row_order, wsz);
-  else if (out_dtype == ZV_F16)
-    k1_vpass<__half><<<(unsigned)vblk, 256, 0, stream>>>(dcrops, n, dcoef, ws, dlut, static_cast<__half*>(out_dev), row_order, wsz);
-  else
-    k1_vpass<float><<<(unsigned)vblk, 256, 0, stream>>>(dcrops, n, dcoef, ws, dlut, static_cast<float*>(out_dev),
-                                                         row_order, wsz);
-  zv::count_launch(2);
+  {
+    zv::KernelTimer timer(zv::KC_K1_VPASS, stream);
+    for (const Launch& l : vl) {
+      const int32_t* ids = dlists + l.ids_off;
+      const int32_t* blk0 = dlists + l.blk_off;
+      const unsigned nb = (unsigned)l.blocks;
+      if (out_dtype == ZV_BF16) launch_vpass<__nv_bfloat16>(l.nw, nb, stream, dcrops, ids, blk0, l.count, dcoef, ws, dlut, out_dev, row_order, wsz);
+      else if (out_dtype == ZV_F16) launch_vpass<__half>(l.nw, nb, stream, dcrops, ids, blk0, l.count, dcoef, ws, dlut, out_dev, row_order, wsz);
+      else launch_vpass<float>(l.nw, nb, stream, dcrops, ids, blk0, l.count, dcoef, ws, dlut, out_dev, row_order, wsz);
+      zv::count_launch();
+    }
+  }
   e = cudaGetLastError();
   if (e != cudaSuccess) return zv::fail(ZV_ECUDA, "zv_preprocess: launch: %s", cudaGetErrorString(e));
   return ZV_OK;
