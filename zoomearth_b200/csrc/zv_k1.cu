@@ -17,8 +17,8 @@
 // (k = l0 + 256 l1 + 65536 l2, l2 signed); the host emits, per output index, a word-aligned tap window whose limb
 // bytes are packed four taps to a word, so one dp4a does four taps of one limb and no per-thread realignment of the
 // pixels is needed:
-//   hpass_fast  a CTA stages 8 source rows x the span of 128 output columns into shared memory, de-interleaved to
-//               R/G/B planes (coalesced word loads, byte permutes); a thread owns one output column with its limb
+//   hpass_fast  a CTA stages 8 source rows x the span of 128 output columns into shared memory (16-byte cp.async of
+//               the raw bytes, then a byte-permute pass to R/G/B planes); a thread owns one output column with its limb
 //               words in registers, runs 4 rows x 3 channels, and writes tmp packed 4 rows to a word.
 //   vpass_fast  tmp's row-quad words are directly dp4a operands along y; a warp owns output rows with their limb words
 //               in registers and sweeps the columns coalesced; the CTA assembles two merge groups' patch rows in shared
@@ -201,38 +201,50 @@ __global__ void __launch_bounds__(256) k1_hpass_fast(const K1Crop* __restrict__ 
   const int seg_words = min(seg_words_max, lt[(int64_t)(xx1 - 1) * kStride] + NW - w_first);
   const int r0 = strip * kHRows;                                         // first tmp row of the strip
 
-  // ---- stage: 8 rows x seg_words pixel quads, interleaved RGB -> planes, zero outside the image
-  const uintptr_t img_lo = reinterpret_cast<uintptr_t>(c.src);
-  const uintptr_t img_hi = img_lo + (uintptr_t)c.src_h * (uintptr_t)c.pitch;
-  for (int i = threadIdx.x; i < kHRows * seg_words; i += blockDim.x) {
-    const int row = i / seg_words, wq = i - row * seg_words;
-    const int y_img = c.y0 + c.ybox0 + r0 + row;
-    const int x_img = c.x0 + (w_first + wq) * 4;                         // image x of the quad's first pixel
-    uint32_t R = 0, G = 0, B = 0;
-    if (y_img >= 0 && y_img < c.src_h && x_img + 3 >= 0 && x_img < c.src_w) {
-      const int64_t off = (int64_t)y_img * c.pitch + 3 * (int64_t)x_img;  // may be negative (box left of the image)
-      const int64_t base = off & ~(int64_t)3;
-      const uint32_t sh = (uint32_t)(off & 3) * 8;
-      uint32_t w[4];
+  // ---- stage A: raw bytes of the 8 row segments -> shared memory with 16-byte cp.async (warp w = row w);
+  //      bytes outside the image (box beyond the border) are zeros (Image.crop semantics)
+  uint8_t* raw = reinterpret_cast<uint8_t*>(planes + kHRows * 3 * seg_words_max);    // [8][raw_pitch]
+  const int raw_pitch = (seg_words_max * 12 + 32 + 15) & ~15;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int y_img = c.y0 + c.ybox0 + r0 + warp;
+  const bool row_ok = y_img >= 0 && y_img < c.src_h;
+  const int64_t b0 = 3 * (int64_t)(c.x0 + w_first * 4);                  // first byte of the segment in the row (may be < 0)
+  const uint8_t* rowp = c.src + (int64_t)(row_ok ? y_img : 0) * c.pitch;
+  const int delta = (int)((reinterpret_cast<uintptr_t>(rowp) + (uintptr_t)(b0 & 15) + 16) & 15);   // (rowp + b0) mod 16
+  const int64_t g0 = b0 - delta;                                         // row byte offset of raw[0]; rowp + g0 is 16-aligned
+  const int n_chunks = (delta + seg_words * 12 + 15) >> 4;
+  const int64_t row_bytes = 3 * (int64_t)c.src_w;
+  uint8_t* rraw = raw + warp * raw_pitch;
+  for (int ck = lane; ck < n_chunks; ck += 32) {
+    const int64_t o = g0 + 16 * (int64_t)ck;
+    uint8_t* dst = rraw + 16 * ck;
+    if (row_ok && o >= 0 && o + 16 <= row_bytes) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(rowp + o) : "memory");
+    } else {
+      uint32_t wv[4] = {0u, 0u, 0u, 0u};
+      if (row_ok && o + 16 > 0 && o < row_bytes) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int64_t a = base + 4 * k;
-        w[k] = (a >= 0 && (uintptr_t)(a + 4) <= img_hi - img_lo) ? __ldg(reinterpret_cast<const uint32_t*>(c.src + a)) : 0u;
+        for (int k = 0; k < 16; ++k)
+          if (o + k >= 0 && o + k < row_bytes) wv[k >> 2] |= (uint32_t)__ldg(rowp + o + k) << (8 * (k & 3));
       }
-      const uint32_t v0 = __funnelshift_r(w[0], w[1], sh), v1 = __funnelshift_r(w[1], w[2], sh),
-                     v2 = __funnelshift_r(w[2], w[3], sh);
-      R = __byte_perm(__byte_perm(v0, v1, 0x0630), v2, 0x5210);
-      G = __byte_perm(__byte_perm(v0, v1, 0x0741), v2, 0x6210);
-      B = __byte_perm(__byte_perm(v0, v1, 0x0052), v2, 0x7410);
-      if (x_img < 0 || x_img + 3 >= c.src_w) {                           // quad straddles the image edge
-        uint32_t m = 0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) if (x_img + j >= 0 && x_img + j < c.src_w) m |= 0xFFu << (8 * j);
-        R &= m; G &= m; B &= m;
-      }
+      *reinterpret_cast<uint4*>(dst) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
     }
-    uint32_t* p = planes + (row * 3) * seg_words_max + wq;
-    p[0] = R; p[seg_words_max] = G; p[2 * seg_words_max] = B;
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
+  // ---- stage B: de-interleave this warp's row, 4 pixels (12 bytes) per lane step: RGBRGBRGBRGB -> R4 | G4 | B4
+  {
+    const uint32_t sh = (uint32_t)(delta & 3) * 8;
+    const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(rraw + (delta & ~3));
+    uint32_t* p = planes + (warp * 3) * seg_words_max;
+    for (int wq = lane; wq < seg_words; wq += 32) {
+      const uint32_t w0 = wsrc[3 * wq], w1 = wsrc[3 * wq + 1], w2 = wsrc[3 * wq + 2], w3 = wsrc[3 * wq + 3];
+      const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh), v2 = __funnelshift_r(w2, w3, sh);
+      p[wq] = __byte_perm(__byte_perm(v0, v1, 0x0630), v2, 0x5210);
+      p[seg_words_max + wq] = __byte_perm(__byte_perm(v0, v1, 0x0741), v2, 0x6210);
+      p[2 * seg_words_max + wq] = __byte_perm(__byte_perm(v0, v1, 0x0052), v2, 0x7410);
+    }
   }
   __syncthreads();
 
@@ -288,9 +300,19 @@ __global__ void __launch_bounds__(256) k1_vpass_fast(const K1Crop* __restrict__ 
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t* __restrict__ tmp4 = reinterpret_cast<const uint32_t*>(ws + c.tmp_off) + mx0 * 84;
-  const int64_t qpitch = (int64_t)c.ow * 3;                              // words per row quad
+  const int qpitch = c.ow * 3;                                           // words per row quad
   constexpr int kStride = 1 + 3 * NW;
   const int q_origin = c.ybox0 >> 2;                                     // tmp quads are counted from ybox0 (multiple of 4)
+  // per-lane column decomposition, hoisted out of the row loop: stage offset and LUT base of columns lane + 32 i
+  int eoff[6], lbase[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const int col = lane + 32 * i;
+    const int xl = col / 3, ch = col - xl * 3;                           // xl in [0, 56)
+    const int grp = xl / 28, xg = xl - grp * 28;
+    eoff[i] = (grp * 4 + xg / 14) * kPatchElems + ch * 392 + (xg % 14);
+    lbase[i] = ch * 256;
+  }
   for (int yl = warp; yl < 28; yl += 8) {
     const int yy = my * 28 + yl;
     const int32_t* __restrict__ e = coef + c.off_lv + (int64_t)yy * kStride;
@@ -298,24 +320,23 @@ __global__ void __launch_bounds__(256) k1_vpass_fast(const K1Crop* __restrict__ 
     uint32_t l0[NW], l1[NW], l2[NW];
 #pragma unroll
     for (int k = 0; k < NW; ++k) { l0[k] = __ldg(e + 1 + k); l1[k] = __ldg(e + 1 + NW + k); l2[k] = __ldg(e + 1 + 2 * NW + k); }
-    const uint32_t* __restrict__ base = tmp4 + (int64_t)q0 * qpitch;
-    for (int col = lane; col < ncols; col += 32) {
-      int a0 = 0, a1 = 0, a2 = 0;
+    const uint32_t* __restrict__ base = tmp4 + (int64_t)q0 * qpitch + lane;
+    const int rowoff = (yl / 14) * 2 * kPatchElems + (yl % 14) * 14;
 #pragma unroll
-      for (int k = 0; k < NW; ++k) {
-        const uint32_t v = __ldg(base + (int64_t)k * qpitch + col);
-        a0 = dp4a_uu(v, l0[k], a0);
-        a1 = dp4a_uu(v, l1[k], a1);
-        a2 = dp4a_us(v, l2[k], a2);
+    for (int i = 0; i < 6; ++i) {
+      if (lane + 32 * i < ncols) {
+        int a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll
+        for (int k = 0; k < NW; ++k) {
+          const uint32_t v = __ldg(base + k * qpitch + 32 * i);
+          a0 = dp4a_uu(v, l0[k], a0);
+          a1 = dp4a_uu(v, l1[k], a1);
+          a2 = dp4a_us(v, l2[k], a2);
+        }
+        const OutT o = to_out<OutT>(s_lut[lbase[i] + finish8(a0, a1, a2)]);
+        stage[eoff[i] + rowoff] = o;
+        stage[eoff[i] + rowoff + 196] = o;
       }
-      const int xl = col / 3, ch = col - xl * 3;                         // xl in [0, 56)
-      const float v = s_lut[ch * 256 + finish8(a0, a1, a2)];
-      const int grp = xl / 28, xg = xl - grp * 28;
-      const int j = (yl / 14) * 2 + (xg / 14);
-      const int el = (grp * 4 + j) * kPatchElems + ch * 392 + (yl % 14) * 14 + (xg % 14);
-      const OutT o = to_out<OutT>(v);
-      stage[el] = o;
-      stage[el + 196] = o;
     }
   }
   __syncthreads();
@@ -502,7 +523,7 @@ int zv_preprocess(const zv_cfg* cfg, int32_t n, const uint8_t* const* src_dev, c
     c.off_bh = h.off_bounds; c.off_kh = h.off_kk; c.off_bv = v.off_bounds; c.off_kv = v.off_kk;
     c.off_lh = h.off_limbs; c.off_lv = v.off_limbs;
     const bool aligned = (reinterpret_cast<uintptr_t>(c.src) & 3) == 0 && (c.pitch & 3) == 0;
-    c.fast = (!generic_only && aligned && h.nw > 0 && v.nw > 0 && kHRows * 3 * h.seg_words * 4 <= 200 * 1024) ? 1 : 0;
+    c.fast = (!generic_only && aligned && h.nw > 0 && v.nw > 0 && kHRows * (h.seg_words * 24 + 48) <= 200 * 1024) ? 1 : 0;
     c.nwh = c.fast ? h.nw : 0; c.nwv = c.fast ? v.nw : 0;
     seg_h[i] = h.seg_words;
     c.ybox0 = L.ybox0[i]; c.nrows = L.nrows[i];
@@ -569,7 +590,7 @@ int zv_preprocess(const zv_cfg* cfg, int32_t n, const uint8_t* const* src_dev, c
     for (const Launch& l : hl) {
       const int32_t* ids = dlists + l.ids_off;
       const int32_t* blk0 = dlists + l.blk_off;
-      const int smem = kHRows * 3 * l.seg_words * 4;
+      const int smem = kHRows * 3 * l.seg_words * 4 + kHRows * ((l.seg_words * 12 + 32 + 15) & ~15);
       const unsigned nb = (unsigned)l.blocks;
       switch (l.nw) {
         case 0: k1_hpass<<<nb, 256, 0, stream>>>(dcrops, ids, blk0, l.count, dcoef, ws); break;
