@@ -19,6 +19,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "zv_common.h"
@@ -35,11 +36,12 @@ constexpr int BM = 128, BK = 64, UMMA_K = 16;
 constexpr int kThreads = 384;          // 4 role warps + 8 epilogue warps
 constexpr int kTmemCols = 512;
 
-template <int BN> struct Cfg {
+template <int BN, int CG> struct Cfg {
+  static constexpr int kBRows = BN / CG;                       // B rows staged per CTA (half the tile in a CTA pair)
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN > 128) ? 4 : 6;
+  static constexpr int kStages = (kBRows > 128) ? 4 : 6;
   static constexpr int kBarBytes = 256;
   static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;   // +1024: manual alignment slack
 };
@@ -259,10 +261,55 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int m_blk, int n_b
   }
 }
 
-template <int BN, int EPI>
+// cta_group::2 helpers (CTA pair = cluster of 2 along M; the even CTA is the MMA leader)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load into this CTA's smem, completing on the LEADER CTA's mbarrier (peer bit of the address cleared)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* tmap, uint64_t* bar, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all prior MMAs of this thread are done) on the same barrier in both CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar, uint32_t cta) {      // arrive on CTA `cta`'s copy of `bar`
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tmbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2) per 256 x BN tile with tcgen05 cta_group::2:
+// each CTA stages its own 128 A rows and HALF of the B rows (BN/2), the leader issues one M=256 MMA that reads both
+// CTAs' shared memory and writes both CTAs' TMEM, so per-CTA L2->smem traffic drops by a third (A 16 KB + B 16 KB
+// instead of A 16 KB + B 32 KB per k-block) and the smem ring is six stages deep instead of four.
+template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc(const __grid_constant__ CUtensorMap tma_a,
                                                        const __grid_constant__ CUtensorMap tma_b, const GemmArgs g) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
@@ -273,45 +320,58 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc(const __grid_constant__ C
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0;
+  const bool leader = rank == 0;
   const int n_blocks = g.N / BN;
-  const int m_blocks = (g.M + BM - 1) / BM;
+  const int m_blocks = (g.M + BM * CG - 1) / (BM * CG);
   const int num_tiles = m_blocks * n_blocks;
   const int k_blocks = (g.K + BK - 1) / BK;
+  const int first_tile = blockIdx.x / CG, tile_step = gridDim.x / CG;
 
   if (threadIdx.x == 0) {
     prefetch_tensormap(&tma_a);
     prefetch_tensormap(&tma_b);
     for (int s = 0; s < C::kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 8); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 8 * CG); }
     fence_mbar_init();
   }
-  if (warp == 2) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
+  if (warp == 2) {
+    if constexpr (CG == 2) tmem_alloc_pair(tmem_slot, kTmemCols);
+    else { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+        const int m_row = (tile / n_blocks) * BM * CG + (int)rank * BM;
+        const int n_row = (tile % n_blocks) * BN + (int)rank * C::kBRows;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(empty + stage, phase ^ 1);
           uint8_t* sa = smem + stage * C::kStageBytes;
-          mbar_arrive_expect_tx(full + stage, C::kStageBytes);
-          tma_load_2d(sa, &tma_a, full + stage, kb * BK, m_blk * BM);
-          tma_load_2d(sa + C::kABytes, &tma_b, full + stage, kb * BK, n_blk * BN);
+          if constexpr (CG == 2) {
+            if (leader) mbar_arrive_expect_tx(full + stage, 2 * C::kStageBytes);     // both CTAs' bytes land on the leader
+            tma_load_2d_pair(sa, &tma_a, full + stage, kb * BK, m_row);
+            tma_load_2d_pair(sa + C::kABytes, &tma_b, full + stage, kb * BK, n_row);
+          } else {
+            mbar_arrive_expect_tx(full + stage, C::kStageBytes);
+            tma_load_2d(sa, &tma_a, full + stage, kb * BK, m_row);
+            tma_load_2d(sa + C::kABytes, &tma_b, full + stage, kb * BK, n_row);
+          }
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (elect_one()) {
-      const uint32_t idesc = umma_idesc_16bit(BM, BN, g.op_f16 != 0);
+    if (leader && elect_one()) {
+      const uint32_t idesc = umma_idesc_16bit(BM * CG, BN, g.op_f16 != 0);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(tempty + acc, acc_phase ^ 1);
@@ -323,19 +383,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc(const __grid_constant__ C
           const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
           const uint64_t da = umma_desc_k128(sa), db = umma_desc_k128(sa + C::kABytes);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k)
-            umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);   // +32 B per K step, in 16 B units
-          umma_commit(empty + stage);
+          for (int k = 0; k < BK / UMMA_K; ++k) {                                   // +32 B per K step, in 16 B units
+            if constexpr (CG == 2) umma_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            else umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          }
+          if constexpr (CG == 2) umma_commit_pair(empty + stage); else umma_commit(empty + stage);
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tfull + acc);
+        if constexpr (CG == 2) umma_commit_pair(tfull + acc); else umma_commit(tfull + acc);
       }
     }
   } else if (warp >= 4) {
     const int q = warp & 3, half = (warp - 4) >> 2;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
+      const int m_blk = (tile / n_blocks) * CG + (int)rank, n_blk = tile % n_blocks;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
@@ -345,12 +407,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc(const __grid_constant__ C
       });
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty + acc);
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_cta(tempty + acc, 0); else mbar_arrive(tempty + acc);
+      }
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    if constexpr (CG == 2) tmem_dealloc_pair(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
+  }
 }
 
 // ---- host side
@@ -390,29 +457,41 @@ int num_sms() {
   return n;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CG>
 int launch(const GemmArgs& g, const void* a, int64_t lda, const void* b, int64_t ldb, cudaStream_t stream) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CG>;
   if (g.N % BN) return fail(ZV_EINVAL, "gemm: N=%d is not a multiple of the %d-wide tile", g.N, BN);
   CUtensorMap ta, tb;
   int rc = make_tmap(&ta, a, g.M, g.K, lda, BM, g.op_f16 != 0);
   if (rc) return rc;
-  rc = make_tmap(&tb, b, g.N, g.K, ldb, BN, g.op_f16 != 0);
+  rc = make_tmap(&tb, b, g.N, g.K, ldb, C::kBRows, g.op_f16 != 0);
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc<BN, EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) return fail(ZV_ECUDA, "gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const int tiles = ((g.M + BM - 1) / BM) * (g.N / BN);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
+  const int tiles = ((g.M + BM * CG - 1) / (BM * CG)) * (g.N / BN);
+  const int slots = num_sms() / CG;
+  const int grid = (tiles < slots ? tiles : slots) * CG;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e;
   {
     KernelTimer timer(KC_GEMM_STORE + EPI, stream);
-    gemm_tc<BN, EPI><<<grid, kThreads, C::kSmemBytes, stream>>>(ta, tb, g);
+    e = cudaLaunchKernelEx(&cfg, gemm_tc<BN, EPI, CG>, ta, tb, g);
   }
   count_launch();
-  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return fail(ZV_ECUDA, "gemm: launch: %s", cudaGetErrorString(e));
   return ZV_OK;
 }
@@ -444,15 +523,28 @@ int make_tmap_2d(void* tm_, const void* base, int64_t rows, int64_t cols, int64_
 int gemm(int epi, const GemmArgs& g, const void* a, int64_t lda, const void* b, int64_t ldb, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return fail(ZV_EINVAL, "gemm: empty problem %dx%dx%d", g.M, g.N, g.K);
+  static const bool pair = std::getenv("ZV_GEMM_1CTA") == nullptr;     // debug switch: single-CTA kernels everywhere
+  if (!pair) {
+    switch (epi) {
+      case EPI_STORE:
+        return g.N % 256 == 0 ? launch<256, EPI_STORE, 1>(g, a, lda, b, ldb, stream)
+                              : launch<128, EPI_STORE, 1>(g, a, lda, b, ldb, stream);
+      case EPI_QKV_ROPE: return launch<240, EPI_QKV_ROPE, 1>(g, a, lda, b, ldb, stream);
+      case EPI_RESID: return launch<256, EPI_RESID, 1>(g, a, lda, b, ldb, stream);
+      case EPI_SWIGLU: return launch<256, EPI_SWIGLU, 1>(g, a, lda, b, ldb, stream);
+      case EPI_GELU: return launch<256, EPI_GELU, 1>(g, a, lda, b, ldb, stream);
+      case EPI_SCATTER: return launch<256, EPI_SCATTER, 1>(g, a, lda, b, ldb, stream);
+    }
+  }
   switch (epi) {
     case EPI_STORE:
-      return g.N % 256 == 0 ? launch<256, EPI_STORE>(g, a, lda, b, ldb, stream)
-                            : launch<128, EPI_STORE>(g, a, lda, b, ldb, stream);
-    case EPI_QKV_ROPE: return launch<240, EPI_QKV_ROPE>(g, a, lda, b, ldb, stream);
-    case EPI_RESID: return launch<256, EPI_RESID>(g, a, lda, b, ldb, stream);
-    case EPI_SWIGLU: return launch<256, EPI_SWIGLU>(g, a, lda, b, ldb, stream);
-    case EPI_GELU: return launch<256, EPI_GELU>(g, a, lda, b, ldb, stream);
-    case EPI_SCATTER: return launch<256, EPI_SCATTER>(g, a, lda, b, ldb, stream);
+      return g.N % 256 == 0 ? launch<256, EPI_STORE, 2>(g, a, lda, b, ldb, stream)
+                            : launch<128, EPI_STORE, 1>(g, a, lda, b, ldb, stream);
+    case EPI_QKV_ROPE: return launch<240, EPI_QKV_ROPE, 2>(g, a, lda, b, ldb, stream);
+    case EPI_RESID: return launch<256, EPI_RESID, 2>(g, a, lda, b, ldb, stream);
+    case EPI_SWIGLU: return launch<256, EPI_SWIGLU, 2>(g, a, lda, b, ldb, stream);
+    case EPI_GELU: return launch<256, EPI_GELU, 2>(g, a, lda, b, ldb, stream);
+    case EPI_SCATTER: return launch<256, EPI_SCATTER, 2>(g, a, lda, b, ldb, stream);
   }
   return fail(ZV_EINVAL, "gemm: unknown epilogue %d", epi);
 }
