@@ -22,7 +22,7 @@ constexpr int HD = 80;          // head dim
 constexpr int BQ = 64, BKV = 64;
 constexpr int LDS = 88;         // smem row pitch in elements (176 B: conflict-free ldmatrix)
 constexpr int kTileElems = 64 * LDS;
-template <int NW> constexpr int smem_bytes() { return (16 * NW + 4 * 64) * LDS * 2; }   // Q (16*NW rows) + 2 x (K, V)
+template <int NW> constexpr int smem_bytes() { return (16 * NW + (NW == 4 ? 2 : 4) * 64) * LDS * 2; }   // Q + (K, V) x 1 (windows) or x 2 (long segments)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
@@ -73,8 +73,9 @@ __global__ void __launch_bounds__(32 * NW) attn_kernel(const __nv_bfloat16* __re
                                                    const int4* __restrict__ tiles, int heads, float scale_log2) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_raw);
-  __nv_bfloat16* sK = sQ + 16 * NW * LDS;       // [2][64][LDS]
-  __nv_bfloat16* sV = sK + 2 * kTileElems;      // [2][64][LDS]
+  constexpr int NBUF = NW == 4 ? 1 : 2;         // window tiles (NW = 4) hold the whole segment in one K/V tile
+  __nv_bfloat16* sK = sQ + 16 * NW * LDS;       // [NBUF][64][LDS]
+  __nv_bfloat16* sV = sK + NBUF * kTileElems;   // [NBUF][64][LDS]
   const int4 tl = tiles[blockIdx.x];
   const int q0 = tl.x, q_len = tl.y, seg_b = tl.z, seg_e = tl.w;
   const int head = blockIdx.y;
@@ -100,8 +101,8 @@ __global__ void __launch_bounds__(32 * NW) attn_kernel(const __nv_bfloat16* __re
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
 
   for (int j = 0; j < n_kv; ++j) {
-    const int buf = j & 1;
-    if (j + 1 < n_kv) {            // prefetch the next K/V tile into the other buffer
+    const int buf = NBUF == 2 ? (j & 1) : 0;
+    if (NBUF == 2 && j + 1 < n_kv) {            // prefetch the next K/V tile into the other buffer
       const int nv = min(BKV, kv_len - (j + 1) * BKV);
       load_tile(sK + (buf ^ 1) * kTileElems, gk + (int64_t)(j + 1) * BKV * ld, ld, nv, BKV);
       load_tile(sV + (buf ^ 1) * kTileElems, gv + (int64_t)(j + 1) * BKV * ld, ld, nv, BKV);

@@ -197,9 +197,13 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const __grid_const
 #pragma unroll
         for (int i = 0; i < 64; ++i) if (i < lo || i >= hi) s[i] = -INFINITY;
       }
-      float mx = s[0];
+      float mx4[4] = {s[0], s[1], s[2], s[3]};          // four independent chains, not one 64-deep dependency
 #pragma unroll
-      for (int i = 1; i < 64; ++i) mx = fmaxf(mx, s[i]);
+      for (int i = 4; i < 64; i += 4) {
+        mx4[0] = fmaxf(mx4[0], s[i]); mx4[1] = fmaxf(mx4[1], s[i + 1]);
+        mx4[2] = fmaxf(mx4[2], s[i + 2]); mx4[3] = fmaxf(mx4[3], s[i + 3]);
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const bool grow = (mx - m_used) * sl2 > 8.0f;          // true on the first tile (m_used = -inf)
       float factor = 1.0f;
       if (grow) { factor = exp2f((m_used - mx) * sl2); m_used = mx; l *= factor; }
@@ -221,15 +225,15 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const __grid_const
         }
       }
       const float ms = m_used * sl2;
-      float rs = 0.f;
+      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
       uint32_t pk[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const float p0 = exp2f(s[2 * i] * sl2 - ms), p1 = exp2f(s[2 * i + 1] * sl2 - ms);
-        rs += p0 + p1;
+        rs4[i & 3] += p0 + p1;
         pk[i] = pack2(p0, p1, f16);
       }
-      l += rs;
+      l += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
       // P row -> shared memory, K-major 128B swizzle: 16-byte chunk c of row r lives at chunk (c ^ (r & 7))
 #pragma unroll
       for (int c = 0; c < 8; ++c)
