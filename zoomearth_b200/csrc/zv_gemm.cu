@@ -36,14 +36,18 @@ constexpr int BM = 128, BK = 64, UMMA_K = 16;
 constexpr int kThreads = 384;          // 4 role warps + 8 epilogue warps
 constexpr int kTmemCols = 512;
 
-template <int BN, int CG> struct Cfg {
+constexpr int kXposePitch = 36;                                 // floats per staged row (32 + 4: conflict-free 16 B accesses)
+constexpr int kXposeBytesPerWarp = 32 * kXposePitch * 4;
+template <int BN, int CG, int EPI = 0> struct Cfg {
   static constexpr int kBRows = BN / CG;                       // B rows staged per CTA (half the tile in a CTA pair)
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (kBRows > 128) ? 4 : 6;
+  // the residual epilogue transposes its tile through shared memory (8 warps x 4.5 KB): one pipeline stage less
+  static constexpr int kXposeBytes = EPI == EPI_RESID ? 8 * kXposeBytesPerWarp : 0;
+  static constexpr int kStages = ((kBRows > 128) ? 4 : 6) - (EPI == EPI_RESID ? 1 : 0);
   static constexpr int kBarBytes = 256;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;   // +1024: manual alignment slack
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kXposeBytes + 1024;   // +1024: manual alignment slack
 };
 
 __device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
@@ -70,12 +74,55 @@ __device__ __forceinline__ void load_bias32(const float* __restrict__ b, float (
 // h = (warp - 4) >> 2.  One thread = one accumulator row, half of the tile's columns.  `taddr` carries the quarter.
 template <int BN, int EPI, typename WaitFn>
 __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int m_blk, int n_blk, int row_local, int half,
-                                              const GemmArgs& g, WaitFn wait_accumulator) {
+                                              const GemmArgs& g, float* xpose, WaitFn wait_accumulator) {
   const int row = m_blk * BM + row_local;
   const bool valid = row < g.M;
   const bool of16 = g.out_dtype == ZV_F16;
   if constexpr (EPI != EPI_RESID) wait_accumulator();
-  if constexpr (EPI == EPI_STORE || EPI == EPI_GELU || EPI == EPI_SCATTER || EPI == EPI_RESID) {
+  if constexpr (EPI == EPI_RESID) {
+    // X(fp32) += acc + bias, coalesced: the accumulator chunk (32 rows x 32 columns per warp, one row per thread)
+    // is transposed through shared memory so that a warp instruction touches 4 rows x 128 contiguous bytes of X
+    // (4 L1 wavefronts) instead of 32 rows x 16 bytes (32 wavefronts).  The residual values of a chunk are fetched
+    // before its accumulator is read; the first chunk's even before the MMAs of the tile have finished.
+    constexpr int HALF = BN / 2;
+    const int lane = row_local & 31;
+    const int rr = lane >> 3, cc = (lane & 7) * 4;                      // this lane's row (mod 4) and column in the chunk
+    const int row_base = m_blk * BM + (row_local & ~31);
+    float* xrow = static_cast<float*>(g.out) + (int64_t)row_base * g.ldo + n_blk * BN + half * HALF + cc;
+    float4 xv[8];
+    auto load_x = [&](int c) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = 4 * i + rr;
+        xv[i] = (row_base + r < g.M) ? *reinterpret_cast<const float4*>(xrow + (int64_t)r * g.ldo + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    load_x(0);
+    wait_accumulator();
+#pragma unroll 1
+    for (int c = 0; c < HALF; c += 32) {
+      uint32_t r[32];
+      __syncwarp();
+      tmem_ld_x32(taddr + half * HALF + c, r);
+      float v[32];
+      load_bias32(g.bias + n_blk * BN + half * HALF + c, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(xpose + lane * kXposePitch + 4 * j) =
+            make_float4(v[4 * j] + __uint_as_float(r[4 * j]), v[4 * j + 1] + __uint_as_float(r[4 * j + 1]),
+                        v[4 * j + 2] + __uint_as_float(r[4 * j + 2]), v[4 * j + 3] + __uint_as_float(r[4 * j + 3]));
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rw = 4 * i + rr;
+        const float4 a = *reinterpret_cast<const float4*>(xpose + rw * kXposePitch + cc);
+        if (row_base + rw < g.M)
+          *reinterpret_cast<float4*>(xrow + (int64_t)rw * g.ldo + c) = make_float4(xv[i].x + a.x, xv[i].y + a.y, xv[i].z + a.z, xv[i].w + a.w);
+      }
+      if (c + 32 < HALF) load_x(c + 32);
+    }
+  } else if constexpr (EPI == EPI_STORE || EPI == EPI_GELU || EPI == EPI_SCATTER) {
     constexpr int HALF = BN / 2;
     int64_t orow = row;
     if constexpr (EPI == EPI_SCATTER) orow = valid ? (int64_t)__ldg(g.scatter + row) : 0;
@@ -309,7 +356,7 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols
 template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc(const __grid_constant__ CUtensorMap tma_a,
                                                        const __grid_constant__ CUtensorMap tma_b, const GemmArgs g) {
-  using C = Cfg<BN, CG>;
+  using C = Cfg<BN, CG, EPI>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
@@ -395,13 +442,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc(const __grid_constant__ C
     }
   } else if (warp >= 4) {
     const int q = warp & 3, half = (warp - 4) >> 2;
+    float* xpose = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes + C::kBarBytes) + (warp - 4) * (kXposeBytesPerWarp / 4);
     int it = 0;
     for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
       const int m_blk = (tile / n_blocks) * CG + (int)rank, n_blk = tile % n_blocks;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
-      epilogue_tile<BN, EPI>(taddr, m_blk, n_blk, q * 32 + lane, half, g, [&] {
+      epilogue_tile<BN, EPI>(taddr, m_blk, n_blk, q * 32 + lane, half, g, xpose, [&] {
         mbar_wait(tfull + acc, acc_phase);
         tc_fence_after();
       });
@@ -459,7 +507,7 @@ int num_sms() {
 
 template <int BN, int EPI, int CG>
 int launch(const GemmArgs& g, const void* a, int64_t lda, const void* b, int64_t ldb, cudaStream_t stream) {
-  using C = Cfg<BN, CG>;
+  using C = Cfg<BN, CG, EPI>;
   if (g.N % BN) return fail(ZV_EINVAL, "gemm: N=%d is not a multiple of the %d-wide tile", g.N, BN);
   CUtensorMap ta, tb;
   int rc = make_tmap(&ta, a, g.M, g.K, lda, BM, g.op_f16 != 0);
