@@ -112,3 +112,18 @@ def test_zoom_step_end_to_end(cuda):
     cos, maxrel = _metrics(emb, ref)
     assert cos >= 0.999 and maxrel <= 1e-2, f"cos {cos} maxrel {maxrel}"
     assert enc.last_launches > 0
+
+
+def test_encode_host_pipeline_matches_resident_path(cuda):
+    """The chunked host pipeline (H2D / compute / D2H on three streams) returns exactly what the resident path does."""
+    from zoomearth_b200 import FusedImageProcessor, ZoomEncoder
+    cfg = OT.small_cfg(depth=2, fullatt=(1,))
+    sd = OT.make_weights(4, cfg)
+    fv = _fused(sd, cfg, cuda, dtype=torch.bfloat16)
+    enc = ZoomEncoder(fv, FusedImageProcessor(min_pixels=3136, max_pixels=100352, device=cuda))
+    rng = np.random.default_rng(9)
+    host = [torch.from_numpy(rng.integers(0, 256, (400 + 40 * i, 500, 3), dtype=np.uint8)).pin_memory() for i in range(5)]
+    out, grid = enc.encode_host(host, chunk=2)
+    ref, rgrid, _ = enc.encode([h.to(cuda) for h in host], None)
+    assert grid.tolist() == rgrid.tolist()
+    assert torch.equal(out, ref.cpu())

@@ -43,6 +43,56 @@ class ZoomEncoder:
             return emb, grid, crop, pv
         return emb, grid, crop
 
+    @torch.no_grad()
+    def encode_host(self, host_images, chunk=16, out_host=None):
+        """Global views of HOST images (pinned (H, W, 3) uint8 tensors), pipelined: the pixels of chunk i+1 are
+        copied to the GPU on a side stream while chunk i runs through K1 + the tower, and the embeddings of chunk i
+        go back to `out_host` (pinned) behind the compute.  Returns (out_host, image_grid_thw).  This is the ingest
+        half of the reference loop (`Image.open(...)` -> processor -> `.to(device)`, infer.py:215-223) with the
+        copy moved upstream to the raw uint8 pixels."""
+        dev = self.visual.device
+        compute = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(dev)
+            self._d2h_stream = torch.cuda.Stream(dev)
+        groups = [host_images[i:i + chunk] for i in range(0, len(host_images), chunk)]
+        staged = []
+
+        def stage(g):
+            with torch.cuda.stream(self._copy_stream):
+                t = [h.to(dev, non_blocking=True) for h in g]
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+            return t, ev
+
+        staged.append(stage(groups[0]))
+        grids, row, launches, keep = [], 0, 0, []
+        for i in range(len(groups)):
+            if i + 1 < len(groups):
+                staged.append(stage(groups[i + 1]))
+            imgs, ev = staged[i]
+            compute.wait_event(ev)
+            for t in imgs:
+                t.record_stream(compute)
+            emb, grid, _ = self.encode(imgs, None)
+            launches += self.last_launches
+            grids.append(grid)
+            if out_host is None:
+                total = sum(int(g[:, 0].mul(g[:, 1]).mul(g[:, 2]).sum()) // self.visual.spatial_merge_unit for g in grids)
+                est = total * len(groups)            # same-size chunks; grows below if the guess was short
+                out_host = torch.empty((est, emb.shape[1]), dtype=emb.dtype).pin_memory()
+            done = torch.cuda.Event()
+            done.record(compute)
+            with torch.cuda.stream(self._d2h_stream):
+                self._d2h_stream.wait_event(done)
+                out_host[row:row + emb.shape[0]].copy_(emb, non_blocking=True)
+                emb.record_stream(self._d2h_stream)
+            keep.append(emb)
+            row += emb.shape[0]
+        self._d2h_stream.synchronize()
+        self.last_launches = launches
+        return out_host[:row], torch.cat(grids, 0)
+
     def tokens_per_crop(self, grid_thw):
         g = np.asarray(grid_thw)
         return (g[:, 0] * g[:, 1] * g[:, 2]) // (self.visual.spatial_merge_unit)
