@@ -55,7 +55,9 @@ class ZoomEncoder:
         if not hasattr(self, "_copy_stream"):
             self._copy_stream = torch.cuda.Stream(dev)
             self._d2h_stream = torch.cuda.Stream(dev)
-        groups = [host_images[i:i + chunk] for i in range(0, len(host_images), chunk)]
+        # a short first chunk keeps the exposed (un-overlapped) first upload small
+        first = max(1, chunk // 4) if len(host_images) > chunk else len(host_images)
+        groups = [host_images[:first]] + [host_images[i:i + chunk] for i in range(first, len(host_images), chunk)]
         staged = []
 
         def stage(g):
@@ -79,7 +81,7 @@ class ZoomEncoder:
             grids.append(grid)
             if out_host is None:
                 total = sum(int(g[:, 0].mul(g[:, 1]).mul(g[:, 2]).sum()) // self.visual.spatial_merge_unit for g in grids)
-                est = total * len(groups)            # same-size chunks; grows below if the guess was short
+                est = (total // len(imgs) + 1) * len(host_images) * 2        # generous: crops may differ in size
                 out_host = torch.empty((est, emb.shape[1]), dtype=emb.dtype).pin_memory()
             done = torch.cuda.Event()
             done.record(compute)
