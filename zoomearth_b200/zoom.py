@@ -80,9 +80,8 @@ class ZoomEncoder:
             launches += self.last_launches
             grids.append(grid)
             if out_host is None:
-                total = sum(int(g[:, 0].mul(g[:, 1]).mul(g[:, 2]).sum()) // self.visual.spatial_merge_unit for g in grids)
-                est = (total // len(imgs) + 1) * len(host_images) * 2        # generous: crops may differ in size
-                out_host = torch.empty((est, emb.shape[1]), dtype=emb.dtype).pin_memory()
+                tokens = sum(self.processor.get_number_of_image_patches(int(h.shape[0]), int(h.shape[1])) for h in host_images)
+                out_host = torch.empty((tokens // self.visual.spatial_merge_unit, emb.shape[1]), dtype=emb.dtype).pin_memory()
             done = torch.cuda.Event()
             done.record(compute)
             with torch.cuda.stream(self._d2h_stream):
