@@ -201,6 +201,146 @@ __global__ void __launch_bounds__(32 * NW) attn_kernel(const __nv_bfloat16* __re
   }
 }
 
+// Window layers: every segment fits one 64-row tile, so there is no online softmax; the kernel is persistent and
+// software-pipelined over (window, head) items: while item i is in the tensor cores, the Q/K/V tiles of item i+1 are
+// already streaming into the other shared-memory set with cp.async, so the kernel runs at memory speed instead of
+// paying the load latency once per CTA.
+template <bool F16>
+__global__ void __launch_bounds__(128, 3) attn_window_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+                                                             const int4* __restrict__ tiles, int n_items, int heads,
+                                                             float scale_log2) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __nv_bfloat16* sbase = reinterpret_cast<__nv_bfloat16*>(smem_raw);       // [2 sets][Q, K, V][64][LDS]
+  const int hidden = heads * HD;
+  const int64_t ld = 3 * (int64_t)hidden;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int mi = lane >> 3, r8 = lane & 7;
+
+  auto issue_loads = [&](int item, int set) {
+    const int4 tl = tiles[item / heads];
+    const int head = item % heads;
+    const int len = tl.w - tl.z;                                          // windows: q rows == kv rows == the segment
+    __nv_bfloat16* s = sbase + set * 3 * kTileElems;
+    const __nv_bfloat16* gq = qkv + (int64_t)tl.z * ld + head * HD;
+    load_tile(s, gq, ld, len, 64);
+    load_tile(s + kTileElems, gq + hidden, ld, len, 64);
+    load_tile(s + 2 * kTileElems, gq + 2 * hidden, ld, len, 64);
+    cp_async_commit();
+  };
+
+  int item = blockIdx.x;
+  if (item >= n_items) return;
+  issue_loads(item, 0);
+  for (int it = 0; item < n_items; item += gridDim.x, ++it) {
+    const int set = it & 1;
+    const int next = item + gridDim.x;
+    if (next < n_items) { issue_loads(next, set ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncthreads();
+    const int4 tl = tiles[item / heads];
+    const int head = item % heads;
+    const int len = tl.w - tl.z;
+    __nv_bfloat16* sQ = sbase + set * 3 * kTileElems;
+    const __nv_bfloat16* k = sQ + kTileElems;
+    const __nv_bfloat16* v = sQ + 2 * kTileElems;
+    float s[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+#pragma unroll
+    for (int ks = 0; ks < 5; ++ks) {
+      uint32_t qf[4];
+      ldsm_x4(qf, sQ + (16 * warp + (mi & 1) * 8 + r8) * LDS + 16 * ks + (mi >> 1) * 8);
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t b[4];
+        ldsm_x4(b, k + (16 * np + (mi >> 1) * 8 + r8) * LDS + 16 * ks + (mi & 1) * 8);
+        mma_16<F16>(s[2 * np], qf, b[0], b[1]);
+        mma_16<F16>(s[2 * np + 1], qf, b[2], b[3]);
+      }
+    }
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = 8 * i + 2 * t;
+      if (c >= len) { s[i][0] = -INFINITY; s[i][2] = -INFINITY; }
+      if (c + 1 >= len) { s[i][1] = -INFINITY; s[i][3] = -INFINITY; }
+      mx0 = fmaxf(mx0, fmaxf(s[i][0], s[i][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[i][2], s[i][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float ms0 = mx0 * scale_log2, ms1 = mx1 * scale_log2;
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s[i][0] = exp2f(s[i][0] * scale_log2 - ms0); s[i][1] = exp2f(s[i][1] * scale_log2 - ms0);
+      s[i][2] = exp2f(s[i][2] * scale_log2 - ms1); s[i][3] = exp2f(s[i][3] * scale_log2 - ms1);
+      l0 += s[i][0] + s[i][1];
+      l1 += s[i][2] + s[i][3];
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    float o[10][4];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t a[4];
+      a[0] = pack_16<F16>(s[2 * kk][0], s[2 * kk][1]);
+      a[1] = pack_16<F16>(s[2 * kk][2], s[2 * kk][3]);
+      a[2] = pack_16<F16>(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      a[3] = pack_16<F16>(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+      for (int np = 0; np < 5; ++np) {
+        uint32_t b[4];
+        ldsm_x4_trans(b, v + (16 * kk + (mi & 1) * 8 + r8) * LDS + 8 * (2 * np + (mi >> 1)));
+        mma_16<F16>(o[2 * np], a, b[0], b[1]);
+        mma_16<F16>(o[2 * np + 1], a, b[2], b[3]);
+      }
+    }
+    // this warp's 16 output rows: stage over its own (already consumed) Q rows, then 16-byte stores
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+    __nv_bfloat16* so = sQ + 16 * warp * LDS;
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      *reinterpret_cast<uint32_t*>(so + g * LDS + 8 * i + 2 * t) = pack_16<F16>(o[i][0] * i0, o[i][1] * i0);
+      *reinterpret_cast<uint32_t*>(so + (g + 8) * LDS + 8 * i + 2 * t) = pack_16<F16>(o[i][2] * i1, o[i][3] * i1);
+    }
+    __syncwarp();
+    for (int i = lane; i < 16 * 10; i += 32) {
+      const int r = i / 10, c = i % 10;
+      const int row = 16 * warp + r;
+      if (row < len)
+        *reinterpret_cast<uint4*>(out + (int64_t)(tl.z + row) * hidden + head * HD + c * 8) =
+            *reinterpret_cast<const uint4*>(so + r * LDS + c * 8);
+    }
+    __syncthreads();        // everyone is done with this set before the next iteration prefetches into it
+  }
+}
+
+template <bool F16>
+int launch_window(const void* qkv, void* out, int heads, const int32_t* tiles_dev, int n_tiles, float scale_log2, void* stream_) {
+  constexpr int kSmem = 2 * 3 * kTileElems * 2;
+  static bool attr_set = false;
+  static int n_sm = 0;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_window_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (e != cudaSuccess) return fail(ZV_ECUDA, "attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    attr_set = true;
+  }
+  const int n_items = n_tiles * heads;
+  const int grid = n_items < 3 * n_sm ? n_items : 3 * n_sm;
+  KernelTimer timer(KC_ATTN_WINDOW, stream_);
+  attn_window_kernel<F16><<<grid, 128, kSmem, static_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), reinterpret_cast<const int4*>(tiles_dev),
+      n_items, heads, scale_log2);
+  return ZV_OK;
+}
+
 template <int NW, bool F16>
 int launch_attn(const void* qkv, void* out, int heads, const int32_t* tiles_dev, int n_tiles, float scale_log2,
                 void* stream_, int cls) {
@@ -229,10 +369,10 @@ int attention(const void* qkv, void* out, int heads, int head_dim, const int32_t
   int rc;
   if (f16)
     rc = full_layer ? launch_attn<8, true>(qkv, out, heads, tiles_dev, n_tiles, scale_log2, stream_, KC_ATTN_FULL)
-                    : launch_attn<4, true>(qkv, out, heads, tiles_dev, n_tiles, scale_log2, stream_, KC_ATTN_WINDOW);
+                    : launch_window<true>(qkv, out, heads, tiles_dev, n_tiles, scale_log2, stream_);
   else
     rc = full_layer ? launch_attn<8, false>(qkv, out, heads, tiles_dev, n_tiles, scale_log2, stream_, KC_ATTN_FULL)
-                    : launch_attn<4, false>(qkv, out, heads, tiles_dev, n_tiles, scale_log2, stream_, KC_ATTN_WINDOW);
+                    : launch_window<false>(qkv, out, heads, tiles_dev, n_tiles, scale_log2, stream_);
   if (rc) return rc;
   count_launch();
   cudaError_t e = cudaGetLastError();
