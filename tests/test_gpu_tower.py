@@ -115,7 +115,9 @@ def test_zoom_step_end_to_end(cuda):
 
 
 def test_encode_host_pipeline_matches_resident_path(cuda):
-    """The chunked host pipeline (H2D / compute / D2H on three streams) returns exactly what the resident path does."""
+    """The chunked host pipeline (H2D / compute / D2H on three streams) returns what the resident path does.  Not
+    bitwise: the full-attention kernel aligns its K/V tiles to 8 rows of the batch, so a segment's tile split (and
+    with it the rounding of the online softmax) depends on where the segment starts in the batch."""
     from zoomearth_b200 import FusedImageProcessor, ZoomEncoder
     cfg = OT.small_cfg(depth=2, fullatt=(1,))
     sd = OT.make_weights(4, cfg)
@@ -126,4 +128,6 @@ def test_encode_host_pipeline_matches_resident_path(cuda):
     out, grid = enc.encode_host(host, chunk=2)
     ref, rgrid, _ = enc.encode([h.to(cuda) for h in host], None)
     assert grid.tolist() == rgrid.tolist()
-    assert torch.equal(out, ref.cpu())
+    assert out.shape == ref.shape
+    cos, maxrel = _metrics(out, ref)
+    assert cos >= 0.9999 and maxrel <= 4e-3, f"cos {cos} maxrel {maxrel}"
