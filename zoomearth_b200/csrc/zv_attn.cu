@@ -14,6 +14,7 @@
 
 #include "zv_common.h"
 #include "zv_gemm.h"
+#include "zv_ptx.cuh"
 
 namespace zv {
 namespace {
@@ -24,7 +25,7 @@ constexpr int LDS = 88;         // smem row pitch in elements (176 B: conflict-f
 constexpr int kTileElems = 64 * LDS;
 template <int NW> constexpr int smem_bytes() { return (16 * NW + (NW == 4 ? 2 : 4) * 64) * LDS * 2; }   // Q + (K, V) x 1 (windows) or x 2 (long segments)
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+using ptx::smem_u32;
 __device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
   const int n = valid ? 16 : 0;   // src-size 0 => 16 bytes of zeros
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(n) : "memory");
@@ -148,14 +149,14 @@ __global__ void __launch_bounds__(32 * NW) attn_kernel(const __nv_bfloat16* __re
     }
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    const float c0 = exp2f((m0 - mx0) * scale_log2), c1 = exp2f((m1 - mx1) * scale_log2);
+    const float c0 = ptx::ex2_approx((m0 - mx0) * scale_log2), c1 = ptx::ex2_approx((m1 - mx1) * scale_log2);
     m0 = mx0; m1 = mx1;
     const float ms0 = mx0 * scale_log2, ms1 = mx1 * scale_log2;
     float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      s[i][0] = exp2f(s[i][0] * scale_log2 - ms0); s[i][1] = exp2f(s[i][1] * scale_log2 - ms0);
-      s[i][2] = exp2f(s[i][2] * scale_log2 - ms1); s[i][3] = exp2f(s[i][3] * scale_log2 - ms1);
+      s[i][0] = ptx::ex2_approx(s[i][0] * scale_log2 - ms0); s[i][1] = ptx::ex2_approx(s[i][1] * scale_log2 - ms0);
+      s[i][2] = ptx::ex2_approx(s[i][2] * scale_log2 - ms1); s[i][3] = ptx::ex2_approx(s[i][3] * scale_log2 - ms1);
       rs0 += s[i][0] + s[i][1];
       rs1 += s[i][2] + s[i][3];
     }
@@ -273,8 +274,8 @@ __global__ void __launch_bounds__(128, 3) attn_window_kernel(const __nv_bfloat16
     float l0 = 0.f, l1 = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      s[i][0] = exp2f(s[i][0] * scale_log2 - ms0); s[i][1] = exp2f(s[i][1] * scale_log2 - ms0);
-      s[i][2] = exp2f(s[i][2] * scale_log2 - ms1); s[i][3] = exp2f(s[i][3] * scale_log2 - ms1);
+      s[i][0] = ptx::ex2_approx(s[i][0] * scale_log2 - ms0); s[i][1] = ptx::ex2_approx(s[i][1] * scale_log2 - ms0);
+      s[i][2] = ptx::ex2_approx(s[i][2] * scale_log2 - ms1); s[i][3] = ptx::ex2_approx(s[i][3] * scale_log2 - ms1);
       l0 += s[i][0] + s[i][1];
       l1 += s[i][2] + s[i][3];
     }

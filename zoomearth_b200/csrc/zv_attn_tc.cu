@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const __grid_const
       const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const bool grow = (mx - m_used) * sl2 > 8.0f;          // true on the first tile (m_used = -inf)
       float factor = 1.0f;
-      if (grow) { factor = exp2f((m_used - mx) * sl2); m_used = mx; l *= factor; }
+      if (grow) { factor = ex2_approx((m_used - mx) * sl2); m_used = mx; l *= factor; }
       if (j > 0) {
         mbar_wait(pv_done, (j - 1) & 1);                     // P buffer free, O_{j-1} accumulated
         if (__any_sync(0xffffffffu, grow)) {
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const __grid_const
       uint32_t pk[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const float p0 = exp2f(s[2 * i] * sl2 - ms), p1 = exp2f(s[2 * i + 1] * sl2 - ms);
+        const float p0 = ex2_approx(s[2 * i] * sl2 - ms), p1 = ex2_approx(s[2 * i + 1] * sl2 - ms);
         rs4[i & 3] += p0 + p1;
         pk[i] = pack2(p0, p1, f16);
       }

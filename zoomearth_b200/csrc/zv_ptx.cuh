@@ -37,17 +37,33 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes or ~hint ns pass, so a
+// waiting role warp does not burn the issue slots of the warps that share its scheduler.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a pipeline bug must surface as a trapped launch, never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {   // ~2 s at 2 GHz
+  for (uint32_t spins = 0; !mbar_try_wait_hint(bar, parity, 20000u); ++spins) {
+    if (spins > 4000000u) {               // >= seconds even if the hint is ignored
       printf("zoomvit: mbarrier wait timed out (block %d thread %d bar %p parity %u)\n", blockIdx.x, threadIdx.x,
              (void*)bar, parity);
       __trap();
     }
   }
+}
+// 2^x on the SFU, one MUFU.EX2 (exp2f() adds a range check and two scalings per call)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 // ---------------------------------------------------------------- TMA
