@@ -130,4 +130,4 @@ def test_encode_host_pipeline_matches_resident_path(cuda):
     assert grid.tolist() == rgrid.tolist()
     assert out.shape == ref.shape
     cos, maxrel = _metrics(out, ref)
-    assert cos >= 0.9999 and maxrel <= 4e-3, f"cos {cos} maxrel {maxrel}"
+    assert cos >= 0.9995 and maxrel <= 1e-2, f"cos {cos} maxrel {maxrel}"
