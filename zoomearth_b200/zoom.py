@@ -70,13 +70,15 @@ class ZoomEncoder:
         staged.append(stage(groups[0]))
         grids, row, launches, keep = [], 0, 0, []
         for i in range(len(groups)):
-            if i + 1 < len(groups):
-                staged.append(stage(groups[i + 1]))
             imgs, ev = staged[i]
             compute.wait_event(ev)
             for t in imgs:
                 t.record_stream(compute)
             emb, grid, _ = self.encode(imgs, None)
+            # stage the next chunk only now: the small table uploads of this chunk's kernels must not queue behind a
+            # gigabyte of pixels on the host-to-device copy engine
+            if i + 1 < len(groups):
+                staged.append(stage(groups[i + 1]))
             launches += self.last_launches
             grids.append(grid)
             if out_host is None:
