@@ -78,7 +78,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int m_blk, int n_b
   const int row = m_blk * BM + row_local;
   const bool valid = row < g.M;
   const bool of16 = g.out_dtype == ZV_F16;
-  if constexpr (EPI != EPI_RESID && EPI != EPI_QKV_ROPE) wait_accumulator();
+  if constexpr (EPI != EPI_RESID) wait_accumulator();
   if constexpr (EPI == EPI_RESID) {
     // X(fp32) += acc + bias, coalesced: the accumulator chunk (32 rows x 32 columns per warp, one row per thread)
     // is transposed through shared memory so that a warp instruction touches 4 rows x 128 contiguous bytes of X
@@ -219,13 +219,6 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int m_blk, int n_b
     if (valid) { ph = __ldg(g.pos + 2 * row); pw = __ldg(g.pos + 2 * row + 1); }
     const float2* rope_h = g.rope + (int64_t)ph * 20;
     const float2* rope_w = g.rope + (int64_t)pw * 20;
-    // the row's rotary table lines and the tile's bias go to L1 while the MMAs of this tile are still running
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(rope_h));
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(rope_h + 16));
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(rope_w));
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(rope_w + 16));
-    if ((row_local & 31) < 8) asm volatile("prefetch.global.L1 [%0];" ::"l"(g.bias + n_blk * 240 + (row_local & 31) * 32));
-    wait_accumulator();
     const bool rot_heads_possible = n_blk * 3 < 2 * g.heads;
     if (half == 0) {
       constexpr int NP = 24;
