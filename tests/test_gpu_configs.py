@@ -1,0 +1,157 @@
+"""BASELINE.json configs as parity cases (GPU, through the C ABI), at sizes the CPU oracle finishes in seconds, plus
+size-independent properties at the full sizes."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import geometry as OG, processor as OP, tower as OT
+
+pytestmark = pytest.mark.gpu
+
+
+def _metrics(got, ref):
+    got, ref = got.float().cpu(), ref.float().cpu()
+    cos = torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0).item()
+    return cos, ((got - ref).abs().max() / ref.abs().max()).item()
+
+
+def _encoder(cuda, cfg, sd, max_pixels, operand_dtype=torch.float16):
+    from zoomearth_b200 import FusedImageProcessor, FusedVisual, ZoomEncoder
+    fv = FusedVisual(sd, device=cuda, dtype=torch.float32, operand_dtype=operand_dtype, depth=cfg["depth"],
+                     fullatt=list(cfg["fullatt"]))
+    return ZoomEncoder(fv, FusedImageProcessor(min_pixels=3136, max_pixels=max_pixels, device=cuda))
+
+
+def test_config1_one_zoom_step_on_5000px_image(cuda):
+    """configs[0]: one synthetic 5000x5000 image, bbox (1000,1200,2300,2100), max_pixels 12845056 ->
+    crop 1300x900 -> 896x1288 -> grid (1,64,92), 5888 patches; 4-block tower vs the fp32 oracle."""
+    cfg = OT.small_cfg(depth=4, fullatt=(1, 3))
+    sd = OT.make_weights(11, cfg)
+    img = np.random.default_rng(0).integers(0, 256, (5000, 5000, 3), dtype=np.uint8)
+    enc = _encoder(cuda, cfg, sd, 12845056)
+    emb, grid, crop = enc.encode([enc.upload(img)], [(1000, 1200, 2300, 2100)])
+    assert tuple(int(v) for v in crop[0]) == (1000, 1200, 2300, 2100) and grid.tolist() == [[1, 64, 92]]
+    _, pv, rgrid = OP.zoom_step_u8(img, (1000, 1200, 2300, 2100), 512, 3136, 12845056)
+    ref = OT.forward(sd, torch.from_numpy(pv), rgrid, cfg)
+    cos, maxrel = _metrics(emb, ref)
+    assert emb.shape == (1472, 2048) and cos >= 0.999 and maxrel <= 1e-2, f"cos {cos} maxrel {maxrel}"
+
+
+def test_config3_nested_zoom_trajectory_ragged(cuda):
+    """configs[2] in miniature: per question three nested boxes through cut_image (min 512), one ragged batch per zoom
+    depth mixing crop sizes; boxes, grids and embeddings against the oracle."""
+    cfg = OT.small_cfg(depth=2, fullatt=(1,))
+    sd = OT.make_weights(12, cfg)
+    enc = _encoder(cuda, cfg, sd, 401408)
+    imgs = [np.random.default_rng(100 + q).integers(0, 256, (1800, 2200, 3), dtype=np.uint8) for q in range(3)]
+    dev = [enc.upload(i) for i in imgs]
+    for depth in range(3):
+        boxes = []
+        for q in range(3):
+            rng = np.random.default_rng(1000 + q)
+            x0, y0, w, h = 0, 0, 2200, 1800
+            for d in range(depth + 1):
+                lo, hi = [(900, 1700), (450, 900), (120, 450)][d]
+                nw, nh = int(rng.integers(lo, min(hi, w))), int(rng.integers(lo, min(hi, h)))
+                x0, y0 = x0 + int(rng.integers(0, w - nw + 1)), y0 + int(rng.integers(0, h - nh + 1))
+                w, h = nw, nh
+            boxes.append((x0, y0, x0 + w, y0 + h))
+        emb, grid, crop = enc.encode(dev, boxes, image_index=[0, 1, 2])
+        rows, grids = [], []
+        for q, b in enumerate(boxes):
+            box, pv, g = OP.zoom_step_u8(imgs[q], b, 512, 3136, 401408)
+            assert tuple(int(v) for v in crop[q]) == box
+            rows.append(pv)
+            grids.append(g)
+        rgrid = np.concatenate(grids, 0)
+        assert grid.tolist() == rgrid.tolist()
+        ref = OT.forward(sd, torch.from_numpy(np.concatenate(rows, 0)), rgrid, cfg)
+        cos, maxrel = _metrics(emb, ref)
+        assert cos >= 0.999 and maxrel <= 1e-2, f"depth {depth}: cos {cos} maxrel {maxrel}"
+
+
+def test_config4_mixed_crops_batch_equals_per_crop(cuda):
+    """configs[3] property: a ragged batch of mixed-size crops gives, crop by crop, what each crop gives alone
+    (crops are independent sequences - the basis of sharding by crop), and the LPT partition covers every crop once."""
+    from zoomearth_b200 import sharding
+    cfg = OT.small_cfg(depth=2, fullatt=(0,))
+    sd = OT.make_weights(13, cfg)
+    enc = _encoder(cuda, cfg, sd, 12845056, operand_dtype=torch.bfloat16)
+    img = np.random.default_rng(4).integers(0, 256, (2400, 2400, 3), dtype=np.uint8)
+    dev = enc.upload(img)
+    rng = np.random.default_rng(4)
+    boxes = []
+    for _ in range(10):
+        w, h = int(rng.integers(256, 1400)), int(rng.integers(256, 1400))
+        x, y = int(rng.integers(0, 2400 - w)), int(rng.integers(0, 2400 - h))
+        boxes.append((x, y, x + w, y + h))
+    emb, grid, crop = enc.encode([dev], boxes, image_index=[0] * 10)
+    tokens = enc.tokens_per_crop(grid.numpy())
+    starts = np.concatenate([[0], np.cumsum(tokens)])
+    for i in (0, 3, 9):
+        e1, g1, _ = enc.encode([dev], [boxes[i]], image_index=[0])
+        assert g1.tolist() == [grid[i].tolist()]
+        cos, maxrel = _metrics(emb[starts[i]:starts[i + 1]], e1)
+        assert cos >= 0.9995 and maxrel <= 1e-2, f"crop {i}: cos {cos} maxrel {maxrel}"
+    parts = sharding.partition(sharding.crop_cost(grid.numpy()), 4)
+    assert sorted(i for p in parts for i in p) == list(range(10))
+
+
+def test_config5_max_resolution_crop(cuda):
+    """configs[4]: a 3584x3584 crop at max_pixels = 16384*28*28 -> grid (1,256,256), 65 536 patches, one full-attention
+    segment of 65 536.  Too large for the CPU oracle; checked through properties: geometry bit-exact, patches bit-exact
+    against live Pillow on a sampled set of rows, embeddings finite, and the first-window embeddings equal those of a
+    run where the tower sees the same patches in HF order (gather path) instead of the fused window order."""
+    from PIL import Image
+    cfg = OT.small_cfg(depth=2, fullatt=(1,))
+    sd = OT.make_weights(14, cfg)
+    enc = _encoder(cuda, cfg, sd, 16384 * 28 * 28, operand_dtype=torch.bfloat16)
+    img = np.random.default_rng(5).integers(0, 256, (3700, 3700, 3), dtype=np.uint8)
+    box = (50, 60, 3634, 3644)
+    dev = enc.upload(img)
+    emb, grid, crop, pv = enc.encode([dev], [box], return_patches=True)
+    assert grid.tolist() == [[1, 256, 256]] and emb.shape == (16384, 2048)
+    assert OG.smart_resize(3584, 3584, 28, 3136, 16384 * 28 * 28) == (3584, 3584)
+    assert torch.isfinite(emb).all()
+    # same-size crop: Pillow copies the pixels; window-ordered bf16 patches must equal the LUT of the raw crop
+    cropped = np.asarray(Image.fromarray(img).crop(box))
+    lut = OP.normalize_lut()
+    ref_pv, _ = OP.patchify(np.stack([lut[c][cropped[:, :, c]] for c in range(3)], 0))
+    widx, _ = OT.window_index(np.array([[1, 256, 256]]))
+    ref_w = torch.from_numpy(ref_pv).view(-1, 4, 1176)[torch.from_numpy(widx)].reshape(-1, 1176).to(torch.bfloat16)
+    assert torch.equal(pv.cpu(), ref_w)
+    emb_hf = enc.visual(torch.from_numpy(ref_pv).to(cuda), grid)            # fp32 patches, HF order -> gather path
+    cos, maxrel = _metrics(emb, emb_hf)
+    assert cos >= 0.9999 and maxrel <= 5e-3, f"cos {cos} maxrel {maxrel}"
+
+
+def test_install_swaps_hf_visual_and_matches_it(cuda):
+    """Drop-in through HF's own call path: install() replaces model.visual of a (tiny-LM) Qwen2.5-VL model; the HF
+    get_image_features() then returns what the original HF tower returned, within the stated tolerance."""
+    import transformers
+    from transformers import Qwen2_5_VLConfig, Qwen2_5_VLForConditionalGeneration
+    from zoomearth_b200 import install
+    vis = dict(depth=2, hidden_size=1280, intermediate_size=3420, num_heads=16, out_hidden_size=2048, patch_size=14,
+               spatial_merge_size=2, temporal_patch_size=2, window_size=112, fullatt_block_indexes=[1], hidden_act="silu")
+    text = dict(hidden_size=2048, intermediate_size=256, num_hidden_layers=1, num_attention_heads=16, num_key_value_heads=2,
+                vocab_size=152064, max_position_embeddings=4096,
+                rope_parameters={"rope_type": "default", "mrope_section": [16, 24, 24], "rope_theta": 1000000.0})
+    try:
+        config = Qwen2_5_VLConfig(vision_config=vis, text_config=text)
+    except Exception as e:                       # config schema differs across transformers majors
+        pytest.skip(f"cannot build a tiny Qwen2_5_VLConfig on transformers {transformers.__version__}: {e}")
+    torch.manual_seed(0)
+    model = Qwen2_5_VLForConditionalGeneration(config).eval()
+    owner = model if hasattr(model, "visual") else model.model
+    hf_visual = owner.visual
+    grid = torch.tensor([[1, 16, 20], [1, 8, 8]])
+    pv = torch.randn(int((grid[:, 1] * grid[:, 2]).sum()), 1176, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        ref = hf_visual(pv, grid_thw=grid)
+    ref = ref.pooler_output if hasattr(ref, "pooler_output") else ref
+    fv, _ = install(model, device=cuda, dtype=torch.float32)
+    assert owner.visual is fv and fv.dtype == torch.float32 and fv.spatial_merge_size == 2
+    out = owner.visual(pv.to(cuda), grid_thw=grid)
+    out = out.pooler_output if hasattr(out, "pooler_output") else out
+    cos, maxrel = _metrics(out, ref)
+    assert cos >= 0.999 and maxrel <= 1e-2, f"cos {cos} maxrel {maxrel}"
