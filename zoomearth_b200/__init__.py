@@ -19,7 +19,7 @@ def __getattr__(name):            # torch-dependent pieces are imported lazily
         from .zoom import ZoomEncoder
         return ZoomEncoder
     if name == "install":
-        from .install import install
+        from .dropin import install
         return install
     if name == "Plan":
         from .plan import Plan
