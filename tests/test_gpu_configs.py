@@ -155,3 +155,30 @@ def test_install_swaps_hf_visual_and_matches_it(cuda):
     out = out.pooler_output if hasattr(out, "pooler_output") else out
     cos, maxrel = _metrics(out, ref)
     assert cos >= 0.999 and maxrel <= 1e-2, f"cos {cos} maxrel {maxrel}"
+
+
+def test_zoom_session_caches_global_view_and_batches_crops(cuda):
+    """ZoomSession: stage 1 is computed once per image; stage 2 returns, per question, the [global, crop] pair the
+    reference hands the model, equal to encoding them directly."""
+    from zoomearth_b200 import ZoomSession
+    cfg = OT.small_cfg(depth=2, fullatt=(1,))
+    sd = OT.make_weights(15, cfg)
+    enc = _encoder(cuda, cfg, sd, 200704, operand_dtype=torch.bfloat16)
+    sess = ZoomSession(enc)
+    imgs = {k: np.random.default_rng(50 + i).integers(0, 256, (900 + 100 * i, 1200, 3), dtype=np.uint8)
+            for i, k in enumerate("ab")}
+    for k, im in imgs.items():
+        sess.add_image(k, im)
+    e1, g1 = sess.stage1(["a", "b"])
+    launches = enc.last_launches
+    e1b, _ = sess.stage1(["b", "a"])
+    assert e1b[0].data_ptr() == e1[1].data_ptr() and enc.last_launches == launches      # served from the cache
+    keys, boxes = ["a", "b", "a"], [(100, 100, 700, 600), (50.5, 60.2, 300.0, 200.9), (400, 300, 1100, 880)]
+    out, crop = sess.stage2(keys, boxes)
+    assert len(out) == 3
+    for (embs, grid), k, b, c in zip(out, keys, boxes, crop):
+        assert tuple(int(v) for v in c) == sess.crop_box(k, b) == OG.cut_box(1200, imgs[k].shape[0], b)
+        ref, rgrid, _ = enc.encode([sess.add_image(k, None)], [b], image_index=[0])
+        assert grid[1].tolist() == rgrid[0].tolist() and embs[0].shape[0] * 4 == int(grid[0, 1] * grid[0, 2])
+        cos, maxrel = _metrics(embs[1], ref)
+        assert cos >= 0.9995 and maxrel <= 1e-2

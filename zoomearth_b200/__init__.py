@@ -18,6 +18,9 @@ def __getattr__(name):            # torch-dependent pieces are imported lazily
     if name == "ZoomEncoder":
         from .zoom import ZoomEncoder
         return ZoomEncoder
+    if name == "ZoomSession":
+        from .session import ZoomSession
+        return ZoomSession
     if name == "install":
         from .dropin import install
         return install
