@@ -36,6 +36,9 @@ sys.path.insert(0, ROOT)
 IMG = 5000
 MAX_PIXELS = 1280 * 28 * 28
 MIN_PIXELS = 56 * 56
+# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the four per-block GEMMs at this exact
+# workload (64 images, M = 313 600), from the ncu capture committed as profiles/r01_ncu_traffic_gemm_64img.csv
+NCU_TRAFFIC_GB = {"gemm_qkv": 3.77, "gemm_proj": 4.23, "gemm_swiglu": 3.42, "gemm_down": 6.82}
 KCLASS = {"k1_hpass": 0, "k1_vpass": 1, "gemm_store": 2, "gemm_qkv": 3, "gemm_resid": 4, "gemm_swiglu": 5,
           "gemm_gelu": 6, "gemm_scatter": 7, "attn_window": 8, "attn_full": 9, "rmsnorm": 10, "gather": 11}
 
@@ -295,8 +298,10 @@ def run_ours(args):
             "roofline": {"bound": "tensor", "kernel": "gemm_tc (tcgen05, all epilogues)", "achieved": gemm_tf,
                          "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": gemm_tf / pk["tf_sust"],
                          "frac_of_burst": gemm_tf / pk["tf_burst"], "peak_source": pk["src"] + ", sustained",
-                         "traffic": None, "launches": gemm_n, "ms_total": gemm_ms,
-                         "share_of_step": gemm_ms / ms},
+                         "traffic": (sum(NCU_TRAFFIC_GB.values()) * 32 / 128 * 1e9) if n_img == 64 else None,
+                         "traffic_note": "mean DRAM bytes per launch over the 128 per-block GEMM launches, ncu at this "
+                                         "workload (profiles/r01_ncu_traffic_gemm_64img.csv); algorithmic mean 3.9e9",
+                         "launches": gemm_n, "ms_total": gemm_ms, "share_of_step": gemm_ms / ms},
             "roofline_k1": {"bound": "hbm", "kernel": "k1_hpass + k1_vpass", "achieved": k1_gbs, "peak": pk["hbm"],
                             "unit": "GB/s", "frac": k1_gbs / pk["hbm"], "ms_total": k1_ms, "share_of_step": k1_ms / ms,
                             "traffic": None},
