@@ -28,12 +28,13 @@ namespace {
 
 constexpr int HD = 80, BQ = 128, BKV = 64, STAGES = 3;
 constexpr int kQ64 = BQ * 64 * 2, kQ16 = BQ * 16 * 2;                   // 16384, 4096
-constexpr int kK64 = BKV * 64 * 2, kK16 = BKV * 16 * 2, kVt = HD * BKV * 2;   // 8192, 2048, 10240
-constexpr int kStage = kK64 + kK16 + kVt;                                // 20480
+constexpr int VROWS = 96;                                                 // V^T rows in smem: 80 head dims, a row of ones, 15 zero rows
+constexpr int kK64 = BKV * 64 * 2, kK16 = BKV * 16 * 2, kVtTma = HD * BKV * 2, kVt = VROWS * BKV * 2;   // 8192, 2048, 10240, 12288
+constexpr int kStage = kK64 + kK16 + kVt;                                // 22528
 constexpr int kP = BQ * BKV * 2;                                         // 16384
 constexpr int kOffQ16 = kQ64, kOffStage = kQ64 + kQ16, kOffP = kOffStage + STAGES * kStage, kOffBar = kOffP + kP;
 constexpr int kSmem = kOffBar + 256 + 1024;
-constexpr int kTmemCols = 256;                                           // S0 [0,64) S1 [64,128) O [128,208)
+constexpr int kTmemCols = 256;                                           // S0 [0,64) S1 [64,128) O [128,224): 80 dims + row sum
 constexpr int kThreads = 192;
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout) {
@@ -54,8 +55,9 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ uint32_t pack2(float a, float b, bool f16) {
-  if (f16) { __half2 v = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&v); }
+template <bool F16>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  if constexpr (F16) { __half2 v = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&v); }
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
@@ -67,6 +69,7 @@ struct AttnArgs {
   float scale_log2;
 };
 
+template <bool F16>
 __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qk64,
                                                               const __grid_constant__ CUtensorMap tm_qk16,
                                                               const __grid_constant__ CUtensorMap tm_vt, const AttnArgs a) {
@@ -102,6 +105,15 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const __grid_const
     fence_mbar_init();
   }
   if (warp == 0) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
+  // rows 80..95 of every V^T stage: a row of ones (so that column 80 of O = P [V | 1] is the softmax row sum, computed
+  // by the tensor core from the same rounded P that multiplies V) and zero rows; constant rows are swizzle-invariant
+  for (int i = threadIdx.x; i < STAGES * 16 * 8; i += kThreads) {
+    const int st = i / 128, r = (i % 128) / 8, c = i % 8;
+    const uint32_t one2 = F16 ? 0x3C003C00u : 0x3F803F80u;
+    const uint32_t v = r == 0 ? one2 : 0u;
+    *reinterpret_cast<uint4*>(smem + kOffStage + st * kStage + kK64 + kK16 + (HD + r) * 128 + c * 16) = make_uint4(v, v, v, v);
+  }
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -126,15 +138,15 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const __grid_const
         tma_load_2d(sk, &tm_qk64, k_full + st, colk, row);
         tma_load_2d(sk + kK64, &tm_qk16, k_full + st, colk + 64, row);
         mbar_wait(v_empty + st, ph ^ 1);
-        mbar_arrive_expect_tx(v_full + st, kVt);
+        mbar_arrive_expect_tx(v_full + st, kVtTma);
         tma_load_2d(sk + kK64 + kK16, &tm_vt, v_full + st, row, head * HD);
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {
       // ---- MMA issuer
-      const uint32_t idesc_qk = umma_idesc_16bit(BQ, BKV, a.f16 != 0);
-      const uint32_t idesc_pv = umma_idesc_16bit(BQ, HD, a.f16 != 0);
+      const uint32_t idesc_qk = umma_idesc_16bit(BQ, BKV, F16);
+      const uint32_t idesc_pv = umma_idesc_16bit(BQ, VROWS, F16);
       const uint32_t sq = smem_u32(smem), sq16 = smem_u32(smem + kOffQ16), sp = smem_u32(smem + kOffP);
       auto issue_qk = [&](int t) {
         const int st = t % STAGES;
@@ -174,9 +186,8 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const __grid_const
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    const bool f16 = a.f16 != 0;
     const float sl2 = a.scale_log2;
-    float m_used = -INFINITY, l = 0.f;      // scale in use (raw score units) and the row sum in that scale
+    float m_used = -INFINITY;               // scale in use (raw score units); the row sum lives in O column 80
     uint8_t* prow = smem + kOffP + row * 128;
 
     for (int j = 0; j < n_kv; ++j) {
@@ -206,13 +217,13 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const __grid_const
       const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const bool grow = (mx - m_used) * sl2 > 8.0f;          // true on the first tile (m_used = -inf)
       float factor = 1.0f;
-      if (grow) { factor = ex2_approx((m_used - mx) * sl2); m_used = mx; l *= factor; }
+      if (grow) { factor = ex2_approx((m_used - mx) * sl2); m_used = mx; }
       if (j > 0) {
         mbar_wait(pv_done, (j - 1) & 1);                     // P buffer free, O_{j-1} accumulated
         if (__any_sync(0xffffffffu, grow)) {
           tc_fence_after();
 #pragma unroll
-          for (int c = 0; c < 80; c += 16) {
+          for (int c = 0; c < VROWS; c += 16) {
             uint32_t t[16];
             tmem_ld_x16(tmem + lane_addr + 128 + c, t);
             tmem_ld_wait();
@@ -225,15 +236,9 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const __grid_const
         }
       }
       const float ms = m_used * sl2;
-      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
       uint32_t pk[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float p0 = ex2_approx(s[2 * i] * sl2 - ms), p1 = ex2_approx(s[2 * i + 1] * sl2 - ms);
-        rs4[i & 3] += p0 + p1;
-        pk[i] = pack2(p0, p1, f16);
-      }
-      l += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+      for (int i = 0; i < 32; ++i) pk[i] = pack2<F16>(ex2_approx(s[2 * i] * sl2 - ms), ex2_approx(s[2 * i + 1] * sl2 - ms));
       // P row -> shared memory, K-major 128B swizzle: 16-byte chunk c of row r lives at chunk (c ^ (r & 7))
 #pragma unroll
       for (int c = 0; c < 8; ++c)
@@ -244,7 +249,13 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const __grid_const
     }
     mbar_wait(pv_done, (n_kv - 1) & 1);
     tc_fence_after();
-    const float inv = 1.f / l;
+    float inv;
+    {
+      uint32_t t[16];
+      tmem_ld_x16(tmem + lane_addr + 128 + HD, t);       // column 80 = sum of the row's probabilities
+      tmem_ld_wait();
+      inv = 1.f / __uint_as_float(t[0]);
+    }
     uint16_t* dst = static_cast<uint16_t*>(a.out) + (int64_t)(q0 + row) * a.hidden + head * HD;
 #pragma unroll
     for (int c = 0; c < 80; c += 16) {
@@ -255,10 +266,10 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const __grid_const
 #pragma unroll
         for (int h = 0; h < 2; ++h)
           *reinterpret_cast<uint4*>(dst + c + 8 * h) =
-              make_uint4(pack2(__uint_as_float(t[8 * h]) * inv, __uint_as_float(t[8 * h + 1]) * inv, f16),
-                         pack2(__uint_as_float(t[8 * h + 2]) * inv, __uint_as_float(t[8 * h + 3]) * inv, f16),
-                         pack2(__uint_as_float(t[8 * h + 4]) * inv, __uint_as_float(t[8 * h + 5]) * inv, f16),
-                         pack2(__uint_as_float(t[8 * h + 6]) * inv, __uint_as_float(t[8 * h + 7]) * inv, f16));
+              make_uint4(pack2<F16>(__uint_as_float(t[8 * h]) * inv, __uint_as_float(t[8 * h + 1]) * inv),
+                         pack2<F16>(__uint_as_float(t[8 * h + 2]) * inv, __uint_as_float(t[8 * h + 3]) * inv),
+                         pack2<F16>(__uint_as_float(t[8 * h + 4]) * inv, __uint_as_float(t[8 * h + 5]) * inv),
+                         pack2<F16>(__uint_as_float(t[8 * h + 6]) * inv, __uint_as_float(t[8 * h + 7]) * inv));
       }
     }
     tc_fence_before();
@@ -313,7 +324,8 @@ int attention_tc(const void* qkv, const void* vt, int64_t s_pad, void* out, int6
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (e != cudaSuccess) return fail(ZV_ECUDA, "attention_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -323,7 +335,8 @@ int attention_tc(const void* qkv, const void* vt, int64_t s_pad, void* out, int6
   dim3 grid((unsigned)n_tiles, (unsigned)heads);
   {
     KernelTimer timer(KC_ATTN_FULL, stream_);
-    attn_tc_kernel<<<grid, kThreads, kSmem, static_cast<cudaStream_t>(stream_)>>>(t64, t16, tvt, a);
+    if (f16) attn_tc_kernel<true><<<grid, kThreads, kSmem, static_cast<cudaStream_t>(stream_)>>>(t64, t16, tvt, a);
+    else attn_tc_kernel<false><<<grid, kThreads, kSmem, static_cast<cudaStream_t>(stream_)>>>(t64, t16, tvt, a);
   }
   count_launch();
   cudaError_t e = cudaGetLastError();
