@@ -188,7 +188,28 @@ def run_ours(args):
     S_img, T_img = 4900, 1225
     tokens_step = n_img * T_img
 
+    pg, gather_kind = None, "none"
+    if world > 1:
+        gather_kind = "nccl all_gather_into_tensor"
+        if not args.nccl_gather:
+            try:
+                from zoomearth_b200.sharding import PeerGather
+                pg = PeerGather(world * tokens_step, 2048, torch.bfloat16, dev)
+                gather_kind = "fused: merger GEMM epilogue stores into every rank's buffer over NVLink (symmetric memory)"
+            except Exception as e:          # symmetric memory unavailable on this box: the NCCL collective still gathers
+                pg = None
+                if rank == 0:
+                    print(f"bench.py: fused peer gather unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
+        ok = torch.tensor([1 if pg is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 0 and pg is not None:
+            pg, gather_kind = None, "nccl all_gather_into_tensor"
+
     def step():
+        if pg is not None:
+            enc.encode(images, None, gather=pg, gather_row=rank * tokens_step)
+            pg.barrier()                                   # every rank's rows have landed in every buffer
+            return pg.buffer
         emb, grid, _ = enc.encode(images, None)
         if world > 1:
             out = torch.empty((world * emb.shape[0], emb.shape[1]), dtype=emb.dtype, device=dev)
@@ -292,7 +313,7 @@ def run_ours(args):
                                    "Qwen2.5-VL-3B vision tower (random init)",
                        "images_per_step_per_gpu": n_img, "tokens_per_step_per_gpu": tokens_step,
                        "l2": "inputs larger than L2 (4.8 GB of pixels, 5.5 GB of activations per step)",
-                       "parallelism": f"dp{world} by image, NCCL all-gather of embeddings" if world > 1 else "single GPU"},
+                       "parallelism": f"dp{world} by image; embedding gather: {gather_kind}" if world > 1 else "single GPU"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": e2e,
             "roofline": {"bound": "tensor", "kernel": "gemm_tc (tcgen05, all epilogues)", "achieved": gemm_tf,
@@ -327,6 +348,7 @@ def main():
     ap.add_argument("--e2e-images", type=int, default=64)
     ap.add_argument("--e2e-chunk", type=int, default=16, help="images per pipelined upload/compute chunk in the e2e leg")
     ap.add_argument("--ref-images", type=int, default=1, help="images in the CPU reference sample")
+    ap.add_argument("--nccl-gather", action="store_true", help="gather embeddings with NCCL instead of the fused peer stores")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -144,6 +144,14 @@ ZV_API int zv_visual_forward(const zv_cfg* cfg, const void* weights_dev, const z
                              const void* patches_dev, int32_t in_dtype, int32_t in_order, void* merged_out_dev,
                              int32_t out_dtype, void* hidden_out_dev, void* workspace_dev,
                              int64_t workspace_bytes, void* stream);
+/* Same forward with the embedding gather fused into the last GEMM's epilogue: every output row is also written at
+ * row (peer_row_off + row) of each of the n_peers (<= 8) peer buffers - device pointers into the OTHER ranks' gather
+ * buffers, mapped into this process (CUDA IPC / symmetric memory), element type out_dtype (16-bit), row = out_hidden
+ * elements.  The caller synchronises the ranks afterwards (any barrier); no collective is needed. */
+ZV_API int zv_visual_forward_gather(const zv_cfg* cfg, const void* weights_dev, const zv_plan* p, const void* plan_dev,
+                                    const void* patches_dev, int32_t in_dtype, int32_t in_order, void* merged_out_dev,
+                                    int32_t out_dtype, void* workspace_dev, int64_t workspace_bytes,
+                                    void* const* peer_out_dev, int32_t n_peers, int64_t peer_row_off, void* stream);
 /* Number of kernels the last zv_preprocess / zv_visual_forward call on this thread launched. */
 ZV_API int64_t zv_last_launch_count(void);
 

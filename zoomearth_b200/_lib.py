@@ -68,6 +68,9 @@ _PROTOS = {
     "zv_visual_workspace_bytes": (C.c_int64, [_P(ZvCfg), C.c_void_p]),
     "zv_visual_forward": (C.c_int, [_P(ZvCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                     C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "zv_visual_forward_gather": (C.c_int, [_P(ZvCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                           C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int64,
+                                           C.c_void_p]),
     "zv_last_launch_count": (C.c_int64, []),
     "zv_timing_enable": (None, [C.c_int]),
     "zv_timing_reset": (None, []),

@@ -173,11 +173,23 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int m_blk, int n_b
             o[j] = x;
           }
         } else {
-          uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(g.out) + orow * g.ldo + n0);
+          uint4 pk[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            o[j] = make_uint4(pack2(v[8 * j], v[8 * j + 1], of16), pack2(v[8 * j + 2], v[8 * j + 3], of16),
-                              pack2(v[8 * j + 4], v[8 * j + 5], of16), pack2(v[8 * j + 6], v[8 * j + 7], of16));
+            pk[j] = make_uint4(pack2(v[8 * j], v[8 * j + 1], of16), pack2(v[8 * j + 2], v[8 * j + 3], of16),
+                               pack2(v[8 * j + 4], v[8 * j + 5], of16), pack2(v[8 * j + 6], v[8 * j + 7], of16));
+          uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(g.out) + orow * g.ldo + n0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] = pk[j];
+          if constexpr (EPI == EPI_SCATTER) {
+            // fused embedding gather: the same 64 bytes go straight into every peer's gather buffer (P2P stores over
+            // NVLink / NVSwitch), so the transfer rides along with the GEMM tile by tile instead of a collective after it
+            for (int p = 0; p < g.n_peers; ++p) {
+              uint4* po = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(g.peers[p]) + (g.peer_row_off + orow) * g.ldo + n0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) po[j] = pk[j];
+            }
+          }
         }
       }
       if constexpr (EPI == EPI_RESID) {

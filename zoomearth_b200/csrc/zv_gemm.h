@@ -18,6 +18,11 @@ struct GemmArgs {
   const float2* rope;       // EPI_QKV_ROPE: [max_pos][20] (cos, sin)
   const int32_t* scatter;   // EPI_SCATTER: [M] output row of accumulator row i
   int heads;                // EPI_QKV_ROPE
+  // EPI_SCATTER fused with the embedding gather: besides `out`, row i is also stored at row (peer_row_off +
+  // scatter[i]) of every peer buffer (peer-mapped device pointers of the other ranks, written over NVLink)
+  void* peers[8];
+  int n_peers;
+  int64_t peer_row_off;
 };
 
 // C = A[M,K] * B[N,K]^T with the chosen epilogue, enqueued on `stream`.

@@ -321,10 +321,36 @@ int64_t zv_visual_workspace_bytes(const zv_cfg* cfg, const zv_plan* p) {
   return workspace_layout(cfg, p->S).bytes;
 }
 
+namespace {
+int visual_forward_impl(const zv_cfg* cfg, const void* weights_dev, const zv_plan* p, const void* plan_dev,
+                        const void* patches_dev, int32_t in_dtype, int32_t in_order, void* merged_out_dev,
+                        int32_t out_dtype, void* hidden_out_dev, void* workspace_dev, int64_t workspace_bytes,
+                        void* const* peer_out_dev, int32_t n_peers, int64_t peer_row_off, void* stream);
+}
+
 int zv_visual_forward(const zv_cfg* cfg, const void* weights_dev, const zv_plan* p, const void* plan_dev,
                       const void* patches_dev, int32_t in_dtype, int32_t in_order, void* merged_out_dev,
                       int32_t out_dtype, void* hidden_out_dev, void* workspace_dev, int64_t workspace_bytes,
                       void* stream) {
+  return visual_forward_impl(cfg, weights_dev, p, plan_dev, patches_dev, in_dtype, in_order, merged_out_dev, out_dtype,
+                             hidden_out_dev, workspace_dev, workspace_bytes, nullptr, 0, 0, stream);
+}
+
+int zv_visual_forward_gather(const zv_cfg* cfg, const void* weights_dev, const zv_plan* p, const void* plan_dev,
+                             const void* patches_dev, int32_t in_dtype, int32_t in_order, void* merged_out_dev,
+                             int32_t out_dtype, void* workspace_dev, int64_t workspace_bytes, void* const* peer_out_dev,
+                             int32_t n_peers, int64_t peer_row_off, void* stream) {
+  if (n_peers < 0 || n_peers > 8 || (n_peers > 0 && !peer_out_dev)) return fail(ZV_EINVAL, "zv_visual_forward_gather: bad peer list");
+  if (n_peers > 0 && out_dtype == ZV_F32) return fail(ZV_EINVAL, "zv_visual_forward_gather: the fused gather writes 16-bit embeddings");
+  return visual_forward_impl(cfg, weights_dev, p, plan_dev, patches_dev, in_dtype, in_order, merged_out_dev, out_dtype,
+                             nullptr, workspace_dev, workspace_bytes, peer_out_dev, n_peers, peer_row_off, stream);
+}
+
+namespace {
+int visual_forward_impl(const zv_cfg* cfg, const void* weights_dev, const zv_plan* p, const void* plan_dev,
+                        const void* patches_dev, int32_t in_dtype, int32_t in_order, void* merged_out_dev,
+                        int32_t out_dtype, void* hidden_out_dev, void* workspace_dev, int64_t workspace_bytes,
+                        void* const* peer_out_dev, int32_t n_peers, int64_t peer_row_off, void* stream) {
   reset_launch_count();
   int rc = check_cfg(cfg, "zv_visual_forward");
   if (rc) return rc;
@@ -421,6 +447,8 @@ int zv_visual_forward(const zv_cfg* cfg, const void* weights_dev, const zv_plan*
   g.op_f16 = f16;
   g.M = (int)T; g.N = (int)O; g.K = (int)(4 * H); g.out = merged_out_dev; g.ldo = O; g.out_dtype = out_dtype;
   g.bias = reinterpret_cast<const float*>(wb + L.b2); g.scatter = d_widx;
+  g.n_peers = n_peers; g.peer_row_off = peer_row_off;
+  for (int i = 0; i < n_peers; ++i) g.peers[i] = peer_out_dev[i];
   ZV_TRY(gemm(EPI_SCATTER, g, BIG, 4 * H, wb + L.w2, 4 * H, stream));
 #undef ZV_TRY
   (void)launches;
@@ -428,6 +456,7 @@ int zv_visual_forward(const zv_cfg* cfg, const void* weights_dev, const zv_plan*
   if (e != cudaSuccess) return fail(ZV_ECUDA, "zv_visual_forward: %s", cudaGetErrorString(e));
   return ZV_OK;
 }
+}  // namespace
 
 int zv_attention(const void* qkv_dev, void* out_dev, int32_t heads, int32_t head_dim, const int32_t* cu_host,
                  int32_t n_seg, void* work_dev, int64_t work_bytes, int32_t dtype, void* stream) {

@@ -62,3 +62,30 @@ def gather_embeddings(local_emb, local_tokens, parts, group=None):
             out[int(starts[i]): int(starts[i]) + n] = gathered[r, off: off + n]
             off += n
     return out, counts
+
+
+class PeerGather:
+    """Gather buffer in symmetric memory for the fused GEMM -> gather path (C1 without a collective).
+
+    Every rank owns one (rows_total, dim) buffer; all of them are mapped into every process
+    (torch.distributed._symmetric_memory: CUDA VMM handles exchanged once at construction).  The tower's last GEMM
+    (merger.mlp.2 + un-reorder) then stores each embedding row into its own buffer and, over NVLink, into every
+    peer's buffer at the same global row, so after one cross-rank barrier each rank holds all embeddings - the
+    transfer overlaps the GEMM tile by tile and no NCCL collective runs on the data path.
+    """
+
+    def __init__(self, rows_total, dim, dtype, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.buffer = symm_mem.empty((rows_total, dim), dtype=dtype, device=device)
+        self.handle = symm_mem.rendezvous(self.buffer, self.group)
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self.local_ptr = ptrs[self.rank]
+        self.peer_ptrs = [p for r, p in enumerate(ptrs) if r != self.rank]
+        if len(self.peer_ptrs) > 8:
+            raise ValueError("the fused gather supports at most 9 ranks per node")
+
+    def barrier(self):
+        """All ranks' stores are visible after this (device-side barrier over the signal pads, on the current stream)."""
+        self.handle.barrier()

@@ -127,9 +127,11 @@ class FusedVisual(nn.Module):
         return self._ws
 
     @torch.no_grad()
-    def forward(self, hidden_states, grid_thw, window_order=False, return_hidden=False, **kwargs):
+    def forward(self, hidden_states, grid_thw, window_order=False, return_hidden=False, gather=None, gather_row=0,
+                **kwargs):
         """hidden_states: (S, 1176) patches, float32/bfloat16, HF row order (or the window-ordered bf16 output of
-        the fused preprocess when ``window_order=True``)."""
+        the fused preprocess when ``window_order=True``).  ``gather`` (a ``sharding.PeerGather``) fuses the multi-GPU
+        embedding gather into the last GEMM: this rank's rows land at ``gather_row`` of every rank's gather buffer."""
         lib = _lib.lib()
         plan = self.plan_for(grid_thw)
         x = hidden_states
@@ -146,13 +148,25 @@ class FusedVisual(nn.Module):
         with torch.cuda.device(self._device):
             tables = plan.device_tables(self._device, stream)
             ws = self._workspace(_lib.check(lib.zv_visual_workspace_bytes(C.byref(self.cfg), plan.handle)))
-            out = torch.empty((plan.num_tokens, self.cfg.out_hidden), dtype=self._dtype, device=self._device)
+            if gather is not None:
+                if gather.buffer.dtype != self._dtype or self._dtype == torch.float32:
+                    raise ValueError("the fused gather needs a 16-bit gather buffer of the tower's output dtype")
+                out = gather.buffer[gather_row:gather_row + plan.num_tokens]
+            else:
+                out = torch.empty((plan.num_tokens, self.cfg.out_hidden), dtype=self._dtype, device=self._device)
             hidden = (torch.empty((plan.num_patches, self.cfg.hidden), dtype=torch.float32, device=self._device)
                       if (return_hidden or self.return_pooling_output) else None)
-            _lib.check(lib.zv_visual_forward(
-                C.byref(self.cfg), self.packed_weights.data_ptr(), plan.handle, tables.data_ptr(), x.data_ptr(),
-                _DT[x.dtype], _lib.ORDER_WINDOW if window_order else _lib.ORDER_HF, out.data_ptr(), _DT[self._dtype],
-                hidden.data_ptr() if hidden is not None else None, ws.data_ptr(), ws.numel(), stream))
+            if gather is not None:
+                peers = (C.c_void_p * len(gather.peer_ptrs))(*gather.peer_ptrs)
+                _lib.check(lib.zv_visual_forward_gather(
+                    C.byref(self.cfg), self.packed_weights.data_ptr(), plan.handle, tables.data_ptr(), x.data_ptr(),
+                    _DT[x.dtype], _lib.ORDER_WINDOW if window_order else _lib.ORDER_HF, out.data_ptr(), _DT[self._dtype],
+                    ws.data_ptr(), ws.numel(), peers, len(gather.peer_ptrs), int(gather_row), stream))
+            else:
+                _lib.check(lib.zv_visual_forward(
+                    C.byref(self.cfg), self.packed_weights.data_ptr(), plan.handle, tables.data_ptr(), x.data_ptr(),
+                    _DT[x.dtype], _lib.ORDER_WINDOW if window_order else _lib.ORDER_HF, out.data_ptr(), _DT[self._dtype],
+                    hidden.data_ptr() if hidden is not None else None, ws.data_ptr(), ws.numel(), stream))
         self.last_launches = lib.zv_last_launch_count()
         if self.return_pooling_output:
             from transformers.modeling_outputs import BaseModelOutputWithPooling
