@@ -26,7 +26,10 @@ class Plan:
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
         if h:
-            _lib.lib().zv_plan_free(h)
+            try:
+                _lib.lib().zv_plan_free(h)
+            except Exception:           # interpreter shutdown: the module globals are already gone
+                pass
 
     @property
     def handle(self):
