@@ -52,6 +52,7 @@ class FusedVisual(nn.Module):
         self.spatial_merge_unit = self.cfg.merge ** 2
         self.return_pooling_output = return_pooling_output
         self._plans = OrderedDict()
+        self._graphs = OrderedDict()      # (grid bytes, input dtype, order) -> captured CUDA graph of the tower
         self._ws = None
         self.last_launches = 0
         self._pack(state_dict)
@@ -126,14 +127,52 @@ class FusedVisual(nn.Module):
             self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self._device)
         return self._ws
 
+    # ---- CUDA-graph replay for launch-bound (small) batches
+    def graph_buffers(self, grid_thw, in_dtype=None, window_order=True):
+        """Static (input, output) tensors of the captured graph for this grid; capturing on first use.  The tower is
+        234 kernel launches: for a single zoom crop (1 296 patches) the launches cost more than the kernels, so the
+        whole forward is captured once per grid signature and replayed (`forward(..., use_graph=True)`)."""
+        plan = self.plan_for(grid_thw)
+        in_dtype = in_dtype or self.operand_dtype
+        key = (plan.grid_thw.tobytes(), in_dtype, bool(window_order))
+        ent = self._graphs.get(key)
+        if ent is None:
+            x = torch.zeros((plan.num_patches, 1176), dtype=in_dtype, device=self._device)
+            self._forward_impl(x, plan, window_order, False, None, 0)          # warm-up: attributes, plan tables, workspace
+            torch.cuda.current_stream(self._device).synchronize()
+            out = torch.empty((plan.num_tokens, self.cfg.out_hidden), dtype=self._dtype, device=self._device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._forward_impl(x, plan, window_order, False, None, 0, out=out)
+            ent = (g, x, out, self._ws)          # the workspace captured in the graph must stay alive
+            self._graphs[key] = ent
+            if len(self._graphs) > 16:
+                self._graphs.popitem(last=False)
+        else:
+            self._graphs.move_to_end(key)
+        return ent
+
     @torch.no_grad()
     def forward(self, hidden_states, grid_thw, window_order=False, return_hidden=False, gather=None, gather_row=0,
-                **kwargs):
+                use_graph=False, **kwargs):
+        if use_graph and gather is None and not return_hidden and not self.return_pooling_output:
+            x = hidden_states
+            if x.dtype not in _DT or (x.dtype != torch.float32 and x.dtype != self.operand_dtype):
+                x = x.float()
+            g, xin, out, _ = self.graph_buffers(grid_thw, x.dtype, window_order)
+            if x.data_ptr() != xin.data_ptr():
+                xin.copy_(x, non_blocking=True)
+            g.replay()
+            self.last_launches = 1
+            return out
+        plan = self.plan_for(grid_thw)
+        return self._forward_impl(hidden_states, plan, window_order, return_hidden, gather, gather_row)
+
+    def _forward_impl(self, hidden_states, plan, window_order, return_hidden, gather, gather_row, out=None):
         """hidden_states: (S, 1176) patches, float32/bfloat16, HF row order (or the window-ordered bf16 output of
         the fused preprocess when ``window_order=True``).  ``gather`` (a ``sharding.PeerGather``) fuses the multi-GPU
         embedding gather into the last GEMM: this rank's rows land at ``gather_row`` of every rank's gather buffer."""
         lib = _lib.lib()
-        plan = self.plan_for(grid_thw)
         x = hidden_states
         if x.device != self._device:
             x = x.to(self._device, non_blocking=True)
@@ -152,7 +191,7 @@ class FusedVisual(nn.Module):
                 if gather.buffer.dtype != self._dtype or self._dtype == torch.float32:
                     raise ValueError("the fused gather needs a 16-bit gather buffer of the tower's output dtype")
                 out = gather.buffer[gather_row:gather_row + plan.num_tokens]
-            else:
+            elif out is None:
                 out = torch.empty((plan.num_tokens, self.cfg.out_hidden), dtype=self._dtype, device=self._device)
             hidden = (torch.empty((plan.num_patches, self.cfg.hidden), dtype=torch.float32, device=self._device)
                       if (return_hidden or self.return_pooling_output) else None)

@@ -31,14 +31,14 @@ class ZoomEncoder:
 
     @torch.no_grad()
     def encode(self, images_dev, boxes=None, image_index=None, apply_cut_image=True, return_patches=False,
-               gather=None, gather_row=0):
+               gather=None, gather_row=0, use_graph=False):
         """images_dev: resident images; boxes (n, 4) in image pixels (None = global view of every image).
         Returns (embeddings (T, out_hidden), image_grid_thw (n, 3), crop boxes (n, 4))."""
         pv, grid, crop = self.processor.preprocess_crops(
             images_dev, boxes, out_dtype=self.visual.operand_dtype, window_order=True, image_index=image_index,
             apply_cut_image=apply_cut_image and boxes is not None)
         k1 = self.processor.last_launches
-        emb = self.visual(pv, grid, window_order=True, gather=gather, gather_row=gather_row)
+        emb = self.visual(pv, grid, window_order=True, gather=gather, gather_row=gather_row, use_graph=use_graph)
         self.last_launches = k1 + self.visual.last_launches
         if return_patches:
             return emb, grid, crop, pv
