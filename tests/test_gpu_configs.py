@@ -182,3 +182,27 @@ def test_zoom_session_caches_global_view_and_batches_crops(cuda):
         assert grid[1].tolist() == rgrid[0].tolist() and embs[0].shape[0] * 4 == int(grid[0, 1] * grid[0, 2])
         cos, maxrel = _metrics(embs[1], ref)
         assert cos >= 0.9995 and maxrel <= 1e-2
+
+
+def test_cuda_graph_replay_matches_eager(cuda):
+    """forward(use_graph=True) replays a captured graph of the same launch sequence: identical results, also on reuse."""
+    cfg = OT.small_cfg(depth=2, fullatt=(1,))
+    sd = OT.make_weights(16, cfg)
+    enc = _encoder(cuda, cfg, sd, 401408, operand_dtype=torch.bfloat16)
+    img = np.random.default_rng(8).integers(0, 256, (1500, 1500, 3), dtype=np.uint8)
+    dev = enc.upload(img)
+    for boxes in ([(100, 100, 612, 612)], [(0, 0, 900, 700), (300, 200, 1400, 1300)], [(100, 100, 612, 612)]):
+        eager, g1, _ = enc.encode([dev], boxes, image_index=[0] * len(boxes))
+        graph, g2, _ = enc.encode([dev], boxes, image_index=[0] * len(boxes), use_graph=True)
+        assert g1.tolist() == g2.tolist() and torch.equal(eager, graph)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs on the box")
+def test_fused_peer_gather_equals_nccl_two_gpus():
+    """tools/multi_gpu_check.py under torchrun: the merger GEMM's peer stores reproduce NCCL's all-gather bitwise."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29561", os.path.join(root, "tools", "multi_gpu_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.count("fused gather == nccl all_gather: True") == 2, r.stdout + r.stderr
