@@ -38,14 +38,19 @@ constexpr int kTmemCols = 512;
 
 constexpr int kXposePitch = 36;                                 // floats per staged row (32 + 4: conflict-free 16 B accesses)
 constexpr int kXposeBytesPerWarp = 32 * kXposePitch * 4;
+// QKV epilogue staging: rotary pairs of the 4 half-0 warps (24 pairs x 32 rows x 8 B), of the 4 half-1 warps (16 pairs),
+// then one [32][88] 16-bit output tile per lane quarter
+constexpr int kQkvRope0 = 24 * 32 * 8, kQkvRope1 = 16 * 32 * 8, kQkvTilePitch = 88, kQkvTile = 32 * kQkvTilePitch * 2;
+constexpr int kQkvStageBytes = 4 * kQkvRope0 + 4 * kQkvRope1 + 4 * kQkvTile;
 template <int BN, int CG, int EPI = 0> struct Cfg {
   static constexpr int kBRows = BN / CG;                       // B rows staged per CTA (half the tile in a CTA pair)
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   // the residual epilogue transposes its tile through shared memory (8 warps x 4.5 KB): one pipeline stage less
-  static constexpr int kXposeBytes = EPI == EPI_RESID ? 8 * kXposeBytesPerWarp : 0;
-  static constexpr int kStages = ((kBRows > 128) ? 4 : 6) - (EPI == EPI_RESID ? 1 : 0);
+  // ... and the QKV epilogue keeps each row's rotary (cos, sin) pairs and a 32 x 80 output tile per lane quarter there
+  static constexpr int kXposeBytes = EPI == EPI_RESID ? 8 * kXposeBytesPerWarp : EPI == EPI_QKV_ROPE ? kQkvStageBytes : 0;
+  static constexpr int kStages = ((kBRows > 128) ? 4 : 6) - ((EPI == EPI_RESID || EPI == EPI_QKV_ROPE) ? 1 : 0);
   static constexpr int kBarBytes = 256;
   static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kXposeBytes + 1024;   // +1024: manual alignment slack
 };
@@ -224,28 +229,44 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int m_blk, int n_b
     }
   } else if constexpr (EPI == EPI_QKV_ROPE) {
     static_assert(EPI != EPI_QKV_ROPE || BN == 240, "QKV tiles hold three 80-wide heads");
-    // The two halves split the 40 rotation pairs (d, d+40) of every head 24 : 16, so that every store stays a
-    // 16-byte store: half 0 owns columns [0,24) and [40,64), half 1 owns [24,40) and [64,80).
-    // Angle of pair d: pos_h * f_d for d < 20, pos_w * f_(d-20) for d >= 20 (emb = cat(rot, rot), HF :485).
-    int ph = 0, pw = 0;
-    if (valid) { ph = __ldg(g.pos + 2 * row); pw = __ldg(g.pos + 2 * row + 1); }
-    const float2* rope_h = g.rope + (int64_t)ph * 20;
-    const float2* rope_w = g.rope + (int64_t)pw * 20;
+    // The two warps of a lane quarter split the 40 rotation pairs (d, d+40) of every head 24 : 16 (half 0 owns
+    // columns [0,24) + [40,64), half 1 owns [24,40) + [64,80)).  Angle of pair d: pos_h * f_d for d < 20,
+    // pos_w * f_(d-20) for d >= 20 (emb = cat(rot, rot), HF :485).  Each thread fetches its row's (cos, sin) pairs ONCE
+    // per tile - before the accumulator is ready - and parks them in shared memory; the rotated 16-bit values of a
+    // head go through a [32][80] tile per quarter so that the global stores are whole 160-byte head rows.
+    const int lane = row_local & 31, q = row_local >> 5;
+    uint8_t* stage = reinterpret_cast<uint8_t*>(xpose);
+    float2* ropeS = reinterpret_cast<float2*>(stage + (half == 0 ? q * kQkvRope0 : 4 * kQkvRope0 + q * kQkvRope1));
+    uint16_t* tileS = reinterpret_cast<uint16_t*>(stage + 4 * kQkvRope0 + 4 * kQkvRope1 + q * kQkvTile);
+    const int NP = half == 0 ? 24 : 16, P0 = half == 0 ? 0 : 24;
+    {
+      int ph = 0, pw = 0;
+      if (valid) { ph = __ldg(g.pos + 2 * row); pw = __ldg(g.pos + 2 * row + 1); }
+      const float2* rope_h = g.rope + (int64_t)ph * 20;
+      const float2* rope_w = g.rope + (int64_t)pw * 20;
+      for (int d = 0; d < NP; ++d) {
+        const int pair = P0 + d;
+        ropeS[d * 32 + lane] = pair < 20 ? __ldg(rope_h + pair) : __ldg(rope_w + (pair - 20));
+      }
+    }
+    wait_accumulator();
     const bool rot_heads_possible = n_blk * 3 < 2 * g.heads;
-    if (half == 0) {
-      constexpr int NP = 24;
+    const int row0 = m_blk * BM + q * 32;                  // first row of this quarter
+    const int t64 = half * 32 + lane;                      // thread index inside the quarter's warp pair
 #pragma unroll 1
-      for (int hh = 0; hh < 3; ++hh) {
+    for (int hh = 0; hh < 3; ++hh) {
+      const int n0 = n_blk * 240 + hh * 80;
+      const bool rotate = rot_heads_possible && n_blk * 3 + hh < 2 * g.heads;   // q and k heads; v heads pass through
+      float lo[24], hi[24];
+      if (half == 0) {
         uint32_t l16[16], l8[8], h16[16], h8[8];
         __syncwarp();
         tmem_ld_x16(taddr + hh * 80, l16);
         tmem_ld_x8(taddr + hh * 80 + 16, l8);
         tmem_ld_x16(taddr + hh * 80 + 40, h16);
         tmem_ld_x8(taddr + hh * 80 + 56, h8);
-        const int n0 = n_blk * 240 + hh * 80;
-        float lo[NP], hi[NP];
 #pragma unroll
-        for (int j = 0; j < NP / 4; ++j) {
+        for (int j = 0; j < 6; ++j) {
           const float4 t = __ldg(reinterpret_cast<const float4*>(g.bias + n0) + j);
           lo[4 * j] = t.x; lo[4 * j + 1] = t.y; lo[4 * j + 2] = t.z; lo[4 * j + 3] = t.w;
           const float4 u = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + 40) + j);
@@ -256,66 +277,53 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int m_blk, int n_b
         for (int j = 0; j < 16; ++j) { lo[j] += __uint_as_float(l16[j]); hi[j] += __uint_as_float(h16[j]); }
 #pragma unroll
         for (int j = 0; j < 8; ++j) { lo[16 + j] += __uint_as_float(l8[j]); hi[16 + j] += __uint_as_float(h8[j]); }
-        if (rot_heads_possible && n_blk * 3 + hh < 2 * g.heads) {
-#pragma unroll
-          for (int d = 0; d < NP; ++d) {
-            const float2 cs = d < 20 ? __ldg(rope_h + d) : __ldg(rope_w + (d - 20));
-            const float l = lo[d], h = hi[d];
-            lo[d] = l * cs.x - h * cs.y;         // x*cos + rotate_half(x)*sin, rotate_half = (-x[40:], x[:40])
-            hi[d] = h * cs.x + l * cs.y;
-          }
-        }
-        if (valid) {
-          __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(g.out) + (int64_t)row * g.ldo + n0;
-#pragma unroll
-          for (int j = 0; j < NP / 8; ++j) {
-            *reinterpret_cast<uint4*>(dst + 8 * j) = make_uint4(pack2(lo[8 * j], lo[8 * j + 1], of16), pack2(lo[8 * j + 2], lo[8 * j + 3], of16),
-                                                                pack2(lo[8 * j + 4], lo[8 * j + 5], of16), pack2(lo[8 * j + 6], lo[8 * j + 7], of16));
-            *reinterpret_cast<uint4*>(dst + 40 + 8 * j) = make_uint4(pack2(hi[8 * j], hi[8 * j + 1], of16), pack2(hi[8 * j + 2], hi[8 * j + 3], of16),
-                                                                     pack2(hi[8 * j + 4], hi[8 * j + 5], of16), pack2(hi[8 * j + 6], hi[8 * j + 7], of16));
-          }
-        }
-      }
-    } else {
-      constexpr int NP = 16;
-#pragma unroll 1
-      for (int hh = 0; hh < 3; ++hh) {
+      } else {
         uint32_t l16[16], h16[16];
         __syncwarp();
         tmem_ld_x16(taddr + hh * 80 + 24, l16);
         tmem_ld_x16(taddr + hh * 80 + 64, h16);
-        const int n0 = n_blk * 240 + hh * 80 + 24;
-        float lo[NP], hi[NP];
 #pragma unroll
-        for (int j = 0; j < NP / 4; ++j) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(g.bias + n0) + j);
+        for (int j = 0; j < 4; ++j) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + 24) + j);
           lo[4 * j] = t.x; lo[4 * j + 1] = t.y; lo[4 * j + 2] = t.z; lo[4 * j + 3] = t.w;
-          const float4 u = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + 40) + j);
+          const float4 u = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + 64) + j);
           hi[4 * j] = u.x; hi[4 * j + 1] = u.y; hi[4 * j + 2] = u.z; hi[4 * j + 3] = u.w;
         }
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; ++j) { lo[j] += __uint_as_float(l16[j]); hi[j] += __uint_as_float(h16[j]); }
-        if (rot_heads_possible && n_blk * 3 + hh < 2 * g.heads) {
+      }
+      if (rotate) {
 #pragma unroll
-          for (int d = 0; d < NP; ++d) {
-            const float2 cs = __ldg(rope_w + (d + 4));       // pair index 24 + d -> w angle index 4 + d
+        for (int d = 0; d < 24; ++d) {
+          if (d < NP) {
+            const float2 cs = ropeS[d * 32 + lane];
             const float l = lo[d], h = hi[d];
-            lo[d] = l * cs.x - h * cs.y;
+            lo[d] = l * cs.x - h * cs.y;           // x*cos + rotate_half(x)*sin, rotate_half = (-x[40:], x[:40])
             hi[d] = h * cs.x + l * cs.y;
           }
         }
-        if (valid) {
-          __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(g.out) + (int64_t)row * g.ldo + n0;
+      }
+      // this thread's two column runs of the head row -> the quarter's tile, 16 bytes at a time
+      uint16_t* trow = tileS + lane * kQkvTilePitch + P0;
 #pragma unroll
-          for (int j = 0; j < NP / 8; ++j) {
-            *reinterpret_cast<uint4*>(dst + 8 * j) = make_uint4(pack2(lo[8 * j], lo[8 * j + 1], of16), pack2(lo[8 * j + 2], lo[8 * j + 3], of16),
-                                                                pack2(lo[8 * j + 4], lo[8 * j + 5], of16), pack2(lo[8 * j + 6], lo[8 * j + 7], of16));
-            *reinterpret_cast<uint4*>(dst + 40 + 8 * j) = make_uint4(pack2(hi[8 * j], hi[8 * j + 1], of16), pack2(hi[8 * j + 2], hi[8 * j + 3], of16),
-                                                                     pack2(hi[8 * j + 4], hi[8 * j + 5], of16), pack2(hi[8 * j + 6], hi[8 * j + 7], of16));
-          }
+      for (int j = 0; j < 3; ++j) {
+        if (8 * j < NP) {
+          *reinterpret_cast<uint4*>(trow + 8 * j) = make_uint4(pack2(lo[8 * j], lo[8 * j + 1], of16), pack2(lo[8 * j + 2], lo[8 * j + 3], of16),
+                                                               pack2(lo[8 * j + 4], lo[8 * j + 5], of16), pack2(lo[8 * j + 6], lo[8 * j + 7], of16));
+          *reinterpret_cast<uint4*>(trow + 40 + 8 * j) = make_uint4(pack2(hi[8 * j], hi[8 * j + 1], of16), pack2(hi[8 * j + 2], hi[8 * j + 3], of16),
+                                                                    pack2(hi[8 * j + 4], hi[8 * j + 5], of16), pack2(hi[8 * j + 6], hi[8 * j + 7], of16));
         }
       }
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");           // both warps of the quarter have written the tile
+      uint16_t* gout = static_cast<uint16_t*>(g.out) + n0;
+#pragma unroll
+      for (int c = t64; c < 320; c += 64) {
+        const int r = c / 10, ch = c - r * 10;
+        if (row0 + r < g.M)
+          *reinterpret_cast<uint4*>(gout + (int64_t)(row0 + r) * g.ldo + ch * 8) = *reinterpret_cast<const uint4*>(tileS + r * kQkvTilePitch + ch * 8);
+      }
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");           // tile free for the next head
     }
   }
 }
@@ -454,7 +462,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc(const __grid_constant__ C
     }
   } else if (warp >= 4) {
     const int q = warp & 3, half = (warp - 4) >> 2;
-    float* xpose = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes + C::kBarBytes) + (warp - 4) * (kXposeBytesPerWarp / 4);
+    float* xpose = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes + C::kBarBytes) +
+                   (EPI == EPI_RESID ? (warp - 4) * (kXposeBytesPerWarp / 4) : 0);   // RESID: per-warp area; QKV: the CTA's area
     int it = 0;
     for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
       const int m_blk = (tile / n_blocks) * CG + (int)rank, n_blk = tile % n_blocks;
