@@ -281,14 +281,18 @@ __global__ void __launch_bounds__(256) k1_hpass_fast(const K1Crop* __restrict__ 
 }
 
 // Vertical pass on dp4a + LUT + patchify.  Block = one merge-group row x two merge groups (28 rows x 56 pixels).
+// The row quads of the intermediate that the 28 output rows touch are first copied to shared memory with 16-byte
+// cp.async (coalesced, every word fetched once), so the tap loop runs on shared-memory loads instead of L2 latency.
 template <int NW, typename OutT>
 __global__ void __launch_bounds__(256) k1_vpass_fast(const K1Crop* __restrict__ crops, const int32_t* __restrict__ ids,
                                                      const int32_t* __restrict__ blk0, int n_cls,
                                                      const int32_t* __restrict__ coef, const uint8_t* __restrict__ ws,
                                                      const float* __restrict__ lut, OutT* __restrict__ out,
-                                                     int row_order, int wsz) {
-  __shared__ __align__(16) OutT stage[2 * 4 * kPatchElems];
-  __shared__ float s_lut[768];
+                                                     int row_order, int wsz, int tile_quads_max) {
+  extern __shared__ __align__(16) uint8_t vsm[];
+  uint32_t* tile = reinterpret_cast<uint32_t*>(vsm);                                   // [tile_quads_max][168]
+  OutT* stage = reinterpret_cast<OutT*>(vsm + (size_t)tile_quads_max * 168 * 4);       // [2][4][1176]
+  float* s_lut = reinterpret_cast<float*>(stage + 2 * 4 * kPatchElems);                // [768]
   const int slot = find_slot(blk0, n_cls, blockIdx.x);
   const K1Crop c = crops[ids[slot]];
   const int local = blockIdx.x - blk0[slot];
@@ -296,13 +300,24 @@ __global__ void __launch_bounds__(256) k1_vpass_fast(const K1Crop* __restrict__ 
   const int my = local / pairs, mx0 = (local % pairs) * 2;
   const int ngroups = min(2, c.lw - mx0);
   const int ncols = ngroups * 84;                                        // (pixel, channel) columns of this block
-  for (int i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i] = lut[i];
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t* __restrict__ tmp4 = reinterpret_cast<const uint32_t*>(ws + c.tmp_off) + mx0 * 84;
-  const int qpitch = c.ow * 3;                                           // words per row quad
   constexpr int kStride = 1 + 3 * NW;
+  const int32_t* __restrict__ lt = coef + c.off_lv;
   const int q_origin = c.ybox0 >> 2;                                     // tmp quads are counted from ybox0 (multiple of 4)
+  const int q_lo = lt[(int64_t)(my * 28) * kStride] - q_origin;          // window starts are monotone in yy
+  const int nq = min(tile_quads_max, lt[(int64_t)(my * 28 + 27) * kStride] + NW - q_origin - q_lo);
+  const int qpitch = c.ow * 3;                                           // words per row quad
+  {
+    const uint32_t* __restrict__ g = reinterpret_cast<const uint32_t*>(ws + c.tmp_off) + (int64_t)q_lo * qpitch + mx0 * 84;
+    const int chunks = ncols >> 2;                                       // 16-byte chunks per quad row (21 or 42)
+    for (int i = threadIdx.x; i < nq * chunks; i += blockDim.x) {
+      const int r = i / chunks, ck = i - r * chunks;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(tile + r * 168 + ck * 4)),
+                   "l"(g + (int64_t)r * qpitch + ck * 4) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i] = lut[i];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // per-lane column decomposition, hoisted out of the row loop: stage offset and LUT base of columns lane + 32 i
   int eoff[6], lbase[6];
 #pragma unroll
@@ -313,14 +328,16 @@ __global__ void __launch_bounds__(256) k1_vpass_fast(const K1Crop* __restrict__ 
     eoff[i] = (grp * 4 + xg / 14) * kPatchElems + ch * 392 + (xg % 14);
     lbase[i] = ch * 256;
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
   for (int yl = warp; yl < 28; yl += 8) {
     const int yy = my * 28 + yl;
-    const int32_t* __restrict__ e = coef + c.off_lv + (int64_t)yy * kStride;
-    const int q0 = __ldg(e) - q_origin;
+    const int32_t* __restrict__ e = lt + (int64_t)yy * kStride;
+    const int q0 = __ldg(e) - q_origin - q_lo;
     uint32_t l0[NW], l1[NW], l2[NW];
 #pragma unroll
     for (int k = 0; k < NW; ++k) { l0[k] = __ldg(e + 1 + k); l1[k] = __ldg(e + 1 + NW + k); l2[k] = __ldg(e + 1 + 2 * NW + k); }
-    const uint32_t* __restrict__ base = tmp4 + (int64_t)q0 * qpitch + lane;
+    const uint32_t* __restrict__ base = tile + q0 * 168 + lane;
     const int rowoff = (yl / 14) * 2 * kPatchElems + (yl % 14) * 14;
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
@@ -328,7 +345,7 @@ __global__ void __launch_bounds__(256) k1_vpass_fast(const K1Crop* __restrict__ 
         int a0 = 0, a1 = 0, a2 = 0;
 #pragma unroll
         for (int k = 0; k < NW; ++k) {
-          const uint32_t v = __ldg(base + k * qpitch + 32 * i);
+          const uint32_t v = base[k * 168 + 32 * i];
           a0 = dp4a_uu(v, l0[k], a0);
           a1 = dp4a_uu(v, l1[k], a1);
           a2 = dp4a_us(v, l2[k], a2);
@@ -358,7 +375,7 @@ inline int nw_class(int ksize) {                   // words per tap window (<= 3
   return 0;
 }
 
-struct AxisTables { int32_t off_bounds = 0, off_kk = 0, off_limbs = 0, ksize = 0, nw = 0, seg_words = 0; };
+struct AxisTables { int32_t off_bounds = 0, off_kk = 0, off_limbs = 0, ksize = 0, nw = 0, seg_words = 0, tile_quads = 0; };
 struct Layout {
   int64_t off_desc = 0, off_lut = 0, off_coef = 0, off_lists = 0, off_tmp = 0, bytes = 0;
   std::vector<int64_t> tmp_off;              // per crop, relative to off_tmp
@@ -413,11 +430,13 @@ int build_layout(int32_t n, const int32_t* crop_box, const int32_t* resized_hw, 
               L->coef.push_back((int32_t)word);
             }
         }
-        // widest source span (in words) any 128-column chunk of this axis needs
+        // widest source span (in words) any 128-column chunk of this axis needs (horizontal use), and the most row
+        // quads any 28-row merge-group row needs (vertical use)
         for (int32_t o0 = 0; o0 < key.second; o0 += kHCols) {
           const int32_t o1 = std::min(key.second, o0 + kHCols) - 1;
           t.seg_words = std::max(t.seg_words, w0[o1] + t.nw - w0[o0]);
         }
+        for (int32_t o0 = 0; o0 + 27 < key.second; o0 += 28) t.tile_quads = std::max(t.tile_quads, w0[o0 + 27] + t.nw - w0[o0]);
       }
       L->axis[key] = t;
       coef_ints += ints;
@@ -457,18 +476,26 @@ void launch_hfast(unsigned blocks, int smem, cudaStream_t s, const K1Crop* d, co
   if (!attr) { cudaFuncSetAttribute(k1_hpass_fast<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
   k1_hpass_fast<NW><<<blocks, 256, smem, s>>>(d, ids, blk0, ncls, coef, ws, seg_words);
 }
+template <int NW, typename OutT>
+void launch_vfast(unsigned blocks, cudaStream_t s, const K1Crop* d, const int32_t* ids, const int32_t* blk0, int ncls,
+                  const int32_t* coef, const uint8_t* ws, const float* lut, OutT* out, int row_order, int wsz, int tile_quads) {
+  const int smem = tile_quads * 168 * 4 + 2 * 4 * kPatchElems * (int)sizeof(OutT) + 768 * 4;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(k1_vpass_fast<NW, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+  k1_vpass_fast<NW, OutT><<<blocks, 256, smem, s>>>(d, ids, blk0, ncls, coef, ws, lut, out, row_order, wsz, tile_quads);
+}
 template <typename OutT>
 void launch_vpass(int nw, unsigned blocks, cudaStream_t s, const K1Crop* d, const int32_t* ids, const int32_t* blk0, int ncls,
-                  const int32_t* coef, const uint8_t* ws, const float* lut, void* out_, int row_order, int wsz) {
+                  const int32_t* coef, const uint8_t* ws, const float* lut, void* out_, int row_order, int wsz, int tile_quads) {
   OutT* out = static_cast<OutT*>(out_);
   switch (nw) {
     case 0: k1_vpass<OutT><<<blocks, 256, 0, s>>>(d, ids, blk0, ncls, coef, ws, lut, out, row_order, wsz); break;
-    case 2: k1_vpass_fast<2, OutT><<<blocks, 256, 0, s>>>(d, ids, blk0, ncls, coef, ws, lut, out, row_order, wsz); break;
-    case 3: k1_vpass_fast<3, OutT><<<blocks, 256, 0, s>>>(d, ids, blk0, ncls, coef, ws, lut, out, row_order, wsz); break;
-    case 4: k1_vpass_fast<4, OutT><<<blocks, 256, 0, s>>>(d, ids, blk0, ncls, coef, ws, lut, out, row_order, wsz); break;
-    case 5: k1_vpass_fast<5, OutT><<<blocks, 256, 0, s>>>(d, ids, blk0, ncls, coef, ws, lut, out, row_order, wsz); break;
-    case 7: k1_vpass_fast<7, OutT><<<blocks, 256, 0, s>>>(d, ids, blk0, ncls, coef, ws, lut, out, row_order, wsz); break;
-    default: k1_vpass_fast<10, OutT><<<blocks, 256, 0, s>>>(d, ids, blk0, ncls, coef, ws, lut, out, row_order, wsz); break;
+    case 2: launch_vfast<2, OutT>(blocks, s, d, ids, blk0, ncls, coef, ws, lut, out, row_order, wsz, tile_quads); break;
+    case 3: launch_vfast<3, OutT>(blocks, s, d, ids, blk0, ncls, coef, ws, lut, out, row_order, wsz, tile_quads); break;
+    case 4: launch_vfast<4, OutT>(blocks, s, d, ids, blk0, ncls, coef, ws, lut, out, row_order, wsz, tile_quads); break;
+    case 5: launch_vfast<5, OutT>(blocks, s, d, ids, blk0, ncls, coef, ws, lut, out, row_order, wsz, tile_quads); break;
+    case 7: launch_vfast<7, OutT>(blocks, s, d, ids, blk0, ncls, coef, ws, lut, out, row_order, wsz, tile_quads); break;
+    default: launch_vfast<10, OutT>(blocks, s, d, ids, blk0, ncls, coef, ws, lut, out, row_order, wsz, tile_quads); break;
   }
 }
 
@@ -507,7 +534,7 @@ int zv_preprocess(const zv_cfg* cfg, int32_t n, const uint8_t* const* src_dev, c
   std::vector<uint8_t> host((size_t)L.off_tmp, 0);
   K1Crop* d = reinterpret_cast<K1Crop*>(host.data() + L.off_desc);
   const bool generic_only = std::getenv("ZV_K1_GENERIC") != nullptr;    // debug: force the per-tap kernels
-  std::vector<int32_t> seg_h(n, 0);
+  std::vector<int32_t> seg_h(n, 0), tq_v(n, 0);
   int64_t row = 0;
   for (int32_t i = 0; i < n; ++i) {
     K1Crop& c = d[i];
@@ -523,9 +550,11 @@ int zv_preprocess(const zv_cfg* cfg, int32_t n, const uint8_t* const* src_dev, c
     c.off_bh = h.off_bounds; c.off_kh = h.off_kk; c.off_bv = v.off_bounds; c.off_kv = v.off_kk;
     c.off_lh = h.off_limbs; c.off_lv = v.off_limbs;
     const bool aligned = (reinterpret_cast<uintptr_t>(c.src) & 3) == 0 && (c.pitch & 3) == 0;
-    c.fast = (!generic_only && aligned && h.nw > 0 && v.nw > 0 && kHRows * (h.seg_words * 24 + 48) <= 200 * 1024) ? 1 : 0;
+    c.fast = (!generic_only && aligned && h.nw > 0 && v.nw > 0 && kHRows * (h.seg_words * 24 + 48) <= 200 * 1024 &&
+              v.tile_quads * 168 * 4 + 2 * 4 * kPatchElems * 4 + 768 * 4 <= 200 * 1024) ? 1 : 0;
     c.nwh = c.fast ? h.nw : 0; c.nwv = c.fast ? v.nw : 0;
     seg_h[i] = h.seg_words;
+    tq_v[i] = v.tile_quads;
     c.ybox0 = L.ybox0[i]; c.nrows = L.nrows[i];
     if (c.fast) {                       // row quads are counted from ybox0 rounded down to 4
       const int32_t al = c.ybox0 & ~3;
@@ -540,7 +569,7 @@ int zv_preprocess(const zv_cfg* cfg, int32_t n, const uint8_t* const* src_dev, c
   std::memcpy(host.data() + L.off_coef, L.coef.data(), L.coef.size() * sizeof(int32_t));
 
   // launch lists: crops grouped by kernel class, each class with its own block prefix
-  struct Launch { int nw; int32_t ids_off, blk_off, count; int64_t blocks; int seg_words; };
+  struct Launch { int nw; int32_t ids_off, blk_off, count; int64_t blocks; int seg_words; int tile_quads; };
   std::vector<Launch> hl, vl;
   int32_t* lists = reinterpret_cast<int32_t*>(host.data() + L.off_lists);
   int64_t cur = 0;
@@ -559,7 +588,7 @@ int zv_preprocess(const zv_cfg* cfg, int32_t n, const uint8_t* const* src_dev, c
       for (int32_t id : ids) {
         const K1Crop& c = d[id];
         lists[cur++] = (int32_t)blocks;
-        if (vpass) blocks += nw == 0 ? (int64_t)c.lh * c.lw : (int64_t)c.lh * ((c.lw + 1) / 2);
+        if (vpass) { blocks += nw == 0 ? (int64_t)c.lh * c.lw : (int64_t)c.lh * ((c.lw + 1) / 2); l.tile_quads = std::max(l.tile_quads, tq_v[id]); }
         else if (nw == 0) blocks += ((int64_t)c.nrows * c.ow + 255) / 256;
         else {
           blocks += (((int64_t)c.nrows + kHRows - 1) / kHRows) * ((c.ow + kHCols - 1) / kHCols);
@@ -610,9 +639,9 @@ int zv_preprocess(const zv_cfg* cfg, int32_t n, const uint8_t* const* src_dev, c
       const int32_t* ids = dlists + l.ids_off;
       const int32_t* blk0 = dlists + l.blk_off;
       const unsigned nb = (unsigned)l.blocks;
-      if (out_dtype == ZV_BF16) launch_vpass<__nv_bfloat16>(l.nw, nb, stream, dcrops, ids, blk0, l.count, dcoef, ws, dlut, out_dev, row_order, wsz);
-      else if (out_dtype == ZV_F16) launch_vpass<__half>(l.nw, nb, stream, dcrops, ids, blk0, l.count, dcoef, ws, dlut, out_dev, row_order, wsz);
-      else launch_vpass<float>(l.nw, nb, stream, dcrops, ids, blk0, l.count, dcoef, ws, dlut, out_dev, row_order, wsz);
+      if (out_dtype == ZV_BF16) launch_vpass<__nv_bfloat16>(l.nw, nb, stream, dcrops, ids, blk0, l.count, dcoef, ws, dlut, out_dev, row_order, wsz, l.tile_quads);
+      else if (out_dtype == ZV_F16) launch_vpass<__half>(l.nw, nb, stream, dcrops, ids, blk0, l.count, dcoef, ws, dlut, out_dev, row_order, wsz, l.tile_quads);
+      else launch_vpass<float>(l.nw, nb, stream, dcrops, ids, blk0, l.count, dcoef, ws, dlut, out_dev, row_order, wsz, l.tile_quads);
       zv::count_launch();
     }
   }
