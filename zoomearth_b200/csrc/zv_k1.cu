@@ -85,9 +85,17 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {   // a u
   asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
   return d;
 }
-// sum_t px_t * k_t from the three limb sums, rounded and clipped like Pillow's 8bpc passes
-__device__ __forceinline__ int finish8(int a0, int a1, int a2) {
-  return clip8((a0 + (a1 << 8) + (a2 << 16) + (1 << (kPrecisionBits - 1))) >> kPrecisionBits);
+// sum_t px_t * k_t from the three limb sums, rounded like Pillow's 8bpc passes (not yet clipped)
+__device__ __forceinline__ int finish_raw(int a0, int a1, int a2) {
+  return (a2 * 65536 + (a1 * 256 + (a0 + (1 << (kPrecisionBits - 1))))) >> kPrecisionBits;
+}
+__device__ __forceinline__ int finish8(int a0, int a1, int a2) { return clip8(finish_raw(a0, a1, a2)); }
+// four rounded sums -> four bytes, each saturated to [0, 255] (Pillow's clip8), v0 in the low byte
+__device__ __forceinline__ uint32_t pack4_sat(int v0, int v1, int v2, int v3) {
+  uint32_t hi, d;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(v3), "r"(v2), "r"(0));
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(v1), "r"(v0), "r"(hi));
+  return d;
 }
 
 // Position of merge group (my, mx) in the tower's window order (closed form of argsort(window_index),
@@ -260,12 +268,13 @@ __global__ void __launch_bounds__(256) k1_hpass_fast(const K1Crop* __restrict__ 
 #pragma unroll
   for (int k = 0; k < NW; ++k) { l0[k] = __ldg(e + 1 + k); l1[k] = __ldg(e + 1 + NW + k); l2[k] = __ldg(e + 1 + 2 * NW + k); }
   uint32_t* __restrict__ tmp4 = reinterpret_cast<uint32_t*>(ws + c.tmp_off) + ((int64_t)q * c.ow + xx) * 3;
+  const uint32_t* __restrict__ prow = planes + quad * 12 * seg_words_max + w0;
 #pragma unroll
   for (int ch = 0; ch < 3; ++ch) {
-    uint32_t packed = 0;
+    int val[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      const uint32_t* __restrict__ p = planes + ((quad * 4 + r) * 3 + ch) * seg_words_max + w0;
+      const uint32_t* __restrict__ p = prow + (r * 3 + ch) * seg_words_max;
       int a0 = 0, a1 = 0, a2 = 0;
 #pragma unroll
       for (int k = 0; k < NW; ++k) {
@@ -274,9 +283,9 @@ __global__ void __launch_bounds__(256) k1_hpass_fast(const K1Crop* __restrict__ 
         a1 = dp4a_uu(v, l1[k], a1);
         a2 = dp4a_us(v, l2[k], a2);
       }
-      packed |= (uint32_t)finish8(a0, a1, a2) << (8 * r);
+      val[r] = finish_raw(a0, a1, a2);
     }
-    tmp4[ch] = packed;                              // rows 4q..4q+3 of (xx, ch)
+    tmp4[ch] = pack4_sat(val[0], val[1], val[2], val[3]);      // rows 4q..4q+3 of (xx, ch)
   }
 }
 
