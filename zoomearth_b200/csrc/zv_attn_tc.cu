@@ -9,8 +9,8 @@
 //                   head by transpose_v so that the B operand is K-major); O stays in TMEM for the whole segment and
 //                   is rescaled lazily (only when the row max grows by more than 2^8).  Two CTAs fit per SM, so one
 //                   CTA's softmax overlaps the other's MMAs.
-// Warp roles (320 threads): warp 0 = TMA producer + TMEM allocator, warp 1 = MMA issuer, warps 2-9 = softmax
-// (TMEM lane quarters 2,3,0,1,2,3,0,1; the two warps of a quarter split the 64 score columns).  Rotary is already applied to q,k by the QKV GEMM epilogue.
+// Warp roles (192 threads): warp 0 = TMA producer + TMEM allocator, warp 1 = MMA issuer, warps 2-5 = softmax
+// (TMEM lane quarters 2,3,0,1).  Rotary is already applied to q,k by the QKV GEMM epilogue.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -33,10 +33,9 @@ constexpr int kK64 = BKV * 64 * 2, kK16 = BKV * 16 * 2, kVtTma = HD * BKV * 2, k
 constexpr int kStage = kK64 + kK16 + kVt;                                // 22528
 constexpr int kP = BQ * BKV * 2;                                         // 16384
 constexpr int kOffQ16 = kQ64, kOffStage = kQ64 + kQ16, kOffP = kOffStage + STAGES * kStage, kOffBar = kOffP + kP;
-constexpr int kOffPmax = kOffBar + 256;                                    // float [2][2][128] partial row maxima
-constexpr int kSmem = kOffPmax + 2 * 2 * 128 * 4 + 1024;
+constexpr int kSmem = kOffBar + 256 + 1024;
 constexpr int kTmemCols = 256;                                           // S0 [0,64) S1 [64,128) O [128,224): 80 dims + row sum
-constexpr int kThreads = 320;          // TMA warp, MMA warp, 8 softmax warps
+constexpr int kThreads = 192;
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = 0;
@@ -53,11 +52,6 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[
       ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
         "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
-}
-__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t (&r)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -106,8 +100,8 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const __grid_const
     prefetch_tensormap(&tm_qk64); prefetch_tensormap(&tm_qk16); prefetch_tensormap(&tm_vt);
     mbar_init(q_full, 1);
     for (int s = 0; s < STAGES; ++s) { mbar_init(k_full + s, 1); mbar_init(v_full + s, 1); mbar_init(k_empty + s, 1); mbar_init(v_empty + s, 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(s_full + b, 1); mbar_init(s_empty + b, 8); }
-    mbar_init(p_full, 8); mbar_init(pv_done, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(s_full + b, 1); mbar_init(s_empty + b, 4); }
+    mbar_init(p_full, 4); mbar_init(pv_done, 1);
     fence_mbar_init();
   }
   if (warp == 0) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
@@ -185,76 +179,70 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const __grid_const
       }
     }
   } else {
-    // ---- softmax warps: eight of them, two per TMEM lane quarter; a thread owns one q row and HALF of the tile's 64
-    // score columns (twice the warps in flight per scheduler than one-thread-per-row: the exp2 / pack latency of one
-    // warp hides behind the others).  The two halves of a row exchange their partial maxima through shared memory.
-    // O accumulates in TMEM across KV tiles and is rescaled (tcgen05.ld -> multiply -> tcgen05.st) only when the
-    // running row max grew by more than 2^8 since the scale in use was chosen ("lazy rescale": P may then exceed 1 by
-    // at most 2^8, harmless in fp32 sums and 16-bit P); the row sum is column 80 of O (ones row in V^T).
-    const int sw = warp - 2;                             // 0..7
-    const int quarter = warp & 3, half = sw >> 2;
+    // ---- softmax warps: thread = q row.  O accumulates in TMEM across KV tiles; it is rescaled (tcgen05.ld ->
+    // multiply -> tcgen05.st) only when the running row max grew by more than 2^8 since the scale in use was chosen
+    // ("lazy rescale": P may then exceed 1 by at most 2^8, harmless in fp32 sums and 16-bit P), so the common tile
+    // costs one TMEM row load, 64 exp2 and one 128-byte row store per thread.
+    const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const float sl2 = a.scale_log2;
-    float m_used = -INFINITY;               // scale in use (raw score units)
+    float m_used = -INFINITY;               // scale in use (raw score units); the row sum lives in O column 80
     uint8_t* prow = smem + kOffP + row * 128;
-    float* pmax = reinterpret_cast<float*>(smem + kOffPmax);      // [2 tiles parity][2 halves][128 rows]
 
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(s_full + (j & 1), (j >> 1) & 1);
       tc_fence_after();
-      uint32_t r0[32];
-      tmem_ld_x32(tmem + lane_addr + (j & 1) * 64 + half * 32, r0);
+      uint32_t r0[32], r1[32];
+      tmem_ld_x32(tmem + lane_addr + (j & 1) * 64, r0);
+      tmem_ld_x32(tmem + lane_addr + (j & 1) * 64 + 32, r1);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_empty + (j & 1));
-      float s[32];
+      float s[64];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) s[i] = __uint_as_float(r0[i]);
-      const int lo = seg_b - (kv_base + j * BKV) - half * 32, hi = seg_e - (kv_base + j * BKV) - half * 32;   // valid: [lo, hi)
-      if (lo > 0 || hi < 32) {
+      for (int i = 0; i < 32; ++i) { s[i] = __uint_as_float(r0[i]); s[32 + i] = __uint_as_float(r1[i]); }
+      const int lo = seg_b - (kv_base + j * BKV), hi = seg_e - (kv_base + j * BKV);   // valid columns: [lo, hi)
+      if (lo > 0 || hi < BKV) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) if (i < lo || i >= hi) s[i] = -INFINITY;
+        for (int i = 0; i < 64; ++i) if (i < lo || i >= hi) s[i] = -INFINITY;
       }
-      float mx4[4] = {s[0], s[1], s[2], s[3]};
+      float mx4[4] = {s[0], s[1], s[2], s[3]};          // four independent chains, not one 64-deep dependency
 #pragma unroll
-      for (int i = 4; i < 32; i += 4) {
+      for (int i = 4; i < 64; i += 4) {
         mx4[0] = fmaxf(mx4[0], s[i]); mx4[1] = fmaxf(mx4[1], s[i + 1]);
         mx4[2] = fmaxf(mx4[2], s[i + 2]); mx4[3] = fmaxf(mx4[3], s[i + 3]);
       }
-      float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-      pmax[((j & 1) * 2 + half) * 128 + row] = mx;
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");          // the row's other half has posted its max
-      mx = fmaxf(mx, pmax[((j & 1) * 2 + (half ^ 1)) * 128 + row]);
-      const bool grow = (mx - m_used) * sl2 > 8.0f;          // true on the first tile (m_used = -inf); same in both halves
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      const bool grow = (mx - m_used) * sl2 > 8.0f;          // true on the first tile (m_used = -inf)
       float factor = 1.0f;
       if (grow) { factor = ex2_approx((m_used - mx) * sl2); m_used = mx; }
       if (j > 0) {
         mbar_wait(pv_done, (j - 1) & 1);                     // P buffer free, O_{j-1} accumulated
-        if (__any_sync(0xffffffffu, grow)) {                 // each half rescales its 48 of O's 96 columns
+        if (__any_sync(0xffffffffu, grow)) {
           tc_fence_after();
 #pragma unroll
-          for (int c = 0; c < 48; c += 16) {
+          for (int c = 0; c < VROWS; c += 16) {
             uint32_t t[16];
-            tmem_ld_x16(tmem + lane_addr + 128 + half * 48 + c, t);
+            tmem_ld_x16(tmem + lane_addr + 128 + c, t);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 16; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * factor);
-            tmem_st_x16(tmem + lane_addr + 128 + half * 48 + c, t);
+            tmem_st_x16(tmem + lane_addr + 128 + c, t);
           }
           tmem_st_wait();
           tc_fence_before();
         }
       }
       const float ms = m_used * sl2;
-      uint32_t pk[16];
+      uint32_t pk[32];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) pk[i] = pack2<F16>(ex2_approx(s[2 * i] * sl2 - ms), ex2_approx(s[2 * i + 1] * sl2 - ms));
-      // this half of the P row -> shared memory, K-major 128B swizzle: 16-byte chunk c of row r lives at chunk (c ^ (r & 7))
+      for (int i = 0; i < 32; ++i) pk[i] = pack2<F16>(ex2_approx(s[2 * i] * sl2 - ms), ex2_approx(s[2 * i + 1] * sl2 - ms));
+      // P row -> shared memory, K-major 128B swizzle: 16-byte chunk c of row r lives at chunk (c ^ (r & 7))
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        *reinterpret_cast<uint4*>(prow + (((4 * half + c) ^ (row & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
@@ -268,25 +256,20 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const __grid_const
       tmem_ld_wait();
       inv = 1.f / __uint_as_float(t[0]);
     }
-    uint16_t* dst = static_cast<uint16_t*>(a.out) + (int64_t)(q0 + row) * a.hidden + head * HD + half * 40;
-    {
-      uint32_t t0[32], t1[8];                            // this half's 40 output columns
-      tmem_ld_x32(tmem + lane_addr + 128 + half * 40, t0);
-      tmem_ld_x8(tmem + lane_addr + 128 + half * 40 + 32, t1);
+    uint16_t* dst = static_cast<uint16_t*>(a.out) + (int64_t)(q0 + row) * a.hidden + head * HD;
+#pragma unroll
+    for (int c = 0; c < 80; c += 16) {
+      uint32_t t[16];
+      tmem_ld_x16(tmem + lane_addr + 128 + c, t);
       tmem_ld_wait();
       if (row < q_len) {
 #pragma unroll
-        for (int h = 0; h < 4; ++h)
-          *reinterpret_cast<uint4*>(dst + 8 * h) =
-              make_uint4(pack2<F16>(__uint_as_float(t0[8 * h]) * inv, __uint_as_float(t0[8 * h + 1]) * inv),
-                         pack2<F16>(__uint_as_float(t0[8 * h + 2]) * inv, __uint_as_float(t0[8 * h + 3]) * inv),
-                         pack2<F16>(__uint_as_float(t0[8 * h + 4]) * inv, __uint_as_float(t0[8 * h + 5]) * inv),
-                         pack2<F16>(__uint_as_float(t0[8 * h + 6]) * inv, __uint_as_float(t0[8 * h + 7]) * inv));
-        *reinterpret_cast<uint4*>(dst + 32) =
-            make_uint4(pack2<F16>(__uint_as_float(t1[0]) * inv, __uint_as_float(t1[1]) * inv),
-                       pack2<F16>(__uint_as_float(t1[2]) * inv, __uint_as_float(t1[3]) * inv),
-                       pack2<F16>(__uint_as_float(t1[4]) * inv, __uint_as_float(t1[5]) * inv),
-                       pack2<F16>(__uint_as_float(t1[6]) * inv, __uint_as_float(t1[7]) * inv));
+        for (int h = 0; h < 2; ++h)
+          *reinterpret_cast<uint4*>(dst + c + 8 * h) =
+              make_uint4(pack2<F16>(__uint_as_float(t[8 * h]) * inv, __uint_as_float(t[8 * h + 1]) * inv),
+                         pack2<F16>(__uint_as_float(t[8 * h + 2]) * inv, __uint_as_float(t[8 * h + 3]) * inv),
+                         pack2<F16>(__uint_as_float(t[8 * h + 4]) * inv, __uint_as_float(t[8 * h + 5]) * inv),
+                         pack2<F16>(__uint_as_float(t[8 * h + 6]) * inv, __uint_as_float(t[8 * h + 7]) * inv));
       }
     }
     tc_fence_before();
