@@ -62,21 +62,6 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-// 2^x without the SFU (x <= ~10): round-to-nearest split x = n + f with the 1.5*2^23 trick, degree-4 polynomial for
-// 2^f on [-0.5, 0.5] (max rel err 4e-5, below the 16-bit rounding of P), n added into the exponent field.  Used for a
-// quarter of the scores so that the SFU (16 exp2/clk/SM), which bounds this kernel, only sees the other three quarters.
-__device__ __forceinline__ float ex2_poly(float x) {
-  x = fmaxf(x, -126.0f);
-  const float t = x + 12582912.0f;
-  const float f = x - (t - 12582912.0f);
-  float p = 0.0096181291f;
-  p = fmaf(p, f, 0.0555041087f);
-  p = fmaf(p, f, 0.2402265070f);
-  p = fmaf(p, f, 0.6931471806f);
-  p = fmaf(p, f, 1.0f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
-
 struct AttnArgs {
   void* out;
   const int4* tiles;
@@ -253,10 +238,7 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const __grid_const
       const float ms = m_used * sl2;
       uint32_t pk[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float x0 = s[2 * i] * sl2 - ms, x1 = s[2 * i + 1] * sl2 - ms;
-        pk[i] = pack2<F16>(ex2_approx(x0), (i & 1) ? ex2_poly(x1) : ex2_approx(x1));      // every 4th score off the SFU
-      }
+      for (int i = 0; i < 32; ++i) pk[i] = pack2<F16>(ex2_approx(s[2 * i] * sl2 - ms), ex2_approx(s[2 * i + 1] * sl2 - ms));
       // P row -> shared memory, K-major 128B swizzle: 16-byte chunk c of row r lives at chunk (c ^ (r & 7))
 #pragma unroll
       for (int c = 0; c < 8; ++c)
