@@ -128,3 +128,43 @@ def test_k1_errors(cuda):
         fp.preprocess_crops([dev], None)
     with pytest.raises(ValueError, match="Coordinate 'right' is less than 'left'"):
         fp.preprocess_crops([dev], [(50, 0, 40, 10)])
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_k1_random_sweep_bitexact(cuda, seed):
+    """Randomised parity sweep: image sizes with aligned and unaligned row pitches, boxes inside / partly outside the
+    image, scales from 4x upscale to 12x downscale (every tap-window class of the dp4a path and the per-tap path),
+    ragged batches, fp32 HF order and bf16 window order - all bit-exact against the oracle."""
+    from zoomearth_b200 import FusedImageProcessor
+    rng = np.random.default_rng(1234 + seed)
+    imgs = []
+    for _ in range(3):
+        h, w = int(rng.integers(120, 1500)), int(rng.integers(120, 1500))
+        if rng.random() < 0.5:
+            w = (w // 4) * 4 + int(rng.integers(1, 4))          # pitch not a multiple of 4 -> generic kernels
+        else:
+            w = (w // 4) * 4
+        imgs.append(rng.integers(0, 256, (h, w, 3), dtype=np.uint8))
+    dev = [torch.from_numpy(i).to(cuda) for i in imgs]
+    for max_pixels in (3136 * 4, 50176, 401408, 12845056):
+        boxes, index = [], []
+        for _ in range(6):
+            k = int(rng.integers(0, 3))
+            h, w, _ = imgs[k].shape
+            bw, bh = int(rng.integers(20, w + 40)), int(rng.integers(20, h + 40))
+            bw, bh = max(bw, bh // 150 + 1), max(bh, bw // 150 + 1)          # keep the aspect ratio below 200
+            x0, y0 = int(rng.integers(-30, max(1, w - bw + 30))), int(rng.integers(-30, max(1, h - bh + 30)))
+            boxes.append((x0, y0, x0 + bw, y0 + bh))
+            index.append(k)
+        fp = FusedImageProcessor(min_pixels=3136, max_pixels=max_pixels, device=cuda)
+        pv, grid, crop = fp.preprocess_crops(dev, boxes, torch.float32, image_index=index)
+        refs, grids = zip(*[_oracle_crop(imgs[k], b, 3136, max_pixels) for b, k in zip(boxes, index)])
+        ref = np.concatenate(refs, 0)
+        assert grid.tolist() == np.concatenate(grids, 0).tolist()
+        got = pv.cpu().numpy()
+        bad = np.flatnonzero(got.view(np.uint32).ravel() != ref.view(np.uint32).ravel())
+        assert bad.size == 0, f"max_pixels {max_pixels}: {bad.size} of {got.size} values differ (boxes {boxes})"
+        pvw, _, _ = fp.preprocess_crops(dev, boxes, torch.bfloat16, window_order=True, image_index=index)
+        widx, _ = OT.window_index(np.concatenate(grids, 0))
+        ref_w = torch.from_numpy(ref).view(-1, 4, 1176)[torch.from_numpy(widx)].reshape(-1, 1176).to(torch.bfloat16)
+        assert torch.equal(pvw.cpu(), ref_w)

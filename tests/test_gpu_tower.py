@@ -22,7 +22,8 @@ def _fused(sd, cfg, cuda, dtype=torch.float32, operand_dtype=None):
                        fullatt=list(cfg["fullatt"]))
 
 
-@pytest.mark.parametrize("grid", [[[1, 8, 8]], [[1, 26, 36], [1, 8, 8], [1, 18, 34], [1, 2, 2]], [[1, 36, 36]]])
+@pytest.mark.parametrize("grid", [[[1, 2, 2]], [[1, 8, 8]], [[1, 26, 36], [1, 8, 8], [1, 18, 34], [1, 2, 2]], [[1, 36, 36]],
+                                  [[1, 2, 200]]])
 def test_tower_small_depth_vs_oracle(cuda, grid):
     cfg = OT.small_cfg(depth=3, fullatt=(1,))
     sd = OT.make_weights(1, cfg)
