@@ -346,7 +346,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--images", type=int, default=64, help="images per step per GPU (BASELINE configs[1]: 64)")
     ap.add_argument("--e2e-images", type=int, default=64)
-    ap.add_argument("--e2e-chunk", type=int, default=16, help="images per pipelined upload/compute chunk in the e2e leg")
+    ap.add_argument("--e2e-chunk", type=int, default=8, help="images per pipelined upload/compute chunk in the e2e leg")
     ap.add_argument("--ref-images", type=int, default=1, help="images in the CPU reference sample")
     ap.add_argument("--nccl-gather", action="store_true", help="gather embeddings with NCCL instead of the fused peer stores")
     ap.add_argument("--no-e2e", action="store_true")

@@ -45,7 +45,7 @@ class ZoomEncoder:
         return emb, grid, crop
 
     @torch.no_grad()
-    def encode_host(self, host_images, chunk=16, out_host=None):
+    def encode_host(self, host_images, chunk=8, out_host=None):
         """Global views of HOST images (pinned (H, W, 3) uint8 tensors), pipelined: the pixels of chunk i+1 are
         copied to the GPU on a side stream while chunk i runs through K1 + the tower, and the embeddings of chunk i
         go back to `out_host` (pinned) behind the compute.  Returns (out_host, image_grid_thw).  This is the ingest
