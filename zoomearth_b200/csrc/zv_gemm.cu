@@ -328,43 +328,6 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int m_blk, int n_b
   }
 }
 
-// RMSNorm of the rows [row0, row0+128) of X (fp32, N = 1280 columns) by the 8 epilogue warps: warp w takes 16 rows.
-// Runs in the CTA that finished the last column tile of the block; X was just written by up to five other SMs, so it
-// is read with ld.global.cg (L2, never a stale L1 line).  y = w * (x * rsqrt(mean(x^2) + eps)), as rmsnorm_kernel.
-__device__ __forceinline__ void fused_rmsnorm_block(const GemmArgs& g, int row0, int ewarp, int lane) {
-  const int N = g.N;                       // 1280
-  const int nv = N / 4;
-  const float4* wr = reinterpret_cast<const float4*>(g.norm_w);
-  for (int r = ewarp; r < BM; r += 8) {
-    const int row = row0 + r;
-    if (row >= g.M) break;
-    const float4* xr = reinterpret_cast<const float4*>(static_cast<const float*>(g.out) + (int64_t)row * g.ldo);
-    float4 v[10];
-    float ss = 0.f;
-#pragma unroll
-    for (int i = 0; i < 10; ++i) {
-      const int idx = lane + 32 * i;
-      if (idx < nv) {
-        v[i] = __ldcg(xr + idx);
-        ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
-      }
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    const float rs = rsqrtf(ss / (float)N + g.norm_eps);
-    uint2* yr = reinterpret_cast<uint2*>(static_cast<uint16_t*>(g.norm_out) + (int64_t)row * N);
-#pragma unroll
-    for (int i = 0; i < 10; ++i) {
-      const int idx = lane + 32 * i;
-      if (idx < nv) {
-        const float4 w = __ldg(wr + idx);
-        yr[idx] = make_uint2(pack2(w.x * (v[i].x * rs), w.y * (v[i].y * rs), g.norm_f16 != 0),
-                             pack2(w.z * (v[i].z * rs), w.w * (v[i].w * rs), g.norm_f16 != 0));
-      }
-    }
-  }
-}
-
 // cta_group::2 helpers (CTA pair = cluster of 2 along M; the even CTA is the MMA leader)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -515,21 +478,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc(const __grid_constant__ C
       __syncwarp();
       if (lane == 0) {
         if constexpr (CG == 2) mbar_arrive_cta(tempty + acc, 0); else mbar_arrive(tempty + acc);
-      }
-      if constexpr (EPI == EPI_RESID) {
-        if (g.norm_w != nullptr) {
-          // all eight epilogue warps have stored their part of the tile -> publish it and count the arrival; the CTA
-          // that brings the block's counter to n_blocks owns the norm of the block's 128 rows
-          __threadfence();
-          asm volatile("bar.sync 5, 256;" ::: "memory");
-          int* flag = reinterpret_cast<int*>(tmem_slot + 1);
-          if (warp == 4 && lane == 0) *flag = atomicAdd(g.norm_cnt + m_blk, 1);
-          asm volatile("bar.sync 5, 256;" ::: "memory");
-          if (*flag == n_blocks - 1) {
-            __threadfence();
-            fused_rmsnorm_block(g, m_blk * BM, warp - 4, lane);
-          }
-        }
       }
     }
   }

@@ -23,13 +23,6 @@ struct GemmArgs {
   void* peers[8];
   int n_peers;
   int64_t peer_row_off;
-  // EPI_RESID with the following RMSNorm fused in: the CTA that completes the last column tile of a 128-row block
-  // (per-block arrival counter) normalises those rows straight out of L2 and writes them as 16-bit GEMM operands
-  const float* norm_w;      // [N] gain of the RMSNorm that follows (null = no fused norm)
-  void* norm_out;           // (M, N) 16-bit, row pitch N
-  int* norm_cnt;            // [ceil(M / 128)] zeroed before the launch
-  float norm_eps;
-  int norm_f16;
 };
 
 // C = A[M,K] * B[N,K]^T with the chosen epilogue, enqueued on `stream`.

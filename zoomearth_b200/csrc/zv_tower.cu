@@ -296,7 +296,7 @@ int zv_weights_pack(const zv_cfg* cfg, const zv_tensor* tensors, int32_t n, void
 }
 
 namespace {
-struct Workspace { int64_t p = 0, x = 0, y = 0, big = 0, vt = 0, cnt = 0, s_pad = 0, bytes = 0; };
+struct Workspace { int64_t p = 0, x = 0, y = 0, big = 0, vt = 0, s_pad = 0, bytes = 0; };
 Workspace workspace_layout(const zv_cfg* c, int64_t S) {
   Workspace w;
   const int64_t H = c->hidden;
@@ -309,7 +309,6 @@ Workspace workspace_layout(const zv_cfg* c, int64_t S) {
   w.big = take(S * wide * 2);
   w.s_pad = (S + 7) / 8 * 8;
   w.vt = take(w.s_pad * H * 2);          // V^T per head for the tcgen05 full-attention kernel
-  w.cnt = take(((S + 127) / 128) * 4);   // per-128-row arrival counters of the residual GEMMs' fused RMSNorm
   w.bytes = off;
   return w;
 }
@@ -381,21 +380,6 @@ int visual_forward_impl(const zv_cfg* cfg, const void* weights_dev, const zv_pla
   void* BIG = ws + W.big;
   int64_t launches = 0;
   const bool legacy_full = std::getenv("ZV_ATTN_LEGACY") != nullptr;   // debug: mma.sync kernel for the full layers too
-  const bool fuse_norm = std::getenv("ZV_NO_FUSED_NORM") == nullptr;   // debug: standalone rmsnorm kernels everywhere
-  int* d_cnt = reinterpret_cast<int*>(ws + W.cnt);
-  const size_t cnt_bytes = (size_t)((S + 127) / 128) * 4;
-  // residual GEMM whose epilogue also applies the RMSNorm that follows it (gain `nw`), writing the normalised rows to Y
-  auto resid_gemm = [&](const void* A, int64_t K, const void* Wt, const float* bias, const float* nw) -> int {
-    GemmArgs r{};
-    r.op_f16 = f16;
-    r.M = (int)S; r.N = (int)H; r.K = (int)K; r.out = X; r.ldo = H; r.out_dtype = ZV_F32; r.bias = bias;
-    if (fuse_norm && nw) {
-      cudaError_t ce = cudaMemsetAsync(d_cnt, 0, cnt_bytes, static_cast<cudaStream_t>(stream));
-      if (ce != cudaSuccess) return fail(ZV_ECUDA, "zv_visual_forward: counter memset: %s", cudaGetErrorString(ce));
-      r.norm_w = nw; r.norm_out = Y; r.norm_cnt = d_cnt; r.norm_eps = cfg->eps; r.norm_f16 = f16;
-    }
-    return gemm(EPI_RESID, r, A, K, Wt, K, stream);
-  };
 #define ZV_TRY(expr) do { rc = (expr); if (rc) return rc; } while (0)
 
   // patches -> bf16, window order
@@ -415,9 +399,9 @@ int visual_forward_impl(const zv_cfg* cfg, const void* weights_dev, const zv_pla
   for (int l = 0; l < cfg->depth; ++l) {
     const LayerOff& o = L.layers[l];
     const bool full = (cfg->fullatt_mask_lo >> l) & 1;
-    // Y = rmsnorm1(X): fused into the previous block's down GEMM, except for the first block
-    if (l == 0 || !fuse_norm) ZV_TRY(rmsnorm(X, reinterpret_cast<const float*>(wb + o.n1), Y, f16, S, (int)H, cfg->eps, stream));
+    ZV_TRY(rmsnorm(X, reinterpret_cast<const float*>(wb + o.n1), Y, f16, S, (int)H, cfg->eps, stream));
     g = GemmArgs{};
+  g.op_f16 = f16;
     g.op_f16 = f16;
     g.M = (int)S; g.N = (int)(3 * H); g.K = (int)H; g.out = BIG; g.ldo = 3 * H; g.out_dtype = op;
     g.bias = reinterpret_cast<const float*>(wb + o.bqkv); g.pos = d_pos; g.rope = d_rope; g.heads = cfg->heads;
@@ -428,25 +412,32 @@ int visual_forward_impl(const zv_cfg* cfg, const void* weights_dev, const zv_pla
     } else {
       ZV_TRY(attention(BIG, Y, cfg->heads, (int)(H / cfg->heads), full ? d_full : d_win, full ? p->n_full_tiles : p->n_win_tiles, stream, full, f16 != 0));
     }
-    // X += A Wo^T + b, and Y = rmsnorm2(X) for the blocks whose last column tile just landed (Y's rows of a block
-    // are free by then: every tile that read them as the A operand has finished)
-    ZV_TRY(resid_gemm(Y, H, wb + o.wo, reinterpret_cast<const float*>(wb + o.bo), reinterpret_cast<const float*>(wb + o.n2)));
-    if (!fuse_norm) ZV_TRY(rmsnorm(X, reinterpret_cast<const float*>(wb + o.n2), Y, f16, S, (int)H, cfg->eps, stream));
     g = GemmArgs{};
+  g.op_f16 = f16;
+    g.op_f16 = f16;
+    g.M = (int)S; g.N = (int)H; g.K = (int)H; g.out = X; g.ldo = H; g.out_dtype = ZV_F32;
+    g.bias = reinterpret_cast<const float*>(wb + o.bo);
+    ZV_TRY(gemm(EPI_RESID, g, Y, H, wb + o.wo, H, stream));
+    ZV_TRY(rmsnorm(X, reinterpret_cast<const float*>(wb + o.n2), Y, f16, S, (int)H, cfg->eps, stream));
+    g = GemmArgs{};
+  g.op_f16 = f16;
     g.op_f16 = f16;
     g.M = (int)S; g.N = (int)(2 * IP); g.K = (int)H; g.out = BIG; g.ldo = IP; g.out_dtype = op;
     g.bias = reinterpret_cast<const float*>(wb + o.bgu);
     ZV_TRY(gemm(EPI_SWIGLU, g, Y, H, wb + o.wgu, H, stream));
-    // X += H Wd^T + b, and Y = the NEXT norm of X: norm1 of block l+1, or the merger's ln_q after the last block
-    const float* next_norm = reinterpret_cast<const float*>(l + 1 < cfg->depth ? wb + L.layers[l + 1].n1 : wb + L.ln_q);
-    ZV_TRY(resid_gemm(BIG, IP, wb + o.wd, reinterpret_cast<const float*>(wb + o.bd), next_norm));
+    g = GemmArgs{};
+  g.op_f16 = f16;
+    g.op_f16 = f16;
+    g.M = (int)S; g.N = (int)H; g.K = (int)IP; g.out = X; g.ldo = H; g.out_dtype = ZV_F32;
+    g.bias = reinterpret_cast<const float*>(wb + o.bd);
+    ZV_TRY(gemm(EPI_RESID, g, BIG, IP, wb + o.wd, IP, stream));
   }
   if (hidden_out_dev) {
     cudaError_t e = cudaMemcpyAsync(hidden_out_dev, X, (size_t)(S * H * 4), cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return fail(ZV_ECUDA, "zv_visual_forward: hidden copy: %s", cudaGetErrorString(e));
   }
   // merger (HF :133-146) + un-reorder (HF :512-513)
-  if (!fuse_norm) ZV_TRY(rmsnorm(X, reinterpret_cast<const float*>(wb + L.ln_q), Y, f16, S, (int)H, cfg->eps, stream));
+  ZV_TRY(rmsnorm(X, reinterpret_cast<const float*>(wb + L.ln_q), Y, f16, S, (int)H, cfg->eps, stream));
   g = GemmArgs{};
   g.op_f16 = f16;
   g.M = (int)T; g.N = (int)(4 * H); g.K = (int)(4 * H); g.out = BIG; g.ldo = 4 * H; g.out_dtype = op;
