@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <type_traits>
 
 #include "zv_common.h"
 #include "zv_gemm.h"
@@ -190,7 +191,40 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const __grid_const
     float m_used = -INFINITY;               // scale in use (raw score units); the row sum lives in O column 80
     uint8_t* prow = smem + kOffP + row * 128;
 
-    for (int j = 0; j < n_kv; ++j) {
+    // rescale the O row (and its sum column) by `factor` - warp-collective TMEM round trip, only when some row's
+    // running max grew by more than 2^8
+    auto rescale_o = [&](const float factor) {
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < VROWS; c += 16) {
+        uint32_t t[16];
+        tmem_ld_x16(tmem + lane_addr + 128 + c, t);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * factor);
+        tmem_st_x16(tmem + lane_addr + 128 + c, t);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+    };
+    // this thread's P row -> shared memory, K-major 128B swizzle: chunk c of row r lives at
+    // chunk (c ^ (r & 7))
+    // (st.shared through the 32-bit shared address: the generic-pointer form compiles to ST.E, whose completion the
+    // proxy fence below then waits on for several hundred cycles)
+    const uint32_t prow_s = smem_u32(prow);
+    auto store_p = [&](const uint32_t (&pk)[32]) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow_s + ((c ^ (row & 7)) << 4)), "r"(pk[4 * c]),
+                     "r"(pk[4 * c + 1]), "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3])
+                     : "memory");
+    };
+
+    // One KV tile.  MASK = the tile may hold columns outside [seg_b, seg_e) (only the first and the last tile of a
+    // segment can): the column mask is compiled into that instantiation alone - the compiler if-converts it into
+    // 2 x 64 compares and selects, which the interior tiles must not carry (it doubled the kernel's instruction count).
+    auto softmax_tile = [&](const int j, auto mask_tag) {
+      constexpr bool MASK = decltype(mask_tag)::value;
       mbar_wait(s_full + (j & 1), (j >> 1) & 1);
       tc_fence_after();
       uint32_t r0[32], r1[32];
@@ -203,8 +237,8 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const __grid_const
       float s[64];
 #pragma unroll
       for (int i = 0; i < 32; ++i) { s[i] = __uint_as_float(r0[i]); s[32 + i] = __uint_as_float(r1[i]); }
-      const int lo = seg_b - (kv_base + j * BKV), hi = seg_e - (kv_base + j * BKV);   // valid columns: [lo, hi)
-      if (lo > 0 || hi < BKV) {
+      if constexpr (MASK) {
+        const int lo = seg_b - (kv_base + j * BKV), hi = seg_e - (kv_base + j * BKV);   // valid columns: [lo, hi)
 #pragma unroll
         for (int i = 0; i < 64; ++i) if (i < lo || i >= hi) s[i] = -INFINITY;
       }
@@ -218,34 +252,23 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const __grid_const
       const bool grow = (mx - m_used) * sl2 > 8.0f;          // true on the first tile (m_used = -inf)
       float factor = 1.0f;
       if (grow) { factor = ex2_approx((m_used - mx) * sl2); m_used = mx; }
-      if (j > 0) {
-        mbar_wait(pv_done, (j - 1) & 1);                     // P buffer free, O_{j-1} accumulated
-        if (__any_sync(0xffffffffu, grow)) {
-          tc_fence_after();
-#pragma unroll
-          for (int c = 0; c < VROWS; c += 16) {
-            uint32_t t[16];
-            tmem_ld_x16(tmem + lane_addr + 128 + c, t);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * factor);
-            tmem_st_x16(tmem + lane_addr + 128 + c, t);
-          }
-          tmem_st_wait();
-          tc_fence_before();
-        }
-      }
+      // the exponentials only need registers: they run while the tensor core is still busy with P_{j-1} V_{j-1}
       const float ms = m_used * sl2;
       uint32_t pk[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) pk[i] = pack2<F16>(ex2_approx(s[2 * i] * sl2 - ms), ex2_approx(s[2 * i + 1] * sl2 - ms));
-      // P row -> shared memory, K-major 128B swizzle: 16-byte chunk c of row r lives at chunk (c ^ (r & 7))
-#pragma unroll
-      for (int c = 0; c < 8; ++c)
-        *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+      if (j > 0) {
+        mbar_wait(pv_done, (j - 1) & 1);                     // P buffer free, O_{j-1} accumulated
+        if (__any_sync(0xffffffffu, grow)) rescale_o(factor);
+      }
+      store_p(pk);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
+    };
+    for (int j = 0; j < n_kv; ++j) {
+      if (j == 0 || j == n_kv - 1) softmax_tile(j, std::true_type{});
+      else softmax_tile(j, std::false_type{});
     }
     mbar_wait(pv_done, (n_kv - 1) & 1);
     tc_fence_after();

@@ -39,3 +39,46 @@ def random_vision_state_dict(seed=0, device="cpu", std=0.02, **overrides):
     sd["merger.mlp.2.weight"] = lin(O, 4 * H)
     sd["merger.mlp.2.bias"] = vec(O)
     return sd
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Crop-box workloads of BASELINE.json configs[2..4].  Boxes are in source-image pixels, (x0, y0, x1, y1),
+# BEFORE the reference's cut_image() rule (src/eval/infer.py:41-76), which the encoder applies.
+import numpy as np
+
+
+def trajectory_boxes(n_questions=256, img=5000):
+    """configs[2]: per question three nested boxes, (w1,h1)~U[1536,3072]^2 inside the image, (w2,h2)~U[768,1536]^2
+    inside box 1, (w3,h3)~U[256,768]^2 inside box 2, rng = default_rng(1000 + q).  Returns (n_questions, 3, 4) int64."""
+    out = np.zeros((n_questions, 3, 4), np.int64)
+    for q in range(n_questions):
+        rng = np.random.default_rng(1000 + q)
+        x0, y0, w, h = 0, 0, img, img
+        for d, (lo, hi) in enumerate(((1536, 3072), (768, 1536), (256, 768))):
+            nw = int(rng.integers(lo, min(hi, w) + 1))
+            nh = int(rng.integers(lo, min(hi, h) + 1))
+            x0 += int(rng.integers(0, w - nw + 1))
+            y0 += int(rng.integers(0, h - nh + 1))
+            w, h = nw, nh
+            out[q, d] = (x0, y0, x0 + w, y0 + h)
+    return out
+
+
+def mixed_crop_boxes(n=1024, n_images=16, img=5000, lo=256, hi=2048, seed=4):
+    """configs[3]: n boxes with independent sides ~U[lo,hi] placed uniformly in one of n_images source images.
+    Returns (boxes (n, 4) int64, image_index (n,) int64)."""
+    rng = np.random.default_rng(seed)
+    w = rng.integers(lo, hi + 1, n)
+    h = rng.integers(lo, hi + 1, n)
+    x = (rng.random(n) * (img - w + 1)).astype(np.int64)
+    y = (rng.random(n) * (img - h + 1)).astype(np.int64)
+    return np.stack([x, y, x + w, y + h], 1).astype(np.int64), rng.integers(0, n_images, n)
+
+
+def maxres_boxes(n_3584=64, n_full=64, img=5000):
+    """configs[4]: 3584x3584 boxes (grid 256x256 at max_pixels = 16384*28*28) and full 5000x5000 images (254x254)."""
+    rng = np.random.default_rng(5)
+    xy = rng.integers(0, img - 3584 + 1, (n_3584, 2))
+    a = np.concatenate([xy, xy + 3584], 1)
+    b = np.tile(np.array([[0, 0, img, img]]), (n_full, 1))
+    return np.concatenate([a, b], 0).astype(np.int64)

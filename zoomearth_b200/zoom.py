@@ -44,8 +44,61 @@ class ZoomEncoder:
             return emb, grid, crop, pv
         return emb, grid, crop
 
+    def micro_batches(self, images_dev, boxes, image_index=None, max_patches=400_000, apply_cut_image=True):
+        """Splits a ragged crop list into consecutive micro-batches of at most ``max_patches`` patches (a crop larger
+        than the budget is a batch of its own), so the tower's workspace stays bounded whatever the batch
+        (the reference feeds one question at a time, infer.py:232-247; here hundreds go in one call).
+        Returns a list of index lists into ``boxes``."""
+        from . import geometry
+        n = len(images_dev) if boxes is None else len(boxes)
+        idx = list(range(n)) if image_index is None else list(image_index)
+        cfg = self.processor._cfg()
+        if boxes is None or not apply_cut_image:
+            cfg.min_size = -1
+        img_hw = np.array([[images_dev[i].shape[0], images_dev[i].shape[1]] for i in idx], np.int32)
+        bx = None if boxes is None else np.asarray(boxes, np.float64).reshape(n, 4)
+        _, _, grid = geometry.geometry(cfg, img_hw, bx)
+        patches = grid[:, 1] * grid[:, 2]
+        out, cur, tot = [], [], 0
+        for i, s in enumerate(patches):
+            if cur and tot + int(s) > max_patches:
+                out.append(cur)
+                cur, tot = [], 0
+            cur.append(i)
+            tot += int(s)
+        if cur:
+            out.append(cur)
+        return out
+
     @torch.no_grad()
-    def encode_host(self, host_images, chunk=8, out_host=None):
+    def encode_batched(self, images_dev, boxes=None, image_index=None, max_patches=400_000, apply_cut_image=True,
+                       out=None):
+        """``encode`` over micro-batches of at most ``max_patches`` patches; embeddings land back to back in one
+        tensor, in the order of ``boxes``.  Returns (embeddings, image_grid_thw, crop boxes)."""
+        n = len(images_dev) if boxes is None else len(boxes)
+        idx = list(range(n)) if image_index is None else list(image_index)
+        groups = self.micro_batches(images_dev, boxes, image_index, max_patches, apply_cut_image)
+        embs, grids, crops, launches = [], [], [], 0
+        for g in groups:
+            used = sorted({idx[i] for i in g})
+            local = {k: j for j, k in enumerate(used)}
+            e, grid, crop = self.encode([images_dev[k] for k in used],
+                                        None if boxes is None else [boxes[i] for i in g],
+                                        image_index=[local[idx[i]] for i in g], apply_cut_image=apply_cut_image)
+            launches += self.last_launches
+            embs.append(e); grids.append(grid); crops.append(crop)
+        self.last_launches = launches
+        if out is None:
+            out = torch.cat(embs, 0) if len(embs) > 1 else embs[0]
+        else:
+            row = 0
+            for e in embs:
+                out[row:row + e.shape[0]].copy_(e)
+                row += e.shape[0]
+        return out, torch.cat(grids, 0), np.concatenate(crops, 0)
+
+    @torch.no_grad()
+    def encode_host(self, host_images, chunk=8, out_host=None, schedule=None):
         """Global views of HOST images (pinned (H, W, 3) uint8 tensors), pipelined: the pixels of chunk i+1 are
         copied to the GPU on a side stream while chunk i runs through K1 + the tower, and the embeddings of chunk i
         go back to `out_host` (pinned) behind the compute.  Returns (out_host, image_grid_thw).  This is the ingest
@@ -57,8 +110,18 @@ class ZoomEncoder:
             self._copy_stream = torch.cuda.Stream(dev)
             self._d2h_stream = torch.cuda.Stream(dev)
         # a short first chunk keeps the exposed (un-overlapped) first upload small
-        first = max(1, chunk // 4) if len(host_images) > chunk else len(host_images)
-        groups = [host_images[:first]] + [host_images[i:i + chunk] for i in range(first, len(host_images), chunk)]
+        # (`schedule`: explicit chunk sizes instead, e.g. a ramp [2, 6, 8, 16, 32]; the last size repeats)
+        if schedule:
+            groups, i = [], 0
+            for k in range(len(host_images)):
+                if i >= len(host_images):
+                    break
+                n = schedule[min(k, len(schedule) - 1)]
+                groups.append(host_images[i:i + n])
+                i += n
+        else:
+            first = max(1, chunk // 4) if len(host_images) > chunk else len(host_images)
+            groups = [host_images[:first]] + [host_images[i:i + chunk] for i in range(first, len(host_images), chunk)]
         staged = []
 
         def stage(g):
