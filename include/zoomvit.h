@@ -22,6 +22,11 @@
  *                         :411-451 (get_window_index), :470-496 (cu_window_seqlens, cu_seqlens)
  *   zv_weights_*          state-dict import of `visual.*` (HF:modeling_qwen2_5_vl.py:345-380 module tree)
  *   zv_visual_forward     HF:modeling_qwen2_5_vl.py:455-518 (Qwen2_5_VisionTransformerPretrainedModel.forward)
+ *   zv_visual_forward_into  + HF:modeling_qwen2_5_vl.py:1301-1307 (get_placeholder_mask + masked_scatter into
+ *                         inputs_embeds; reference copy src/train/RL/.../open_r1/model/modeling_qwen2_vl.py:1191-1207)
+ *   zv_rope_index         reference .../open_r1/model/modeling_qwen2_vl.py:967-1114 (get_rope_index; by flag the
+ *                         transformers 5.x variant HF:modeling_qwen2_5_vl.py:1024-1135)
+ *   zv_placeholder_rows   the row list behind masked_scatter (HF:modeling_qwen2_5_vl.py:1179-1218)
  */
 #ifndef ZOOMVIT_H_
 #define ZOOMVIT_H_
@@ -152,6 +157,28 @@ ZV_API int zv_visual_forward_gather(const zv_cfg* cfg, const void* weights_dev, 
                                     const void* patches_dev, int32_t in_dtype, int32_t in_order, void* merged_out_dev,
                                     int32_t out_dtype, void* workspace_dev, int64_t workspace_bytes,
                                     void* const* peer_out_dev, int32_t n_peers, int64_t peer_row_off, void* stream);
+/* Same forward with the LM hand-off fused into the last GEMM's epilogue: embedding k (HF order) is written to row
+ * dest_rows_dev[k] of embeds_dev, the flattened (embeds_rows, out_hidden) inputs_embeds of the language model
+ * (element type embeds_dtype) - torch's inputs_embeds.masked_scatter(image_mask, image_embeds) without the
+ * (T, out_hidden) round trip.  dest_rows_dev: int64 [T] on the device (zv_placeholder_rows, or nonzero() of the mask). */
+ZV_API int zv_visual_forward_into(const zv_cfg* cfg, const void* weights_dev, const zv_plan* p, const void* plan_dev,
+                                  const void* patches_dev, int32_t in_dtype, int32_t in_order, void* embeds_dev,
+                                  int64_t embeds_rows, int32_t embeds_dtype, const int64_t* dest_rows_dev,
+                                  void* workspace_dev, int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- LM hand-off, host side (pure, no device) */
+/* Multimodal rotary position index.  input_ids / attention_mask (may be NULL): [batch][seq_len] int64 on the host;
+ * image_grid_thw [n_images][3] (NULL = text only); position_ids out [3][batch][seq_len], deltas out [batch].
+ * hf5_semantics 0: the reference's copy (padded positions 1, delta against the padded length); 1: transformers 5.x
+ * (padded positions 0, delta against the unpadded length). */
+ZV_API int zv_rope_index(const int64_t* input_ids, const int64_t* attention_mask, int32_t batch, int32_t seq_len,
+                         const int64_t* image_grid_thw, int32_t n_images, int64_t image_token_id,
+                         int64_t video_token_id, int64_t vision_start_token_id, int32_t merge, int32_t hf5_semantics,
+                         int64_t* position_ids, int64_t* deltas);
+/* Flattened rows holding the image placeholder, in order; writes at most rows_cap of them, returns the count. */
+ZV_API int64_t zv_placeholder_rows(const int64_t* input_ids, int64_t n_tokens, int64_t image_token_id,
+                                   int64_t* rows_out, int64_t rows_cap);
+
 /* Number of kernels the last zv_preprocess / zv_visual_forward call on this thread launched. */
 ZV_API int64_t zv_last_launch_count(void);
 

@@ -24,6 +24,9 @@ def __getattr__(name):            # torch-dependent pieces are imported lazily
     if name == "install":
         from .dropin import install
         return install
+    if name in ("get_rope_index", "embed_images", "placeholder_rows"):
+        from . import handoff
+        return getattr(handoff, name)
     if name == "Plan":
         from .plan import Plan
         return Plan

@@ -71,6 +71,11 @@ _PROTOS = {
     "zv_visual_forward_gather": (C.c_int, [_P(ZvCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                            C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int64,
                                            C.c_void_p]),
+    "zv_visual_forward_into": (C.c_int, [_P(ZvCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                         C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "zv_rope_index": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int64,
+                                C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "zv_placeholder_rows": (C.c_int64, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64]),
     "zv_last_launch_count": (C.c_int64, []),
     "zv_timing_enable": (None, [C.c_int]),
     "zv_timing_reset": (None, []),

@@ -94,6 +94,14 @@ __global__ void __launch_bounds__(256) gather_kernel(const SrcT* __restrict__ sr
   }
 }
 
+// LM hand-off: comp[i] = dest[widx[i]] - the inputs_embeds row of the embedding the merger computes at window
+// position i (widx: window position -> HF merge-group index; dest: HF embedding index -> placeholder row).
+__global__ void __launch_bounds__(256) compose_rows_kernel(const int64_t* __restrict__ dest, const int32_t* __restrict__ widx,
+                                                           int32_t* __restrict__ comp, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) comp[i] = (int32_t)dest[widx[i]];
+}
+
 // Weight import: dst[row_map(r)][c] = src[r][c] (to bf16 or f32).  mode 0 identity, 1 gate, 2 up
 // (gate/up rows interleaved in blocks of 128 so one 256-wide GEMM tile holds both halves of 128 outputs).
 template <typename SrcT, typename DstT>
@@ -296,7 +304,7 @@ int zv_weights_pack(const zv_cfg* cfg, const zv_tensor* tensors, int32_t n, void
 }
 
 namespace {
-struct Workspace { int64_t p = 0, x = 0, y = 0, big = 0, vt = 0, s_pad = 0, bytes = 0; };
+struct Workspace { int64_t p = 0, x = 0, y = 0, big = 0, vt = 0, comp = 0, s_pad = 0, bytes = 0; };
 Workspace workspace_layout(const zv_cfg* c, int64_t S) {
   Workspace w;
   const int64_t H = c->hidden;
@@ -309,6 +317,7 @@ Workspace workspace_layout(const zv_cfg* c, int64_t S) {
   w.big = take(S * wide * 2);
   w.s_pad = (S + 7) / 8 * 8;
   w.vt = take(w.s_pad * H * 2);          // V^T per head for the tcgen05 full-attention kernel
+  w.comp = take((S / 4 + 1) * 4);        // int32 [T]: composed scatter rows of zv_visual_forward_into
   w.bytes = off;
   return w;
 }
@@ -325,7 +334,8 @@ namespace {
 int visual_forward_impl(const zv_cfg* cfg, const void* weights_dev, const zv_plan* p, const void* plan_dev,
                         const void* patches_dev, int32_t in_dtype, int32_t in_order, void* merged_out_dev,
                         int32_t out_dtype, void* hidden_out_dev, void* workspace_dev, int64_t workspace_bytes,
-                        void* const* peer_out_dev, int32_t n_peers, int64_t peer_row_off, void* stream);
+                        void* const* peer_out_dev, int32_t n_peers, int64_t peer_row_off, const int64_t* dest_rows_dev,
+                        void* stream);
 }
 
 int zv_visual_forward(const zv_cfg* cfg, const void* weights_dev, const zv_plan* p, const void* plan_dev,
@@ -333,7 +343,17 @@ int zv_visual_forward(const zv_cfg* cfg, const void* weights_dev, const zv_plan*
                       int32_t out_dtype, void* hidden_out_dev, void* workspace_dev, int64_t workspace_bytes,
                       void* stream) {
   return visual_forward_impl(cfg, weights_dev, p, plan_dev, patches_dev, in_dtype, in_order, merged_out_dev, out_dtype,
-                             hidden_out_dev, workspace_dev, workspace_bytes, nullptr, 0, 0, stream);
+                             hidden_out_dev, workspace_dev, workspace_bytes, nullptr, 0, 0, nullptr, stream);
+}
+
+int zv_visual_forward_into(const zv_cfg* cfg, const void* weights_dev, const zv_plan* p, const void* plan_dev,
+                           const void* patches_dev, int32_t in_dtype, int32_t in_order, void* embeds_dev,
+                           int64_t embeds_rows, int32_t embeds_dtype, const int64_t* dest_rows_dev, void* workspace_dev,
+                           int64_t workspace_bytes, void* stream) {
+  if (!dest_rows_dev || !embeds_dev) return fail(ZV_EINVAL, "zv_visual_forward_into: null argument");
+  if (embeds_rows <= 0 || embeds_rows > INT32_MAX) return fail(ZV_EINVAL, "zv_visual_forward_into: inputs_embeds has %lld rows (1 .. 2^31-1 supported)", (long long)embeds_rows);
+  return visual_forward_impl(cfg, weights_dev, p, plan_dev, patches_dev, in_dtype, in_order, embeds_dev, embeds_dtype,
+                             nullptr, workspace_dev, workspace_bytes, nullptr, 0, 0, dest_rows_dev, stream);
 }
 
 int zv_visual_forward_gather(const zv_cfg* cfg, const void* weights_dev, const zv_plan* p, const void* plan_dev,
@@ -343,14 +363,15 @@ int zv_visual_forward_gather(const zv_cfg* cfg, const void* weights_dev, const z
   if (n_peers < 0 || n_peers > 8 || (n_peers > 0 && !peer_out_dev)) return fail(ZV_EINVAL, "zv_visual_forward_gather: bad peer list");
   if (n_peers > 0 && out_dtype == ZV_F32) return fail(ZV_EINVAL, "zv_visual_forward_gather: the fused gather writes 16-bit embeddings");
   return visual_forward_impl(cfg, weights_dev, p, plan_dev, patches_dev, in_dtype, in_order, merged_out_dev, out_dtype,
-                             nullptr, workspace_dev, workspace_bytes, peer_out_dev, n_peers, peer_row_off, stream);
+                             nullptr, workspace_dev, workspace_bytes, peer_out_dev, n_peers, peer_row_off, nullptr, stream);
 }
 
 namespace {
 int visual_forward_impl(const zv_cfg* cfg, const void* weights_dev, const zv_plan* p, const void* plan_dev,
                         const void* patches_dev, int32_t in_dtype, int32_t in_order, void* merged_out_dev,
                         int32_t out_dtype, void* hidden_out_dev, void* workspace_dev, int64_t workspace_bytes,
-                        void* const* peer_out_dev, int32_t n_peers, int64_t peer_row_off, void* stream) {
+                        void* const* peer_out_dev, int32_t n_peers, int64_t peer_row_off, const int64_t* dest_rows_dev,
+                        void* stream) {
   reset_launch_count();
   int rc = check_cfg(cfg, "zv_visual_forward");
   if (rc) return rc;
@@ -401,7 +422,6 @@ int visual_forward_impl(const zv_cfg* cfg, const void* weights_dev, const zv_pla
     const bool full = (cfg->fullatt_mask_lo >> l) & 1;
     ZV_TRY(rmsnorm(X, reinterpret_cast<const float*>(wb + o.n1), Y, f16, S, (int)H, cfg->eps, stream));
     g = GemmArgs{};
-  g.op_f16 = f16;
     g.op_f16 = f16;
     g.M = (int)S; g.N = (int)(3 * H); g.K = (int)H; g.out = BIG; g.ldo = 3 * H; g.out_dtype = op;
     g.bias = reinterpret_cast<const float*>(wb + o.bqkv); g.pos = d_pos; g.rope = d_rope; g.heads = cfg->heads;
@@ -413,20 +433,17 @@ int visual_forward_impl(const zv_cfg* cfg, const void* weights_dev, const zv_pla
       ZV_TRY(attention(BIG, Y, cfg->heads, (int)(H / cfg->heads), full ? d_full : d_win, full ? p->n_full_tiles : p->n_win_tiles, stream, full, f16 != 0));
     }
     g = GemmArgs{};
-  g.op_f16 = f16;
     g.op_f16 = f16;
     g.M = (int)S; g.N = (int)H; g.K = (int)H; g.out = X; g.ldo = H; g.out_dtype = ZV_F32;
     g.bias = reinterpret_cast<const float*>(wb + o.bo);
     ZV_TRY(gemm(EPI_RESID, g, Y, H, wb + o.wo, H, stream));
     ZV_TRY(rmsnorm(X, reinterpret_cast<const float*>(wb + o.n2), Y, f16, S, (int)H, cfg->eps, stream));
     g = GemmArgs{};
-  g.op_f16 = f16;
     g.op_f16 = f16;
     g.M = (int)S; g.N = (int)(2 * IP); g.K = (int)H; g.out = BIG; g.ldo = IP; g.out_dtype = op;
     g.bias = reinterpret_cast<const float*>(wb + o.bgu);
     ZV_TRY(gemm(EPI_SWIGLU, g, Y, H, wb + o.wgu, H, stream));
     g = GemmArgs{};
-  g.op_f16 = f16;
     g.op_f16 = f16;
     g.M = (int)S; g.N = (int)H; g.K = (int)IP; g.out = X; g.ldo = H; g.out_dtype = ZV_F32;
     g.bias = reinterpret_cast<const float*>(wb + o.bd);
@@ -447,6 +464,13 @@ int visual_forward_impl(const zv_cfg* cfg, const void* weights_dev, const zv_pla
   g.op_f16 = f16;
   g.M = (int)T; g.N = (int)O; g.K = (int)(4 * H); g.out = merged_out_dev; g.ldo = O; g.out_dtype = out_dtype;
   g.bias = reinterpret_cast<const float*>(wb + L.b2); g.scatter = d_widx;
+  if (dest_rows_dev) {
+    // LM hand-off (HF :1301-1307 masked_scatter): the un-reorder and the scatter into inputs_embeds are one index map
+    int32_t* comp = reinterpret_cast<int32_t*>(ws + W.comp);
+    compose_rows_kernel<<<(unsigned)((T + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dest_rows_dev, d_widx, comp, T);
+    count_launch();
+    g.scatter = comp;
+  }
   g.n_peers = n_peers; g.peer_row_off = peer_row_off;
   for (int i = 0; i < n_peers; ++i) g.peers[i] = peer_out_dev[i];
   ZV_TRY(gemm(EPI_SCATTER, g, BIG, 4 * H, wb + L.w2, 4 * H, stream));

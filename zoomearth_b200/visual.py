@@ -168,11 +168,33 @@ class FusedVisual(nn.Module):
         plan = self.plan_for(grid_thw)
         return self._forward_impl(hidden_states, plan, window_order, return_hidden, gather, gather_row)
 
-    def _forward_impl(self, hidden_states, plan, window_order, return_hidden, gather, gather_row, out=None):
-        """hidden_states: (S, 1176) patches, float32/bfloat16, HF row order (or the window-ordered bf16 output of
-        the fused preprocess when ``window_order=True``).  ``gather`` (a ``sharding.PeerGather``) fuses the multi-GPU
-        embedding gather into the last GEMM: this rank's rows land at ``gather_row`` of every rank's gather buffer."""
+    @torch.no_grad()
+    def forward_into(self, inputs_embeds, dest_rows, hidden_states, grid_thw, window_order=False):
+        """Tower forward with the LM hand-off fused into the last GEMM (``zv_visual_forward_into``): embedding k (HF
+        order) lands in row ``dest_rows[k]`` of the flattened ``inputs_embeds`` (B, L, out_hidden) - in place, the
+        result of ``inputs_embeds.masked_scatter(image_mask, self(hidden_states, grid_thw))`` (HF modeling_qwen2_5_vl.py
+        :1301-1307) without materialising the embeddings.  ``dest_rows``: int64 CUDA tensor (see handoff.placeholder_rows)."""
         lib = _lib.lib()
+        plan = self.plan_for(grid_thw)
+        e = inputs_embeds
+        if e.device != self._device or e.dtype not in _DT or not e.is_contiguous() or e.shape[-1] != self.cfg.out_hidden:
+            raise ValueError(f"inputs_embeds must be a contiguous (..., {self.cfg.out_hidden}) float32/bfloat16/float16 "
+                             f"tensor on {self._device}")
+        if dest_rows.dtype != torch.int64 or dest_rows.device != self._device or dest_rows.numel() != plan.num_tokens:
+            raise ValueError(f"dest_rows must be {plan.num_tokens} int64 row indices on {self._device}")
+        x = self._check_input(hidden_states, plan, window_order)
+        stream = torch.cuda.current_stream(self._device).cuda_stream
+        with torch.cuda.device(self._device):
+            tables = plan.device_tables(self._device, stream)
+            ws = self._workspace(_lib.check(lib.zv_visual_workspace_bytes(C.byref(self.cfg), plan.handle)))
+            _lib.check(lib.zv_visual_forward_into(
+                C.byref(self.cfg), self.packed_weights.data_ptr(), plan.handle, tables.data_ptr(), x.data_ptr(),
+                _DT[x.dtype], _lib.ORDER_WINDOW if window_order else _lib.ORDER_HF, e.data_ptr(),
+                e.numel() // e.shape[-1], _DT[e.dtype], dest_rows.contiguous().data_ptr(), ws.data_ptr(), ws.numel(), stream))
+        self.last_launches = lib.zv_last_launch_count()
+        return inputs_embeds
+
+    def _check_input(self, hidden_states, plan, window_order):
         x = hidden_states
         if x.device != self._device:
             x = x.to(self._device, non_blocking=True)
@@ -183,6 +205,14 @@ class FusedVisual(nn.Module):
         x = x.contiguous()
         if x.shape != (plan.num_patches, 1176):
             raise ValueError(f"pixel_values has shape {tuple(x.shape)}, grid_thw implies ({plan.num_patches}, 1176)")
+        return x
+
+    def _forward_impl(self, hidden_states, plan, window_order, return_hidden, gather, gather_row, out=None):
+        """hidden_states: (S, 1176) patches, float32/bfloat16, HF row order (or the window-ordered bf16 output of
+        the fused preprocess when ``window_order=True``).  ``gather`` (a ``sharding.PeerGather``) fuses the multi-GPU
+        embedding gather into the last GEMM: this rank's rows land at ``gather_row`` of every rank's gather buffer."""
+        lib = _lib.lib()
+        x = self._check_input(hidden_states, plan, window_order)
         stream = torch.cuda.current_stream(self._device).cuda_stream
         with torch.cuda.device(self._device):
             tables = plan.device_tables(self._device, stream)
