@@ -48,8 +48,10 @@ def test_embed_images_equals_masked_scatter(cuda, embed_dtype):
     # the oracle's statement of the same scatter
     assert np.array_equal(OH.masked_scatter(emb0.float().cpu().numpy(), ids.cpu().numpy(), feats.float().cpu().numpy(), IMG),
                           ref.float().cpu().numpy())
+    short = ids.clone()
+    short[0, int((ids[0] == IMG).nonzero()[0])] = PAD          # one placeholder fewer than embeddings
     with pytest.raises(ValueError, match="do not match"):
-        embed_images(fv, emb0.clone(), ids[:, 1:], pv, grid)
+        embed_images(fv, emb0.clone(), short, pv, grid)
 
 
 def test_embed_images_from_fused_preprocess(cuda):

@@ -190,144 +190,156 @@ __global__ void __launch_bounds__(256) k1_vpass(const K1Crop* __restrict__ crops
 // Limb table of one axis: per output index, (1 + 3 NW) ints: first word of the tap window (in 4-sample words from the
 // axis origin), then NW words of limb 0, NW of limb 1, NW of limb 2 (signed bytes); taps outside the window are 0.
 
-// Horizontal pass on dp4a.  Block = (8 tmp rows) x (128 output columns) of one crop.
+// Both fast kernels are persistent: the grid is a few CTAs per SM and every CTA walks a host-built work list
+// (int4 items) with a stride of gridDim.x.  An item fixes everything that needs dependent global loads (crop
+// descriptor, tap tables of the item's columns / rows) and then covers several units of streaming work, whose loads
+// are double-buffered with cp.async so that the copy of unit u+1 runs under the dp4a loop of unit u.
+
+// Horizontal pass on dp4a.  Item = (crop, 128-column chunk, first strip, strips): the CTA keeps the chunk's limb words
+// in registers (thread = output column x row quad) and streams 8-row strips of the source through shared memory.
 template <int NW>
-__global__ void __launch_bounds__(256) k1_hpass_fast(const K1Crop* __restrict__ crops, const int32_t* __restrict__ ids,
-                                                     const int32_t* __restrict__ blk0, int n_cls,
-                                                     const int32_t* __restrict__ coef, uint8_t* __restrict__ ws,
-                                                     int seg_words_max) {
-  extern __shared__ uint32_t planes[];            // [8 rows][3 planes][seg_words_max]
-  const int slot = find_slot(blk0, n_cls, blockIdx.x);
-  const K1Crop c = crops[ids[slot]];
-  const int local = blockIdx.x - blk0[slot];
-  const int chunks = (c.ow + kHCols - 1) / kHCols;
-  const int strip = local / chunks, chunk = local % chunks;
-  const int xx0 = chunk * kHCols, xx1 = min(c.ow, xx0 + kHCols);
-  const int32_t* __restrict__ lt = coef + c.off_lh;
-  constexpr int kStride = 1 + 3 * NW;
-  const int w_first = lt[(int64_t)xx0 * kStride];                       // window starts are monotone in xx
-  const int seg_words = min(seg_words_max, lt[(int64_t)(xx1 - 1) * kStride] + NW - w_first);
-  const int r0 = strip * kHRows;                                         // first tmp row of the strip
-
-  // ---- stage A: raw bytes of the 8 row segments -> shared memory with 16-byte cp.async (warp w = row w);
-  //      bytes outside the image (box beyond the border) are zeros (Image.crop semantics)
-  uint8_t* raw = reinterpret_cast<uint8_t*>(planes + kHRows * 3 * seg_words_max);    // [8][raw_pitch]
+__global__ void __launch_bounds__(256) k1_hpass_fast(const K1Crop* __restrict__ crops, const int4* __restrict__ items,
+                                                     int n_items, const int32_t* __restrict__ coef,
+                                                     uint8_t* __restrict__ ws, int seg_words_max) {
+  extern __shared__ uint32_t planes[];            // [8 rows][3 planes][seg_words_max], then raw[2][8][raw_pitch]
   const int raw_pitch = (seg_words_max * 12 + 32 + 15) & ~15;
+  uint8_t* raw = reinterpret_cast<uint8_t*>(planes + kHRows * 3 * seg_words_max);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int y_img = c.y0 + c.ybox0 + r0 + warp;
-  const bool row_ok = y_img >= 0 && y_img < c.src_h;
-  const int64_t b0 = 3 * (int64_t)(c.x0 + w_first * 4);                  // first byte of the segment in the row (may be < 0)
-  const uint8_t* rowp = c.src + (int64_t)(row_ok ? y_img : 0) * c.pitch;
-  const int delta = (int)((reinterpret_cast<uintptr_t>(rowp) + (uintptr_t)(b0 & 15) + 16) & 15);   // (rowp + b0) mod 16
-  const int64_t g0 = b0 - delta;                                         // row byte offset of raw[0]; rowp + g0 is 16-aligned
-  const int n_chunks = (delta + seg_words * 12 + 15) >> 4;
-  const int64_t row_bytes = 3 * (int64_t)c.src_w;
-  uint8_t* rraw = raw + warp * raw_pitch;
-  for (int ck = lane; ck < n_chunks; ck += 32) {
-    const int64_t o = g0 + 16 * (int64_t)ck;
-    uint8_t* dst = rraw + 16 * ck;
-    if (row_ok && o >= 0 && o + 16 <= row_bytes) {
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(rowp + o) : "memory");
-    } else {
-      uint32_t wv[4] = {0u, 0u, 0u, 0u};
-      if (row_ok && o + 16 > 0 && o < row_bytes) {
-#pragma unroll
-        for (int k = 0; k < 16; ++k)
-          if (o + k >= 0 && o + k < row_bytes) wv[k >> 2] |= (uint32_t)__ldg(rowp + o + k) << (8 * (k & 3));
-      }
-      *reinterpret_cast<uint4*>(dst) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
-    }
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncwarp();
-  // ---- stage B: de-interleave this warp's row, 4 pixels (12 bytes) per lane step: RGBRGBRGBRGB -> R4 | G4 | B4
-  {
-    const uint32_t sh = (uint32_t)(delta & 3) * 8;
-    const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(rraw + (delta & ~3));
-    uint32_t* p = planes + (warp * 3) * seg_words_max;
-    for (int wq = lane; wq < seg_words; wq += 32) {
-      const uint32_t w0 = wsrc[3 * wq], w1 = wsrc[3 * wq + 1], w2 = wsrc[3 * wq + 2], w3 = wsrc[3 * wq + 3];
-      const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh), v2 = __funnelshift_r(w2, w3, sh);
-      p[wq] = __byte_perm(__byte_perm(v0, v1, 0x0630), v2, 0x5210);
-      p[seg_words_max + wq] = __byte_perm(__byte_perm(v0, v1, 0x0741), v2, 0x6210);
-      p[2 * seg_words_max + wq] = __byte_perm(__byte_perm(v0, v1, 0x0052), v2, 0x7410);
-    }
-  }
-  __syncthreads();
+  constexpr int kStride = 1 + 3 * NW;
 
-  // ---- compute: thread = (output column, row quad)
-  const int xx = xx0 + (threadIdx.x & (kHCols - 1));
-  const int quad = threadIdx.x >> 7;                                     // 0, 1
-  const int nq = (c.nrows + 3) >> 2;
-  const int q = (r0 >> 2) + quad;
-  if (xx >= xx1 || q >= nq) return;
-  const int32_t* __restrict__ e = lt + (int64_t)xx * kStride;
-  const int w0 = __ldg(e) - w_first;
-  uint32_t l0[NW], l1[NW], l2[NW];
+  for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+    const int4 item = __ldg(items + it);
+    const K1Crop& c = crops[item.x];
+    const uint8_t* __restrict__ src = c.src;
+    const int64_t pitch = c.pitch;
+    const int src_h = c.src_h, ow = c.ow, nq = (c.nrows + 3) >> 2;
+    const int y_base = c.y0 + c.ybox0;
+    const int64_t row_bytes = 3 * (int64_t)c.src_w;
+    const int32_t* __restrict__ lt = coef + c.off_lh;
+    const int xx0 = item.y * kHCols, xx1 = min(ow, xx0 + kHCols);
+    const int w_first = __ldg(lt + (int64_t)xx0 * kStride);               // window starts are monotone in xx
+    const int seg_words = min(seg_words_max, __ldg(lt + (int64_t)(xx1 - 1) * kStride) + NW - w_first);
+    const int64_t b0 = 3 * (int64_t)(c.x0 + w_first * 4);                 // first byte of the segment in a row (may be < 0)
+    // this thread's output column: tap window start and limb words stay in registers for the whole item
+    const int xx = xx0 + (threadIdx.x & (kHCols - 1));
+    const int quad = threadIdx.x >> 7;                                    // 0, 1
+    const bool col_ok = xx < xx1;
+    int w0 = 0;
+    uint32_t l0[NW], l1[NW], l2[NW];
+    if (col_ok) {
+      const int32_t* __restrict__ e = lt + (int64_t)xx * kStride;
+      w0 = __ldg(e) - w_first;
 #pragma unroll
-  for (int k = 0; k < NW; ++k) { l0[k] = __ldg(e + 1 + k); l1[k] = __ldg(e + 1 + NW + k); l2[k] = __ldg(e + 1 + 2 * NW + k); }
-  uint32_t* __restrict__ tmp4 = reinterpret_cast<uint32_t*>(ws + c.tmp_off) + ((int64_t)q * c.ow + xx) * 3;
-  const uint32_t* __restrict__ prow = planes + quad * 12 * seg_words_max + w0;
+      for (int k = 0; k < NW; ++k) { l0[k] = __ldg(e + 1 + k); l1[k] = __ldg(e + 1 + NW + k); l2[k] = __ldg(e + 1 + 2 * NW + k); }
+    } else {
 #pragma unroll
-  for (int ch = 0; ch < 3; ++ch) {
-    int val[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const uint32_t* __restrict__ p = prow + (r * 3 + ch) * seg_words_max;
-      int a0 = 0, a1 = 0, a2 = 0;
-#pragma unroll
-      for (int k = 0; k < NW; ++k) {
-        const uint32_t v = p[k];
-        a0 = dp4a_uu(v, l0[k], a0);
-        a1 = dp4a_uu(v, l1[k], a1);
-        a2 = dp4a_us(v, l2[k], a2);
-      }
-      val[r] = finish_raw(a0, a1, a2);
+      for (int k = 0; k < NW; ++k) { l0[k] = 0; l1[k] = 0; l2[k] = 0; }
     }
-    tmp4[ch] = pack4_sat(val[0], val[1], val[2], val[3]);      // rows 4q..4q+3 of (xx, ch)
+    uint32_t* __restrict__ tmp_base = reinterpret_cast<uint32_t*>(ws + c.tmp_off);
+
+    // stage A of strip s: raw bytes of its 8 row segments -> raw[buf] with 16-byte cp.async (warp w = row w); bytes
+    // outside the image (box beyond the border) are zeros (Image.crop semantics).  Returns (rowp + b0) mod 16.
+    auto issue = [&](const int strip, const int buf) -> int {
+      const int y_img = y_base + strip * kHRows + warp;
+      const bool row_ok = y_img >= 0 && y_img < src_h;
+      const uint8_t* rowp = src + (int64_t)(row_ok ? y_img : 0) * pitch;
+      const int delta = (int)((reinterpret_cast<uintptr_t>(rowp) + (uintptr_t)(b0 & 15) + 16) & 15);
+      const int64_t g0 = b0 - delta;                                      // row byte offset of raw[0]; rowp + g0 is 16-aligned
+      const int n_chunks = (delta + seg_words * 12 + 15) >> 4;
+      uint8_t* rraw = raw + (buf * kHRows + warp) * raw_pitch;
+      for (int ck = lane; ck < n_chunks; ck += 32) {
+        const int64_t o = g0 + 16 * (int64_t)ck;
+        uint8_t* dst = rraw + 16 * ck;
+        if (row_ok && o >= 0 && o + 16 <= row_bytes) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(rowp + o) : "memory");
+        } else {
+          uint32_t wv[4] = {0u, 0u, 0u, 0u};
+          if (row_ok && o + 16 > 0 && o < row_bytes) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+              if (o + k >= 0 && o + k < row_bytes) wv[k >> 2] |= (uint32_t)__ldg(rowp + o + k) << (8 * (k & 3));
+          }
+          *reinterpret_cast<uint4*>(dst) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      return delta;
+    };
+
+    int delta_cur = issue(item.z, 0);
+    for (int s = 0; s < item.w; ++s) {
+      const int strip = item.z + s;
+      int delta_next = 0;
+      if (s + 1 < item.w) {
+        delta_next = issue(strip + 1, (s + 1) & 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      __syncthreads();              // every warp is done with the planes of the previous strip; this strip's raw rows landed
+      // ---- stage B: de-interleave this warp's row, 4 pixels (12 bytes) per lane step: RGBRGBRGBRGB -> R4 | G4 | B4
+      {
+        const uint8_t* rraw = raw + ((s & 1) * kHRows + warp) * raw_pitch;
+        const uint32_t sh = (uint32_t)(delta_cur & 3) * 8;
+        const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(rraw + (delta_cur & ~3));
+        uint32_t* p = planes + (warp * 3) * seg_words_max;
+        for (int wq = lane; wq < seg_words; wq += 32) {
+          const uint32_t x0 = wsrc[3 * wq], x1 = wsrc[3 * wq + 1], x2 = wsrc[3 * wq + 2], x3 = wsrc[3 * wq + 3];
+          const uint32_t v0 = __funnelshift_r(x0, x1, sh), v1 = __funnelshift_r(x1, x2, sh), v2 = __funnelshift_r(x2, x3, sh);
+          p[wq] = __byte_perm(__byte_perm(v0, v1, 0x0630), v2, 0x5210);
+          p[seg_words_max + wq] = __byte_perm(__byte_perm(v0, v1, 0x0741), v2, 0x6210);
+          p[2 * seg_words_max + wq] = __byte_perm(__byte_perm(v0, v1, 0x0052), v2, 0x7410);
+        }
+      }
+      delta_cur = delta_next;
+      __syncthreads();
+      // ---- compute: thread = (output column, row quad)
+      const int q = strip * 2 + quad;
+      if (col_ok && q < nq) {
+        uint32_t* __restrict__ tmp4 = tmp_base + ((int64_t)q * ow + xx) * 3;
+        const uint32_t* __restrict__ prow = planes + quad * 12 * seg_words_max + w0;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          int val[4];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const uint32_t* __restrict__ p = prow + (r * 3 + ch) * seg_words_max;
+            int a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll
+            for (int k = 0; k < NW; ++k) {
+              const uint32_t v = p[k];
+              a0 = dp4a_uu(v, l0[k], a0);
+              a1 = dp4a_uu(v, l1[k], a1);
+              a2 = dp4a_us(v, l2[k], a2);
+            }
+            val[r] = finish_raw(a0, a1, a2);
+          }
+          tmp4[ch] = pack4_sat(val[0], val[1], val[2], val[3]);      // rows 4q..4q+3 of (xx, ch)
+        }
+      }
+    }
+    __syncthreads();                // the next item's first copy may land in raw[0] / its planes pass follows a barrier
   }
 }
 
-// Vertical pass on dp4a + LUT + patchify.  Block = one merge-group row x two merge groups (28 rows x 56 pixels).
-// The row quads of the intermediate that the 28 output rows touch are first copied to shared memory with 16-byte
-// cp.async (coalesced, every word fetched once), so the tap loop runs on shared-memory loads instead of L2 latency.
+// Vertical pass on dp4a + LUT + patchify.  Item = (crop, merge-group row, first pair, pairs): the 28 output rows' limb
+// tables are parked in shared memory once per item; a unit is two merge groups (28 rows x 56 pixels) whose row quads of
+// the intermediate arrive by 16-byte cp.async (double-buffered), the CTA assembles the two groups' 1176-element patch
+// rows in shared memory and streams them out with 16-byte stores, straight at their window-order position.
 template <int NW, typename OutT>
-__global__ void __launch_bounds__(256) k1_vpass_fast(const K1Crop* __restrict__ crops, const int32_t* __restrict__ ids,
-                                                     const int32_t* __restrict__ blk0, int n_cls,
-                                                     const int32_t* __restrict__ coef, const uint8_t* __restrict__ ws,
-                                                     const float* __restrict__ lut, OutT* __restrict__ out,
-                                                     int row_order, int wsz, int tile_quads_max) {
+__global__ void __launch_bounds__(256) k1_vpass_fast(const K1Crop* __restrict__ crops, const int4* __restrict__ items,
+                                                     int n_items, const int32_t* __restrict__ coef,
+                                                     const uint8_t* __restrict__ ws, const float* __restrict__ lut,
+                                                     OutT* __restrict__ out, int row_order, int wsz, int tile_quads_max) {
   extern __shared__ __align__(16) uint8_t vsm[];
-  uint32_t* tile = reinterpret_cast<uint32_t*>(vsm);                                   // [tile_quads_max][168]
-  OutT* stage = reinterpret_cast<OutT*>(vsm + (size_t)tile_quads_max * 168 * 4);       // [2][4][1176]
-  float* s_lut = reinterpret_cast<float*>(stage + 2 * 4 * kPatchElems);                // [768]
-  const int slot = find_slot(blk0, n_cls, blockIdx.x);
-  const K1Crop c = crops[ids[slot]];
-  const int local = blockIdx.x - blk0[slot];
-  const int pairs = (c.lw + 1) >> 1;
-  const int my = local / pairs, mx0 = (local % pairs) * 2;
-  const int ngroups = min(2, c.lw - mx0);
-  const int ncols = ngroups * 84;                                        // (pixel, channel) columns of this block
   constexpr int kStride = 1 + 3 * NW;
-  const int32_t* __restrict__ lt = coef + c.off_lv;
-  const int q_origin = c.ybox0 >> 2;                                     // tmp quads are counted from ybox0 (multiple of 4)
-  const int q_lo = lt[(int64_t)(my * 28) * kStride] - q_origin;          // window starts are monotone in yy
-  const int nq = min(tile_quads_max, lt[(int64_t)(my * 28 + 27) * kStride] + NW - q_origin - q_lo);
-  const int qpitch = c.ow * 3;                                           // words per row quad
-  {
-    const uint32_t* __restrict__ g = reinterpret_cast<const uint32_t*>(ws + c.tmp_off) + (int64_t)q_lo * qpitch + mx0 * 84;
-    const int chunks = ncols >> 2;                                       // 16-byte chunks per quad row (21 or 42)
-    for (int i = threadIdx.x; i < nq * chunks; i += blockDim.x) {
-      const int r = i / chunks, ck = i - r * chunks;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(tile + r * 168 + ck * 4)),
-                   "l"(g + (int64_t)r * qpitch + ck * 4) : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  }
+  uint32_t* tile = reinterpret_cast<uint32_t*>(vsm);                                   // [2][tile_quads_max][168]
+  OutT* stage = reinterpret_cast<OutT*>(vsm + (size_t)2 * tile_quads_max * 168 * 4);   // [2][4][1176]
+  float* s_lut = reinterpret_cast<float*>(stage + 2 * 4 * kPatchElems);                // [768]
+  int32_t* s_coef = reinterpret_cast<int32_t*>(s_lut + 768);                           // [28][kStride]
   for (int i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i] = lut[i];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // per-lane column decomposition, hoisted out of the row loop: stage offset and LUT base of columns lane + 32 i
+  // per-lane column decomposition, hoisted out of every loop: stage offset and LUT base of columns lane + 32 i
   int eoff[6], lbase[6];
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
@@ -337,42 +349,83 @@ __global__ void __launch_bounds__(256) k1_vpass_fast(const K1Crop* __restrict__ 
     eoff[i] = (grp * 4 + xg / 14) * kPatchElems + ch * 392 + (xg % 14);
     lbase[i] = ch * 256;
   }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
-  for (int yl = warp; yl < 28; yl += 8) {
-    const int yy = my * 28 + yl;
-    const int32_t* __restrict__ e = lt + (int64_t)yy * kStride;
-    const int q0 = __ldg(e) - q_origin - q_lo;
-    uint32_t l0[NW], l1[NW], l2[NW];
+
+  for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+    const int4 item = __ldg(items + it);
+    const K1Crop& c = crops[item.x];
+    const int my = item.y, lh = c.lh, lw = c.lw;
+    const int qpitch = c.ow * 3;                                         // words per row quad
+    const int q_origin = c.ybox0 >> 2;                                   // tmp quads are counted from ybox0 (multiple of 4)
+    const int64_t out_row0 = c.out_row0;
+    const uint32_t* __restrict__ tmp = reinterpret_cast<const uint32_t*>(ws + c.tmp_off);
+    const int32_t* __restrict__ lt = coef + c.off_lv + (int64_t)(my * 28) * kStride;
+    __syncthreads();                // previous item: every warp is past its tap loop (s_coef, tile) and its stores (stage)
+    for (int i = threadIdx.x; i < 28 * kStride; i += blockDim.x) s_coef[i] = __ldg(lt + i);
+    __syncthreads();
+    const int q_lo = s_coef[0] - q_origin;                               // window starts are monotone in yy
+    const int nq = min(tile_quads_max, s_coef[27 * kStride] + NW - q_origin - q_lo);
+
+    auto issue = [&](const int pair, const int buf) {
+      const int mx0 = pair * 2;
+      const int chunks = (min(2, lw - mx0) * 84) >> 2;                   // 16-byte chunks per quad row (21 or 42)
+      const uint32_t* __restrict__ g = tmp + (int64_t)q_lo * qpitch + mx0 * 84;
+      uint32_t* t = tile + buf * tile_quads_max * 168;
+      for (int i = threadIdx.x; i < nq * chunks; i += blockDim.x) {
+        const int r = i / chunks, ck = i - r * chunks;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(t + r * 168 + ck * 4)),
+                     "l"(g + (int64_t)r * qpitch + ck * 4) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    issue(item.z, 0);
+    for (int u = 0; u < item.w; ++u) {
+      const int mx0 = (item.z + u) * 2;
+      const int ngroups = min(2, lw - mx0);
+      const int ncols = ngroups * 84;                                    // (pixel, channel) columns of this unit
+      if (u + 1 < item.w) {
+        issue(item.z + u + 1, (u + 1) & 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      __syncthreads();              // this unit's tile landed; the previous unit's patch rows have left `stage`
+      const uint32_t* __restrict__ tl = tile + (u & 1) * tile_quads_max * 168;
+      for (int yl = warp; yl < 28; yl += 8) {
+        const int32_t* e = s_coef + yl * kStride;
+        const int q0 = e[0] - q_origin - q_lo;
+        uint32_t l0[NW], l1[NW], l2[NW];
 #pragma unroll
-    for (int k = 0; k < NW; ++k) { l0[k] = __ldg(e + 1 + k); l1[k] = __ldg(e + 1 + NW + k); l2[k] = __ldg(e + 1 + 2 * NW + k); }
-    const uint32_t* __restrict__ base = tile + q0 * 168 + lane;
-    const int rowoff = (yl / 14) * 2 * kPatchElems + (yl % 14) * 14;
+        for (int k = 0; k < NW; ++k) { l0[k] = e[1 + k]; l1[k] = e[1 + NW + k]; l2[k] = e[1 + 2 * NW + k]; }
+        const uint32_t* __restrict__ base = tl + q0 * 168 + lane;
+        const int rowoff = (yl / 14) * 2 * kPatchElems + (yl % 14) * 14;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      if (lane + 32 * i < ncols) {
-        int a0 = 0, a1 = 0, a2 = 0;
+        for (int i = 0; i < 6; ++i) {
+          if (lane + 32 * i < ncols) {
+            int a0 = 0, a1 = 0, a2 = 0;
 #pragma unroll
-        for (int k = 0; k < NW; ++k) {
-          const uint32_t v = base[k * 168 + 32 * i];
-          a0 = dp4a_uu(v, l0[k], a0);
-          a1 = dp4a_uu(v, l1[k], a1);
-          a2 = dp4a_us(v, l2[k], a2);
+            for (int k = 0; k < NW; ++k) {
+              const uint32_t v = base[k * 168 + 32 * i];
+              a0 = dp4a_uu(v, l0[k], a0);
+              a1 = dp4a_uu(v, l1[k], a1);
+              a2 = dp4a_us(v, l2[k], a2);
+            }
+            const OutT o = to_out<OutT>(s_lut[lbase[i] + finish8(a0, a1, a2)]);
+            stage[eoff[i] + rowoff] = o;
+            stage[eoff[i] + rowoff + 196] = o;
+          }
         }
-        const OutT o = to_out<OutT>(s_lut[lbase[i] + finish8(a0, a1, a2)]);
-        stage[eoff[i] + rowoff] = o;
-        stage[eoff[i] + rowoff + 196] = o;
+      }
+      __syncthreads();
+      constexpr int kVec = 4 * kPatchElems * (int)sizeof(OutT) / 16;
+      for (int gi = 0; gi < ngroups; ++gi) {
+        const int mx = mx0 + gi;
+        const int pos = row_order == ZV_ORDER_WINDOW ? window_pos(my, mx, lh, lw, wsz) : my * lw + mx;
+        uint4* dst = reinterpret_cast<uint4*>(out + (out_row0 + 4 * (int64_t)pos) * kPatchElems);
+        const uint4* srcv = reinterpret_cast<const uint4*>(stage + gi * 4 * kPatchElems);
+        for (int i = threadIdx.x; i < kVec; i += blockDim.x) dst[i] = srcv[i];
       }
     }
-  }
-  __syncthreads();
-  constexpr int kVec = 4 * kPatchElems * (int)sizeof(OutT) / 16;
-  for (int gi = 0; gi < ngroups; ++gi) {
-    const int mx = mx0 + gi;
-    const int pos = row_order == ZV_ORDER_WINDOW ? window_pos(my, mx, c.lh, c.lw, wsz) : my * c.lw + mx;
-    uint4* dst = reinterpret_cast<uint4*>(out + (c.out_row0 + 4 * (int64_t)pos) * kPatchElems);
-    const uint4* srcv = reinterpret_cast<const uint4*>(stage + gi * 4 * kPatchElems);
-    for (int i = threadIdx.x; i < kVec; i += blockDim.x) dst[i] = srcv[i];
   }
 }
 
@@ -392,7 +445,12 @@ struct Layout {
   std::map<std::pair<int32_t, int32_t>, AxisTables> axis;   // (in, out) -> table offsets
   std::vector<int32_t> coef;                 // concatenated int32 tables
   int64_t list_ints = 0;
+  // persistent fast kernels: strips per hpass item / pairs per vpass item (chosen from the batch's total work so that
+  // small batches still spread over the whole GPU), and the capacity of the two work lists (int4 items)
+  int32_t strips_per_item = 1, pairs_per_item = 1;
+  int64_t item_cap_h = 0, item_cap_v = 0;
 };
+constexpr int kItemsTarget = 148 * 8;        // aim for at least this many work items per launch
 
 // Workspace layout shared by zv_preprocess_workspace_bytes and zv_preprocess.
 int build_layout(int32_t n, const int32_t* crop_box, const int32_t* resized_hw, Layout* L, bool fill) {
@@ -467,44 +525,77 @@ int build_layout(int32_t n, const int32_t* crop_box, const int32_t* resized_hw, 
     const int64_t quads = (int64_t)((y_last + 3) / 4 - y_first / 4) + kMaxNW + 1;
     tmp_bytes += align_up(std::max<int64_t>((int64_t)L->nrows[i] * ow * 3, quads * ow * 3 * 4), 256);
   }
+  // work-list sizing (geometry only, so that the workspace size does not depend on the tables)
+  int64_t units_h = 0, units_v = 0;
+  for (int32_t i = 0; i < n; ++i) {
+    const int32_t oh = resized_hw[2 * i], ow = resized_hw[2 * i + 1];
+    const int64_t rows = L->nrows[i] + (L->ybox0[i] & 3);
+    units_h += ((rows + kHRows - 1) / kHRows) * ((ow + kHCols - 1) / kHCols);
+    units_v += (int64_t)(oh / 28) * ((ow / 28 + 1) / 2);
+  }
+  L->strips_per_item = (int32_t)std::min<int64_t>(16, std::max<int64_t>(1, units_h / kItemsTarget));
+  L->pairs_per_item = (int32_t)std::min<int64_t>(8, std::max<int64_t>(1, units_v / kItemsTarget));
+  for (int32_t i = 0; i < n; ++i) {
+    const int32_t oh = resized_hw[2 * i], ow = resized_hw[2 * i + 1];
+    const int64_t rows = L->nrows[i] + (L->ybox0[i] & 3);
+    const int64_t strips = (rows + kHRows - 1) / kHRows, pairs = (ow / 28 + 1) / 2;
+    L->item_cap_h += ((ow + kHCols - 1) / kHCols) * ((strips + L->strips_per_item - 1) / L->strips_per_item);
+    L->item_cap_v += (int64_t)(oh / 28) * ((pairs + L->pairs_per_item - 1) / L->pairs_per_item);
+  }
+  if (L->item_cap_h > INT32_MAX / 8 || L->item_cap_v > INT32_MAX / 8) return zv::fail(ZV_EINVAL, "zv_preprocess: batch too large for one launch");
   int64_t off = 0;
   L->off_desc = off; off = align_up(off + (int64_t)n * sizeof(K1Crop), 256);
   L->off_lut = off; off = align_up(off + 768 * sizeof(float), 256);
   L->off_coef = off; off = align_up(off + coef_ints * (int64_t)sizeof(int32_t), 256);
-  L->list_ints = 4 * ((int64_t)n + 16);      // per pass: crop ids + block prefix of every kernel class
+  // work lists of the fast kernels (int4 items) first, then, for the per-tap kernels, crop ids + block prefix per pass
+  L->list_ints = 4 * (L->item_cap_h + L->item_cap_v) + 4 * ((int64_t)n + 16);
   L->off_lists = off; off = align_up(off + L->list_ints * (int64_t)sizeof(int32_t), 256);
   L->off_tmp = off; off += tmp_bytes;
   L->bytes = off;
   return ZV_OK;
 }
 
+// grid of a persistent kernel: every CTA slot of the GPU, or one CTA per item when there are fewer items
+template <typename K>
+int persistent_grid(K kernel, int smem, int64_t n_items) {
+  int dev = 0, sms = 148, per_sm = 1;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  return (int)std::min<int64_t>(n_items, (int64_t)sms * per_sm);
+}
 template <int NW>
-void launch_hfast(unsigned blocks, int smem, cudaStream_t s, const K1Crop* d, const int32_t* ids, const int32_t* blk0,
-                  int ncls, const int32_t* coef, uint8_t* ws, int seg_words) {
+void launch_hfast(int n_items, cudaStream_t s, const K1Crop* d, const int4* items, const int32_t* coef, uint8_t* ws, int seg_words) {
+  const int smem = kHRows * 3 * seg_words * 4 + 2 * kHRows * ((seg_words * 12 + 32 + 15) & ~15);
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(k1_hpass_fast<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
-  k1_hpass_fast<NW><<<blocks, 256, smem, s>>>(d, ids, blk0, ncls, coef, ws, seg_words);
+  k1_hpass_fast<NW><<<persistent_grid(k1_hpass_fast<NW>, smem, n_items), 256, smem, s>>>(d, items, n_items, coef, ws, seg_words);
+}
+inline int vfast_smem(int nw, int tile_quads, int out_bytes) {
+  return 2 * tile_quads * 168 * 4 + 2 * 4 * kPatchElems * out_bytes + 768 * 4 + 28 * (1 + 3 * nw) * 4;
 }
 template <int NW, typename OutT>
-void launch_vfast(unsigned blocks, cudaStream_t s, const K1Crop* d, const int32_t* ids, const int32_t* blk0, int ncls,
-                  const int32_t* coef, const uint8_t* ws, const float* lut, OutT* out, int row_order, int wsz, int tile_quads) {
-  const int smem = tile_quads * 168 * 4 + 2 * 4 * kPatchElems * (int)sizeof(OutT) + 768 * 4;
+void launch_vfast(int n_items, cudaStream_t s, const K1Crop* d, const int4* items, const int32_t* coef, const uint8_t* ws,
+                  const float* lut, OutT* out, int row_order, int wsz, int tile_quads) {
+  const int smem = vfast_smem(NW, tile_quads, (int)sizeof(OutT));
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(k1_vpass_fast<NW, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
-  k1_vpass_fast<NW, OutT><<<blocks, 256, smem, s>>>(d, ids, blk0, ncls, coef, ws, lut, out, row_order, wsz, tile_quads);
+  k1_vpass_fast<NW, OutT><<<persistent_grid(k1_vpass_fast<NW, OutT>, smem, n_items), 256, smem, s>>>(
+      d, items, n_items, coef, ws, lut, out, row_order, wsz, tile_quads);
 }
 template <typename OutT>
-void launch_vpass(int nw, unsigned blocks, cudaStream_t s, const K1Crop* d, const int32_t* ids, const int32_t* blk0, int ncls,
+void launch_vpass(int nw, int count, cudaStream_t s, const K1Crop* d, const int32_t* list, const int32_t* blk0, int ncls,
                   const int32_t* coef, const uint8_t* ws, const float* lut, void* out_, int row_order, int wsz, int tile_quads) {
   OutT* out = static_cast<OutT*>(out_);
+  const int4* items = reinterpret_cast<const int4*>(list);
   switch (nw) {
-    case 0: k1_vpass<OutT><<<blocks, 256, 0, s>>>(d, ids, blk0, ncls, coef, ws, lut, out, row_order, wsz); break;
-    case 2: launch_vfast<2, OutT>(blocks, s, d, ids, blk0, ncls, coef, ws, lut, out, row_order, wsz, tile_quads); break;
-    case 3: launch_vfast<3, OutT>(blocks, s, d, ids, blk0, ncls, coef, ws, lut, out, row_order, wsz, tile_quads); break;
-    case 4: launch_vfast<4, OutT>(blocks, s, d, ids, blk0, ncls, coef, ws, lut, out, row_order, wsz, tile_quads); break;
-    case 5: launch_vfast<5, OutT>(blocks, s, d, ids, blk0, ncls, coef, ws, lut, out, row_order, wsz, tile_quads); break;
-    case 7: launch_vfast<7, OutT>(blocks, s, d, ids, blk0, ncls, coef, ws, lut, out, row_order, wsz, tile_quads); break;
-    default: launch_vfast<10, OutT>(blocks, s, d, ids, blk0, ncls, coef, ws, lut, out, row_order, wsz, tile_quads); break;
+    case 0: k1_vpass<OutT><<<(unsigned)count, 256, 0, s>>>(d, list, blk0, ncls, coef, ws, lut, out, row_order, wsz); break;
+    case 2: launch_vfast<2, OutT>(count, s, d, items, coef, ws, lut, out, row_order, wsz, tile_quads); break;
+    case 3: launch_vfast<3, OutT>(count, s, d, items, coef, ws, lut, out, row_order, wsz, tile_quads); break;
+    case 4: launch_vfast<4, OutT>(count, s, d, items, coef, ws, lut, out, row_order, wsz, tile_quads); break;
+    case 5: launch_vfast<5, OutT>(count, s, d, items, coef, ws, lut, out, row_order, wsz, tile_quads); break;
+    case 7: launch_vfast<7, OutT>(count, s, d, items, coef, ws, lut, out, row_order, wsz, tile_quads); break;
+    default: launch_vfast<10, OutT>(count, s, d, items, coef, ws, lut, out, row_order, wsz, tile_quads); break;
   }
 }
 
@@ -559,8 +650,9 @@ int zv_preprocess(const zv_cfg* cfg, int32_t n, const uint8_t* const* src_dev, c
     c.off_bh = h.off_bounds; c.off_kh = h.off_kk; c.off_bv = v.off_bounds; c.off_kv = v.off_kk;
     c.off_lh = h.off_limbs; c.off_lv = v.off_limbs;
     const bool aligned = (reinterpret_cast<uintptr_t>(c.src) & 3) == 0 && (c.pitch & 3) == 0;
-    c.fast = (!generic_only && aligned && h.nw > 0 && v.nw > 0 && kHRows * (h.seg_words * 24 + 48) <= 200 * 1024 &&
-              v.tile_quads * 168 * 4 + 2 * 4 * kPatchElems * 4 + 768 * 4 <= 200 * 1024) ? 1 : 0;
+    c.fast = (!generic_only && aligned && h.nw > 0 && v.nw > 0 &&
+              kHRows * 3 * h.seg_words * 4 + 2 * kHRows * ((h.seg_words * 12 + 32 + 15) & ~15) <= 200 * 1024 &&
+              vfast_smem(v.nw, v.tile_quads, 4) <= 200 * 1024) ? 1 : 0;
     c.nwh = c.fast ? h.nw : 0; c.nwv = c.fast ? v.nw : 0;
     seg_h[i] = h.seg_words;
     tq_v[i] = v.tile_quads;
@@ -577,43 +669,67 @@ int zv_preprocess(const zv_cfg* cfg, int32_t n, const uint8_t* const* src_dev, c
   zv::normalize_lut(cfg, reinterpret_cast<float*>(host.data() + L.off_lut));
   std::memcpy(host.data() + L.off_coef, L.coef.data(), L.coef.size() * sizeof(int32_t));
 
-  // launch lists: crops grouped by kernel class, each class with its own block prefix
-  struct Launch { int nw; int32_t ids_off, blk_off, count; int64_t blocks; int seg_words; int tile_quads; };
+  // launch lists, crops grouped by kernel class.  Fast classes: a work list of int4 items - hpass (crop, 128-column
+  // chunk, first strip, strips), ordered strip-major so that the CTAs running together read neighbouring row segments;
+  // vpass (crop, merge-group row, first pair, pairs).  Per-tap class (nw 0): crop ids + a block prefix.
+  struct Launch { int nw; int64_t list_off, blk_off; int32_t ncls; int64_t count; int seg_words; int tile_quads; };
   std::vector<Launch> hl, vl;
   int32_t* lists = reinterpret_cast<int32_t*>(host.data() + L.off_lists);
-  int64_t cur = 0;
+  int64_t cur = 0;                                    // in ints; items are appended first, so they stay 16-byte aligned
   auto build = [&](bool vpass, std::vector<Launch>* outl) -> int {
-    for (int nw : {0, 2, 3, 4, 5, 7, 10}) {
-      std::vector<int32_t> ids;
-      for (int32_t i = 0; i < n; ++i) if ((vpass ? d[i].nwv : d[i].nwh) == nw) ids.push_back(i);
-      if (ids.empty()) continue;
+    for (int nw : {2, 3, 4, 5, 7, 10}) {
       Launch l{};
-      l.nw = nw; l.count = (int32_t)ids.size();
-      if (cur + 2 * (int64_t)ids.size() > L.list_ints) return zv::fail(ZV_EINVAL, "zv_preprocess: launch lists overflow");
-      l.ids_off = (int32_t)cur;
-      for (int32_t id : ids) lists[cur++] = id;
-      l.blk_off = (int32_t)cur;
-      int64_t blocks = 0;
-      for (int32_t id : ids) {
-        const K1Crop& c = d[id];
-        lists[cur++] = (int32_t)blocks;
-        if (vpass) { blocks += nw == 0 ? (int64_t)c.lh * c.lw : (int64_t)c.lh * ((c.lw + 1) / 2); l.tile_quads = std::max(l.tile_quads, tq_v[id]); }
-        else if (nw == 0) blocks += ((int64_t)c.nrows * c.ow + 255) / 256;
-        else {
-          blocks += (((int64_t)c.nrows + kHRows - 1) / kHRows) * ((c.ow + kHCols - 1) / kHCols);
-          l.seg_words = std::max(l.seg_words, seg_h[id]);
+      l.nw = nw; l.list_off = cur;
+      for (int32_t i = 0; i < n; ++i) {
+        const K1Crop& c = d[i];
+        if ((vpass ? c.nwv : c.nwh) != nw) continue;
+        if (vpass) {
+          const int pairs = (c.lw + 1) / 2;
+          for (int my = 0; my < c.lh; ++my)
+            for (int p0 = 0; p0 < pairs; p0 += L.pairs_per_item) {
+              lists[cur++] = i; lists[cur++] = my; lists[cur++] = p0; lists[cur++] = std::min(L.pairs_per_item, pairs - p0);
+            }
+          l.tile_quads = std::max(l.tile_quads, tq_v[i]);
+        } else {
+          const int strips = (c.nrows + kHRows - 1) / kHRows, chunks = (c.ow + kHCols - 1) / kHCols;
+          for (int s0 = 0; s0 < strips; s0 += L.strips_per_item)
+            for (int ck = 0; ck < chunks; ++ck) {
+              lists[cur++] = i; lists[cur++] = ck; lists[cur++] = s0; lists[cur++] = std::min(L.strips_per_item, strips - s0);
+            }
+          l.seg_words = std::max(l.seg_words, seg_h[i]);
         }
-        if (blocks > INT32_MAX) return zv::fail(ZV_EINVAL, "zv_preprocess: batch too large for one launch");
       }
-      l.blocks = blocks;
-      outl->push_back(l);
+      l.count = (cur - l.list_off) / 4;
+      if (l.count) outl->push_back(l);
     }
     return ZV_OK;
   };
+  auto build_generic = [&](bool vpass, std::vector<Launch>* outl) -> int {
+    std::vector<int32_t> ids;
+    for (int32_t i = 0; i < n; ++i) if ((vpass ? d[i].nwv : d[i].nwh) == 0) ids.push_back(i);
+    if (ids.empty()) return ZV_OK;
+    Launch l{};
+    l.nw = 0; l.ncls = (int32_t)ids.size();
+    l.list_off = cur;
+    for (int32_t id : ids) lists[cur++] = id;
+    l.blk_off = cur;
+    int64_t blocks = 0;
+    for (int32_t id : ids) {
+      const K1Crop& c = d[id];
+      lists[cur++] = (int32_t)blocks;
+      blocks += vpass ? (int64_t)c.lh * c.lw : ((int64_t)c.nrows * c.ow + 255) / 256;
+      if (blocks > INT32_MAX) return zv::fail(ZV_EINVAL, "zv_preprocess: batch too large for one launch");
+    }
+    l.count = blocks;
+    outl->push_back(l);
+    return ZV_OK;
+  };
   rc = build(false, &hl);
+  if (!rc) rc = build(true, &vl);
+  if (!rc) rc = build_generic(false, &hl);
+  if (!rc) rc = build_generic(true, &vl);
   if (rc) return rc;
-  rc = build(true, &vl);
-  if (rc) return rc;
+  if (cur > L.list_ints) return zv::fail(ZV_EINVAL, "zv_preprocess: launch lists overflow");
 
   uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
   cudaError_t e = cudaMemcpyAsync(ws, host.data(), host.size(), cudaMemcpyHostToDevice, stream);
@@ -626,18 +742,17 @@ int zv_preprocess(const zv_cfg* cfg, int32_t n, const uint8_t* const* src_dev, c
   {
     zv::KernelTimer timer(zv::KC_K1_HPASS, stream);
     for (const Launch& l : hl) {
-      const int32_t* ids = dlists + l.ids_off;
-      const int32_t* blk0 = dlists + l.blk_off;
-      const int smem = kHRows * 3 * l.seg_words * 4 + kHRows * ((l.seg_words * 12 + 32 + 15) & ~15);
-      const unsigned nb = (unsigned)l.blocks;
+      const int32_t* list = dlists + l.list_off;
+      const int4* items = reinterpret_cast<const int4*>(list);
+      const int ni = (int)l.count;
       switch (l.nw) {
-        case 0: k1_hpass<<<nb, 256, 0, stream>>>(dcrops, ids, blk0, l.count, dcoef, ws); break;
-        case 2: launch_hfast<2>(nb, smem, stream, dcrops, ids, blk0, l.count, dcoef, ws, l.seg_words); break;
-        case 3: launch_hfast<3>(nb, smem, stream, dcrops, ids, blk0, l.count, dcoef, ws, l.seg_words); break;
-        case 4: launch_hfast<4>(nb, smem, stream, dcrops, ids, blk0, l.count, dcoef, ws, l.seg_words); break;
-        case 5: launch_hfast<5>(nb, smem, stream, dcrops, ids, blk0, l.count, dcoef, ws, l.seg_words); break;
-        case 7: launch_hfast<7>(nb, smem, stream, dcrops, ids, blk0, l.count, dcoef, ws, l.seg_words); break;
-        default: launch_hfast<10>(nb, smem, stream, dcrops, ids, blk0, l.count, dcoef, ws, l.seg_words); break;
+        case 0: k1_hpass<<<(unsigned)l.count, 256, 0, stream>>>(dcrops, list, dlists + l.blk_off, l.ncls, dcoef, ws); break;
+        case 2: launch_hfast<2>(ni, stream, dcrops, items, dcoef, ws, l.seg_words); break;
+        case 3: launch_hfast<3>(ni, stream, dcrops, items, dcoef, ws, l.seg_words); break;
+        case 4: launch_hfast<4>(ni, stream, dcrops, items, dcoef, ws, l.seg_words); break;
+        case 5: launch_hfast<5>(ni, stream, dcrops, items, dcoef, ws, l.seg_words); break;
+        case 7: launch_hfast<7>(ni, stream, dcrops, items, dcoef, ws, l.seg_words); break;
+        default: launch_hfast<10>(ni, stream, dcrops, items, dcoef, ws, l.seg_words); break;
       }
       zv::count_launch();
     }
@@ -645,12 +760,12 @@ int zv_preprocess(const zv_cfg* cfg, int32_t n, const uint8_t* const* src_dev, c
   {
     zv::KernelTimer timer(zv::KC_K1_VPASS, stream);
     for (const Launch& l : vl) {
-      const int32_t* ids = dlists + l.ids_off;
+      const int32_t* list = dlists + l.list_off;
       const int32_t* blk0 = dlists + l.blk_off;
-      const unsigned nb = (unsigned)l.blocks;
-      if (out_dtype == ZV_BF16) launch_vpass<__nv_bfloat16>(l.nw, nb, stream, dcrops, ids, blk0, l.count, dcoef, ws, dlut, out_dev, row_order, wsz, l.tile_quads);
-      else if (out_dtype == ZV_F16) launch_vpass<__half>(l.nw, nb, stream, dcrops, ids, blk0, l.count, dcoef, ws, dlut, out_dev, row_order, wsz, l.tile_quads);
-      else launch_vpass<float>(l.nw, nb, stream, dcrops, ids, blk0, l.count, dcoef, ws, dlut, out_dev, row_order, wsz, l.tile_quads);
+      const int cnt = (int)l.count;
+      if (out_dtype == ZV_BF16) launch_vpass<__nv_bfloat16>(l.nw, cnt, stream, dcrops, list, blk0, l.ncls, dcoef, ws, dlut, out_dev, row_order, wsz, l.tile_quads);
+      else if (out_dtype == ZV_F16) launch_vpass<__half>(l.nw, cnt, stream, dcrops, list, blk0, l.ncls, dcoef, ws, dlut, out_dev, row_order, wsz, l.tile_quads);
+      else launch_vpass<float>(l.nw, cnt, stream, dcrops, list, blk0, l.ncls, dcoef, ws, dlut, out_dev, row_order, wsz, l.tile_quads);
       zv::count_launch();
     }
   }
