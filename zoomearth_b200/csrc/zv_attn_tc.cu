@@ -1,14 +1,23 @@
 // K4: tcgen05 flash attention for the full-attention layers (whole-image segments; HF modeling_qwen2_5_vl.py
 // :207-287 with cu_seqlens, blocks 7/15/23/31).  One CTA = one 128-row q tile of one head; K/V stream through a
-// 3-stage TMA ring in 64-row tiles.
-//   S_j = Q K_j^T   tcgen05.mma M=128 N=64, K = 80 = 4 x 16 (128B-swizzled [rows][64] block) + 16 (32B-swizzled
-//                   [rows][16] block), accumulator in TMEM (two S buffers: QK_{j+1} is issued while tile j is in softmax)
+// TMA ring in 32-row tiles.
+//   S_j = Q K_j^T   tcgen05.mma M=128 N=32, K = 80 = 4 x 16 (128B-swizzled [rows][64] block) + 16 (32B-swizzled
+//                   [rows][16] block), accumulator in TMEM (one S buffer: the softmax pulls a tile into registers as
+//                   soon as it is complete, which frees the buffer for Q K_{j+1}^T while the exponentials run)
 //   softmax         four warps, one thread per q row: tcgen05.ld of the row, online max/sum in fp32 with exp2,
-//                   P_j rounded to 16 bit and written to shared memory in the 128B-swizzled K-major layout
-//   O += P_j V_j    tcgen05.mma M=128 N=80 K=64 from P (smem) and V^T (smem, kv contiguous: V is pre-transposed per
+//                   P_j rounded to 16 bit and written to shared memory in the 64B-swizzled K-major layout
+//   O += P_j V_j    tcgen05.mma M=128 N=96 K=32 from P (smem) and V^T (smem, kv contiguous: V is pre-transposed per
 //                   head by transpose_v so that the B operand is K-major); O stays in TMEM for the whole segment and
-//                   is rescaled lazily (only when the row max grows by more than 2^8).  Two CTAs fit per SM, so one
-//                   CTA's softmax overlaps the other's MMAs.
+//                   is rescaled lazily (only when the row max grows by more than 2^8).
+// The kernel is bound by the softmax warps (one exp2 per score on a 16/clk/SM unit, plus the latency of each warp's
+// dependent chain), so the CTA is kept small - 128 TMEM columns, ~51 KB of shared memory, <= 85 registers - and FOUR
+// CTAs share an SM: four softmax warps per scheduler keep the SFU busy where two (64-row KV tiles, 256 TMEM columns)
+// left it idle half of the time.
+// K/V traffic: every q tile of a head streams the head's whole K and V, which made the kernel L2 -> SM bandwidth bound
+// (5.9 TB/s of TMA reads whatever the SM-side schedule).  CTAs therefore run as clusters of two neighbouring q tiles of
+// the same head: each CTA fetches half of every K / V^T tile and TMA-multicasts it into both CTAs' shared memory, which
+// halves the L2 reads; a stage is recycled when BOTH tensor cores are done with it (multicast tcgen05.commit).  Pairs
+// that straddle a segment boundary (or the odd last tile) fall back to private loads.
 // Warp roles (192 threads): warp 0 = TMA producer + TMEM allocator, warp 1 = MMA issuer, warps 2-5 = softmax
 // (TMEM lane quarters 2,3,0,1).  Rotary is already applied to q,k by the QKV GEMM epilogue.
 #include <cuda.h>
@@ -27,16 +36,20 @@ namespace zv {
 using namespace ptx;
 namespace {
 
-constexpr int HD = 80, BQ = 128, BKV = 64, STAGES = 3;
+constexpr int HD = 80, BQ = 128, BKV = 32, STAGES = 2, kCtasPerSm = 4;
 constexpr int kQ64 = BQ * 64 * 2, kQ16 = BQ * 16 * 2;                   // 16384, 4096
 constexpr int VROWS = 96;                                                 // V^T rows in smem: 80 head dims, a row of ones, 15 zero rows
-constexpr int kK64 = BKV * 64 * 2, kK16 = BKV * 16 * 2, kVtTma = HD * BKV * 2, kVt = VROWS * BKV * 2;   // 8192, 2048, 10240, 12288
-constexpr int kStage = kK64 + kK16 + kVt;                                // 22528
-constexpr int kP = BQ * BKV * 2;                                         // 16384
+constexpr int kRowP = BKV * 2;                                            // bytes per P / V^T row in smem (64: 64B swizzle)
+constexpr int kK64 = BKV * 64 * 2, kK16 = BKV * 16 * 2, kVtTma = HD * kRowP, kVt = VROWS * kRowP;   // 4096, 1024, 5120, 6144
+constexpr int kStage = kK64 + kK16 + kVt;                                // 11264
+constexpr int kP = BQ * kRowP;                                           // 8192
 constexpr int kOffQ16 = kQ64, kOffStage = kQ64 + kQ16, kOffP = kOffStage + STAGES * kStage, kOffBar = kOffP + kP;
 constexpr int kSmem = kOffBar + 256 + 1024;
-constexpr int kTmemCols = 256;                                           // S0 [0,64) S1 [64,128) O [128,224): 80 dims + row sum
+constexpr int kTmemCols = 128, kOCol = BKV;                              // S [0,32)  O [32,128): 80 dims + row sum + pad
 constexpr int kThreads = 192;
+constexpr uint32_t kSw128 = 2, kSw64 = 4, kSw32 = 6;                     // UMMA descriptor layout types
+static_assert(BKV == 32, "the P / V^T tiles are laid out for 64-byte rows (BKV = 32)");
+static_assert(kStage % 1024 == 0 && kOffStage % 1024 == 0 && (kK64 + kK16) % 512 == 0 && kOffP % 512 == 0, "swizzle atom alignment");
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = 0;
@@ -63,33 +76,69 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA tile load delivered to the same shared-memory offset (data and mbarrier) of every CTA in `mask`
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const void* tmap, uint64_t* bar, int32_t c0, int32_t c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+// arrive, once all prior MMAs of this thread are done, on the same barrier in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+
 struct AttnArgs {
   void* out;
   const int4* tiles;
+  int n_tiles;
   int heads, hidden, f16;
   float scale_log2;
 };
 
 template <bool F16>
-__global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qk64,
-                                                              const __grid_constant__ CUtensorMap tm_qk16,
-                                                              const __grid_constant__ CUtensorMap tm_vt, const AttnArgs a) {
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qk64,
+                                                                       const __grid_constant__ CUtensorMap tm_qk16,
+                                                                       const __grid_constant__ CUtensorMap tm_vt, const AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t* q_full = bars;             // 1
-  uint64_t* k_full = bars + 1;         // STAGES
+  uint64_t* k_full = bars + 1;         // STAGES (<= 3)
   uint64_t* v_full = bars + 4;
   uint64_t* k_empty = bars + 7;
   uint64_t* v_empty = bars + 10;
-  uint64_t* s_full = bars + 13;        // 2
-  uint64_t* s_empty = bars + 15;       // 2
-  uint64_t* p_full = bars + 17;
-  uint64_t* pv_done = bars + 18;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* s_full = bars + 13;
+  uint64_t* s_empty = bars + 14;
+  uint64_t* p_full = bars + 15;
+  uint64_t* pv_done = bars + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
+  // the pair shares K/V when both q tiles exist and belong to the same segment; otherwise each CTA loads privately
+  const uint32_t rank = cluster_ctarank();
+  const bool valid = (int)blockIdx.x < a.n_tiles;
+  if (!valid) {                                  // odd tail of the grid: only keeps the partner's cluster barriers company
+    cluster_sync_all();
+    cluster_sync_all();
+    return;
+  }
   const int4 tl = a.tiles[blockIdx.x];
   const int q0 = tl.x, q_len = tl.y, seg_b = tl.z, seg_e = tl.w;
+  bool shared_kv = false;
+  if ((int)(blockIdx.x ^ 1u) < a.n_tiles) {
+    const int4 to = a.tiles[blockIdx.x ^ 1u];
+    shared_kv = to.z == seg_b && to.w == seg_e;
+  }
   const int head = blockIdx.y;
   // K/V tiles start at the segment start rounded down to 8 rows: the V^T tile's inner TMA coordinate must be
   // 16-byte aligned.  Columns before seg_b (first tile) and from seg_e on (last tile) are masked in the softmax.
@@ -100,35 +149,39 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const __grid_const
   if (threadIdx.x == 0) {
     prefetch_tensormap(&tm_qk64); prefetch_tensormap(&tm_qk16); prefetch_tensormap(&tm_vt);
     mbar_init(q_full, 1);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(k_full + s, 1); mbar_init(v_full + s, 1); mbar_init(k_empty + s, 1); mbar_init(v_empty + s, 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(s_full + b, 1); mbar_init(s_empty + b, 4); }
+    const int users = shared_kv ? 2 : 1;          // tensor cores that must be done with a stage before it is refilled
+    for (int s = 0; s < STAGES; ++s) { mbar_init(k_full + s, 1); mbar_init(v_full + s, 1); mbar_init(k_empty + s, users); mbar_init(v_empty + s, users); }
+    mbar_init(s_full, 1); mbar_init(s_empty, 4);
     mbar_init(p_full, 4); mbar_init(pv_done, 1);
     fence_mbar_init();
   }
   if (warp == 0) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
   // rows 80..95 of every V^T stage: a row of ones (so that column 80 of O = P [V | 1] is the softmax row sum, computed
   // by the tensor core from the same rounded P that multiplies V) and zero rows; constant rows are swizzle-invariant
-  for (int i = threadIdx.x; i < STAGES * 16 * 8; i += kThreads) {
-    const int st = i / 128, r = (i % 128) / 8, c = i % 8;
+  for (int i = threadIdx.x; i < STAGES * 16 * (kRowP / 16); i += kThreads) {
+    const int per = 16 * (kRowP / 16);
+    const int st = i / per, r = (i % per) / (kRowP / 16), c = i % (kRowP / 16);
     const uint32_t one2 = F16 ? 0x3C003C00u : 0x3F803F80u;
     const uint32_t v = r == 0 ? one2 : 0u;
-    *reinterpret_cast<uint4*>(smem + kOffStage + st * kStage + kK64 + kK16 + (HD + r) * 128 + c * 16) = make_uint4(v, v, v, v);
+    *reinterpret_cast<uint4*>(smem + kOffStage + st * kStage + kK64 + kK16 + (HD + r) * kRowP + c * 16) = make_uint4(v, v, v, v);
   }
   fence_proxy_async();
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();                             // both CTAs' barriers exist before either multicasts into the other
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
     if (elect_one()) {
-      // ---- TMA producer: Q once, then the K / V^T ring
+      // ---- TMA producer: Q once, then the K / V^T ring.  Boxes are half tiles (16 K rows, 40 V^T rows): in a sharing
+      // pair CTA `rank` fetches half `rank` and multicasts it to both CTAs; a private CTA fetches both halves itself.
       const int colq = head * HD, colk = a.hidden + head * HD;
       mbar_arrive_expect_tx(q_full, kQ64 + kQ16);
-      tma_load_2d(smem, &tm_qk64, q_full, colq, q0);
-      tma_load_2d(smem + kQ64 / 2, &tm_qk64, q_full, colq, q0 + 64);
-      tma_load_2d(smem + kOffQ16, &tm_qk16, q_full, colq + 64, q0);
-      tma_load_2d(smem + kOffQ16 + kQ16 / 2, &tm_qk16, q_full, colq + 64, q0 + 64);
+#pragma unroll
+      for (int i = 0; i < BQ / 16; ++i) {
+        tma_load_2d(smem + i * (16 * 128), &tm_qk64, q_full, colq, q0 + i * 16);
+        tma_load_2d(smem + kOffQ16 + i * (16 * 32), &tm_qk16, q_full, colq + 64, q0 + i * 16);
+      }
       for (int j = 0; j < n_kv; ++j) {
         const int st = j % STAGES;
         const uint32_t ph = (j / STAGES) & 1;
@@ -136,11 +189,25 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const __grid_const
         const int row = kv_base + j * BKV;
         mbar_wait(k_empty + st, ph ^ 1);
         mbar_arrive_expect_tx(k_full + st, kK64 + kK16);
-        tma_load_2d(sk, &tm_qk64, k_full + st, colk, row);
-        tma_load_2d(sk + kK64, &tm_qk16, k_full + st, colk + 64, row);
+        if (shared_kv) {
+          tma_load_2d_mc(sk + rank * (kK64 / 2), &tm_qk64, k_full + st, colk, row + rank * 16, 3);
+          tma_load_2d_mc(sk + kK64 + rank * (kK16 / 2), &tm_qk16, k_full + st, colk + 64, row + rank * 16, 3);
+        } else {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            tma_load_2d(sk + h * (kK64 / 2), &tm_qk64, k_full + st, colk, row + h * 16);
+            tma_load_2d(sk + kK64 + h * (kK16 / 2), &tm_qk16, k_full + st, colk + 64, row + h * 16);
+          }
+        }
         mbar_wait(v_empty + st, ph ^ 1);
         mbar_arrive_expect_tx(v_full + st, kVtTma);
-        tma_load_2d(sk + kK64 + kK16, &tm_vt, v_full + st, row, head * HD);
+        if (shared_kv) {
+          tma_load_2d_mc(sk + kK64 + kK16 + rank * (kVtTma / 2), &tm_vt, v_full + st, row, head * HD + rank * (HD / 2), 3);
+        } else {
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            tma_load_2d(sk + kK64 + kK16 + h * (kVtTma / 2), &tm_vt, v_full + st, row, head * HD + h * (HD / 2));
+        }
       }
     }
   } else if (warp == 1) {
@@ -153,15 +220,14 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const __grid_const
         const int st = t % STAGES;
         const uint32_t sk = smem_u32(smem + kOffStage + st * kStage);
         mbar_wait(k_full + st, (t / STAGES) & 1);
-        mbar_wait(s_empty + (t & 1), ((t >> 1) & 1) ^ 1);
+        mbar_wait(s_empty, (t & 1) ^ 1);                     // the softmax holds S_{t-1} in registers
         tc_fence_after();
-        const uint32_t d = tmem + (t & 1) * 64;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
-          umma_bf16(d, umma_desc(sq, 1024, 2) + 2 * ks, umma_desc(sk, 1024, 2) + 2 * ks, idesc_qk, ks != 0);
-        umma_bf16(d, umma_desc(sq16, 256, 6), umma_desc(sk + kK64, 256, 6), idesc_qk, 1);
-        umma_commit(k_empty + st);
-        umma_commit(s_full + (t & 1));
+          umma_bf16(tmem, umma_desc(sq, 1024, kSw128) + 2 * ks, umma_desc(sk, 1024, kSw128) + 2 * ks, idesc_qk, ks != 0);
+        umma_bf16(tmem, umma_desc(sq16, 256, kSw32), umma_desc(sk + kK64, 256, kSw32), idesc_qk, 1);
+        if (shared_kv) umma_commit_mc(k_empty + st, 3); else umma_commit(k_empty + st);
+        umma_commit(s_full);
       };
       mbar_wait(q_full, 0);
       issue_qk(0);
@@ -173,9 +239,9 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const __grid_const
         mbar_wait(p_full, j & 1);
         tc_fence_after();
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          umma_bf16(tmem + 128, umma_desc(sp, 1024, 2) + 2 * ks, umma_desc(sv, 1024, 2) + 2 * ks, idesc_pv, (j | ks) != 0);
-        umma_commit(v_empty + st);
+        for (int ks = 0; ks < BKV / 16; ++ks)
+          umma_bf16(tmem + kOCol, umma_desc(sp, 512, kSw64) + 2 * ks, umma_desc(sv, 512, kSw64) + 2 * ks, idesc_pv, (j | ks) != 0);
+        if (shared_kv) umma_commit_mc(v_empty + st, 3); else umma_commit(v_empty + st);
         umma_commit(pv_done);
       }
     }
@@ -183,85 +249,81 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const __grid_const
     // ---- softmax warps: thread = q row.  O accumulates in TMEM across KV tiles; it is rescaled (tcgen05.ld ->
     // multiply -> tcgen05.st) only when the running row max grew by more than 2^8 since the scale in use was chosen
     // ("lazy rescale": P may then exceed 1 by at most 2^8, harmless in fp32 sums and 16-bit P), so the common tile
-    // costs one TMEM row load, 64 exp2 and one 128-byte row store per thread.
+    // costs one TMEM row load, 32 exp2 and one 64-byte row store per thread.
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const float sl2 = a.scale_log2;
     float m_used = -INFINITY;               // scale in use (raw score units); the row sum lives in O column 80
-    uint8_t* prow = smem + kOffP + row * 128;
+    // this thread's P row, K-major 64B swizzle: 16-byte chunk c of row r lives at chunk (c ^ ((r >> 1) & 3))
+    // (st.shared through the 32-bit shared address: the generic-pointer form compiles to ST.E, whose completion the
+    // proxy fence then waits on for several hundred cycles)
+    const uint32_t prow_s = smem_u32(smem + kOffP + row * kRowP);
+    const int psw = (row >> 1) & 3;
 
-    // rescale the O row (and its sum column) by `factor` - warp-collective TMEM round trip, only when some row's
-    // running max grew by more than 2^8
+    // rescale the O row (and its sum column) by `factor` - warp-collective TMEM round trip
     auto rescale_o = [&](const float factor) {
       tc_fence_after();
 #pragma unroll
       for (int c = 0; c < VROWS; c += 16) {
         uint32_t t[16];
-        tmem_ld_x16(tmem + lane_addr + 128 + c, t);
+        tmem_ld_x16(tmem + lane_addr + kOCol + c, t);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * factor);
-        tmem_st_x16(tmem + lane_addr + 128 + c, t);
+        tmem_st_x16(tmem + lane_addr + kOCol + c, t);
       }
       tmem_st_wait();
       tc_fence_before();
     };
-    // this thread's P row -> shared memory, K-major 128B swizzle: chunk c of row r lives at
-    // chunk (c ^ (r & 7))
-    // (st.shared through the 32-bit shared address: the generic-pointer form compiles to ST.E, whose completion the
-    // proxy fence below then waits on for several hundred cycles)
-    const uint32_t prow_s = smem_u32(prow);
-    auto store_p = [&](const uint32_t (&pk)[32]) {
-#pragma unroll
-      for (int c = 0; c < 8; ++c)
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow_s + ((c ^ (row & 7)) << 4)), "r"(pk[4 * c]),
-                     "r"(pk[4 * c + 1]), "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3])
-                     : "memory");
-    };
 
     // One KV tile.  MASK = the tile may hold columns outside [seg_b, seg_e) (only the first and the last tile of a
     // segment can): the column mask is compiled into that instantiation alone - the compiler if-converts it into
-    // 2 x 64 compares and selects, which the interior tiles must not carry (it doubled the kernel's instruction count).
+    // compares and selects on every column, which the interior tiles must not carry.
     auto softmax_tile = [&](const int j, auto mask_tag) {
       constexpr bool MASK = decltype(mask_tag)::value;
-      mbar_wait(s_full + (j & 1), (j >> 1) & 1);
+      mbar_wait(s_full, j & 1);
       tc_fence_after();
-      uint32_t r0[32], r1[32];
-      tmem_ld_x32(tmem + lane_addr + (j & 1) * 64, r0);
-      tmem_ld_x32(tmem + lane_addr + (j & 1) * 64 + 32, r1);
+      uint32_t r0[32];
+      tmem_ld_x32(tmem + lane_addr, r0);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty + (j & 1));
-      float s[64];
+      if (lane == 0) mbar_arrive(s_empty);
+      float s[BKV];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) { s[i] = __uint_as_float(r0[i]); s[32 + i] = __uint_as_float(r1[i]); }
+      for (int i = 0; i < BKV; ++i) s[i] = __uint_as_float(r0[i]);
       if constexpr (MASK) {
         const int lo = seg_b - (kv_base + j * BKV), hi = seg_e - (kv_base + j * BKV);   // valid columns: [lo, hi)
 #pragma unroll
-        for (int i = 0; i < 64; ++i) if (i < lo || i >= hi) s[i] = -INFINITY;
+        for (int i = 0; i < BKV; ++i) if (i < lo || i >= hi) s[i] = -INFINITY;
       }
-      float mx4[4] = {s[0], s[1], s[2], s[3]};          // four independent chains, not one 64-deep dependency
+      float mx4[4] = {s[0], s[1], s[2], s[3]};          // four independent chains, not one deep dependency
 #pragma unroll
-      for (int i = 4; i < 64; i += 4) {
+      for (int i = 4; i < BKV; i += 4) {
         mx4[0] = fmaxf(mx4[0], s[i]); mx4[1] = fmaxf(mx4[1], s[i + 1]);
         mx4[2] = fmaxf(mx4[2], s[i + 2]); mx4[3] = fmaxf(mx4[3], s[i + 3]);
       }
       const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      // the first tile of a segment always holds a valid column, so m_used is finite from then on; a later tile that
+      // is masked entirely (mx = -inf) keeps the scale
       const bool grow = (mx - m_used) * sl2 > 8.0f;          // true on the first tile (m_used = -inf)
       float factor = 1.0f;
       if (grow) { factor = ex2_approx((m_used - mx) * sl2); m_used = mx; }
       // the exponentials only need registers: they run while the tensor core is still busy with P_{j-1} V_{j-1}
       const float ms = m_used * sl2;
-      uint32_t pk[32];
+      uint32_t pk[BKV / 2];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) pk[i] = pack2<F16>(ex2_approx(s[2 * i] * sl2 - ms), ex2_approx(s[2 * i + 1] * sl2 - ms));
+      for (int i = 0; i < BKV / 2; ++i) pk[i] = pack2<F16>(ex2_approx(s[2 * i] * sl2 - ms), ex2_approx(s[2 * i + 1] * sl2 - ms));
       if (j > 0) {
         mbar_wait(pv_done, (j - 1) & 1);                     // P buffer free, O_{j-1} accumulated
         if (__any_sync(0xffffffffu, grow)) rescale_o(factor);
       }
-      store_p(pk);
+#pragma unroll
+      for (int c = 0; c < kRowP / 16; ++c)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow_s + ((c ^ psw) << 4)), "r"(pk[4 * c]),
+                     "r"(pk[4 * c + 1]), "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3])
+                     : "memory");
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
@@ -275,7 +337,7 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const __grid_const
     float inv;
     {
       uint32_t t[16];
-      tmem_ld_x16(tmem + lane_addr + 128 + HD, t);       // column 80 = sum of the row's probabilities
+      tmem_ld_x16(tmem + lane_addr + kOCol + HD, t);     // column 80 = sum of the row's probabilities
       tmem_ld_wait();
       inv = 1.f / __uint_as_float(t[0]);
     }
@@ -283,7 +345,7 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const __grid_const
 #pragma unroll
     for (int c = 0; c < 80; c += 16) {
       uint32_t t[16];
-      tmem_ld_x16(tmem + lane_addr + 128 + c, t);
+      tmem_ld_x16(tmem + lane_addr + kOCol + c, t);
       tmem_ld_wait();
       if (row < q_len) {
 #pragma unroll
@@ -298,7 +360,7 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const __grid_const
     tc_fence_before();
   }
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();                             // the partner's last multicast arrivals have landed before this CTA exits
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, kTmemCols); }
 }
 
@@ -339,11 +401,11 @@ int attention_tc(const void* qkv, const void* vt, int64_t s_pad, void* out, int6
   if (n_tiles <= 0) return ZV_OK;
   const int hidden = heads * head_dim;
   CUtensorMap t64, t16, tvt;
-  int rc = make_tmap_2d(&t64, qkv, S, 3 * hidden, 3 * hidden, 64, 64, 128, f16);
+  int rc = make_tmap_2d(&t64, qkv, S, 3 * hidden, 3 * hidden, 64, 16, 128, f16);      // half K tiles (and 16-row Q pieces)
   if (rc) return rc;
-  rc = make_tmap_2d(&t16, qkv, S, 3 * hidden, 3 * hidden, 16, 64, 32, f16);
+  rc = make_tmap_2d(&t16, qkv, S, 3 * hidden, 3 * hidden, 16, 16, 32, f16);
   if (rc) return rc;
-  rc = make_tmap_2d(&tvt, vt, hidden, S, s_pad, 64, HD, 128, f16);
+  rc = make_tmap_2d(&tvt, vt, hidden, S, s_pad, BKV, HD / 2, 64, f16);                    // half V^T tiles (40 head dims)
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
@@ -353,14 +415,25 @@ int attention_tc(const void* qkv, const void* vt, int64_t s_pad, void* out, int6
     attr_set = true;
   }
   AttnArgs a{};
-  a.out = out; a.tiles = reinterpret_cast<const int4*>(tiles_dev); a.heads = heads; a.hidden = hidden; a.f16 = f16;
+  a.out = out; a.tiles = reinterpret_cast<const int4*>(tiles_dev); a.n_tiles = n_tiles; a.heads = heads; a.hidden = hidden; a.f16 = f16;
   a.scale_log2 = (float)(1.4426950408889634 / std::sqrt((double)head_dim));
-  dim3 grid((unsigned)n_tiles, (unsigned)heads);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)((n_tiles + 1) & ~1), (unsigned)heads);      // clusters of two neighbouring q tiles
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmem;
+  cfg.stream = static_cast<cudaStream_t>(stream_);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le;
   {
     KernelTimer timer(KC_ATTN_FULL, stream_);
-    if (f16) attn_tc_kernel<true><<<grid, kThreads, kSmem, static_cast<cudaStream_t>(stream_)>>>(t64, t16, tvt, a);
-    else attn_tc_kernel<false><<<grid, kThreads, kSmem, static_cast<cudaStream_t>(stream_)>>>(t64, t16, tvt, a);
+    le = f16 ? cudaLaunchKernelEx(&cfg, attn_tc_kernel<true>, t64, t16, tvt, a)
+             : cudaLaunchKernelEx(&cfg, attn_tc_kernel<false>, t64, t16, tvt, a);
   }
+  if (le != cudaSuccess) return fail(ZV_ECUDA, "attention_tc: launch: %s", cudaGetErrorString(le));
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(ZV_ECUDA, "attention_tc: launch: %s", cudaGetErrorString(e));

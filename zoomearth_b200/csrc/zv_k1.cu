@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(256) k1_vpass(const K1Crop* __restrict__ crops
 // Horizontal pass on dp4a.  Item = (crop, 128-column chunk, first strip, strips): the CTA keeps the chunk's limb words
 // in registers (thread = output column x row quad) and streams 8-row strips of the source through shared memory.
 template <int NW>
-__global__ void __launch_bounds__(256) k1_hpass_fast(const K1Crop* __restrict__ crops, const int4* __restrict__ items,
+__global__ void __launch_bounds__(256, NW <= 2 ? 4 : 3) k1_hpass_fast(const K1Crop* __restrict__ crops, const int4* __restrict__ items,
                                                      int n_items, const int32_t* __restrict__ coef,
                                                      uint8_t* __restrict__ ws, int seg_words_max) {
   extern __shared__ uint32_t planes[];            // [8 rows][3 planes][seg_words_max], then raw[2][8][raw_pitch]
@@ -247,19 +247,29 @@ __global__ void __launch_bounds__(256) k1_hpass_fast(const K1Crop* __restrict__ 
       const int64_t g0 = b0 - delta;                                      // row byte offset of raw[0]; rowp + g0 is 16-aligned
       const int n_chunks = (delta + seg_words * 12 + 15) >> 4;
       uint8_t* rraw = raw + (buf * kHRows + warp) * raw_pitch;
+      // chunks [ck_lo, ck_hi) lie wholly inside the image row: plain 16-byte async copies; the few others (box beyond
+      // the left / right border, or the whole row outside the image) are assembled byte by byte with zero fill
+      int ck_lo = 0, ck_hi = 0;
+      if (row_ok) {
+        ck_lo = g0 >= 0 ? 0 : (int)((-g0 + 15) >> 4);
+        ck_hi = (int)min((int64_t)n_chunks, (row_bytes - g0) >> 4);
+        ck_lo = min(ck_lo, n_chunks);
+        ck_hi = max(ck_hi, ck_lo);
+      }
+      const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(rraw);
+      const uint8_t* src0 = rowp + g0;
       for (int ck = lane; ck < n_chunks; ck += 32) {
-        const int64_t o = g0 + 16 * (int64_t)ck;
-        uint8_t* dst = rraw + 16 * ck;
-        if (row_ok && o >= 0 && o + 16 <= row_bytes) {
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(rowp + o) : "memory");
+        if (ck >= ck_lo && ck < ck_hi) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + 16 * ck), "l"(src0 + 16 * (int64_t)ck) : "memory");
         } else {
+          const int64_t o = g0 + 16 * (int64_t)ck;
           uint32_t wv[4] = {0u, 0u, 0u, 0u};
           if (row_ok && o + 16 > 0 && o < row_bytes) {
 #pragma unroll
             for (int k = 0; k < 16; ++k)
               if (o + k >= 0 && o + k < row_bytes) wv[k >> 2] |= (uint32_t)__ldg(rowp + o + k) << (8 * (k & 3));
           }
-          *reinterpret_cast<uint4*>(dst) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+          *reinterpret_cast<uint4*>(rraw + 16 * ck) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
         }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
@@ -283,12 +293,21 @@ __global__ void __launch_bounds__(256) k1_hpass_fast(const K1Crop* __restrict__ 
         const uint32_t sh = (uint32_t)(delta_cur & 3) * 8;
         const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(rraw + (delta_cur & ~3));
         uint32_t* p = planes + (warp * 3) * seg_words_max;
-        for (int wq = lane; wq < seg_words; wq += 32) {
-          const uint32_t x0 = wsrc[3 * wq], x1 = wsrc[3 * wq + 1], x2 = wsrc[3 * wq + 2], x3 = wsrc[3 * wq + 3];
-          const uint32_t v0 = __funnelshift_r(x0, x1, sh), v1 = __funnelshift_r(x1, x2, sh), v2 = __funnelshift_r(x2, x3, sh);
-          p[wq] = __byte_perm(__byte_perm(v0, v1, 0x0630), v2, 0x5210);
-          p[seg_words_max + wq] = __byte_perm(__byte_perm(v0, v1, 0x0741), v2, 0x6210);
-          p[2 * seg_words_max + wq] = __byte_perm(__byte_perm(v0, v1, 0x0052), v2, 0x7410);
+        if (sh == 0) {
+          for (int wq = lane; wq < seg_words; wq += 32) {
+            const uint32_t v0 = wsrc[3 * wq], v1 = wsrc[3 * wq + 1], v2 = wsrc[3 * wq + 2];
+            p[wq] = __byte_perm(__byte_perm(v0, v1, 0x0630), v2, 0x5210);
+            p[seg_words_max + wq] = __byte_perm(__byte_perm(v0, v1, 0x0741), v2, 0x6210);
+            p[2 * seg_words_max + wq] = __byte_perm(__byte_perm(v0, v1, 0x0052), v2, 0x7410);
+          }
+        } else {
+          for (int wq = lane; wq < seg_words; wq += 32) {
+            const uint32_t x0 = wsrc[3 * wq], x1 = wsrc[3 * wq + 1], x2 = wsrc[3 * wq + 2], x3 = wsrc[3 * wq + 3];
+            const uint32_t v0 = __funnelshift_r(x0, x1, sh), v1 = __funnelshift_r(x1, x2, sh), v2 = __funnelshift_r(x2, x3, sh);
+            p[wq] = __byte_perm(__byte_perm(v0, v1, 0x0630), v2, 0x5210);
+            p[seg_words_max + wq] = __byte_perm(__byte_perm(v0, v1, 0x0741), v2, 0x6210);
+            p[2 * seg_words_max + wq] = __byte_perm(__byte_perm(v0, v1, 0x0052), v2, 0x7410);
+          }
         }
       }
       delta_cur = delta_next;
