@@ -5,10 +5,12 @@
 //                   [rows][16] block), accumulator in TMEM (one S buffer: the softmax pulls a tile into registers as
 //                   soon as it is complete, which frees the buffer for Q K_{j+1}^T while the exponentials run)
 //   softmax         four warps, one thread per q row: tcgen05.ld of the row, online max/sum in fp32 with exp2,
-//                   P_j rounded to 16 bit and written to shared memory in the 64B-swizzled K-major layout
-//   O += P_j V_j    tcgen05.mma M=128 N=96 K=32 from P (smem) and V^T (smem, kv contiguous: V is pre-transposed per
-//                   head by transpose_v so that the B operand is K-major); O stays in TMEM for the whole segment and
-//                   is rescaled lazily (only when the row max grows by more than 2^8).
+//                   P_j rounded to 16 bit and written back to TENSOR memory (tcgen05.st, two values per column)
+//   O += P_j V_j    tcgen05.mma M=128 N=80 K=32 with A = P straight from TMEM and B = V^T from shared memory (kv
+//                   contiguous: V is pre-transposed per head by transpose_v so that the B operand is K-major); O stays
+//                   in TMEM for the whole segment and is rescaled lazily (only when the row max grows by more than 2^8).
+//                   P never touches shared memory: the tensor core's operand reads from shared memory were the busiest
+//                   unit of the kernel (80 % with P in smem).
 // The kernel is bound by the softmax warps (one exp2 per score on a 16/clk/SM unit, plus the latency of each warp's
 // dependent chain), so the CTA is kept small - 128 TMEM columns, ~51 KB of shared memory, <= 85 registers - and FOUR
 // CTAs share an SM: four softmax warps per scheduler keep the SFU busy where two (64-row KV tiles, 256 TMEM columns)
@@ -38,18 +40,17 @@ namespace {
 
 constexpr int HD = 80, BQ = 128, BKV = 32, STAGES = 2, kCtasPerSm = 4;
 constexpr int kQ64 = BQ * 64 * 2, kQ16 = BQ * 16 * 2;                   // 16384, 4096
-constexpr int VROWS = 96;                                                 // V^T rows in smem: 80 head dims, a row of ones, 15 zero rows
-constexpr int kRowP = BKV * 2;                                            // bytes per P / V^T row in smem (64: 64B swizzle)
-constexpr int kK64 = BKV * 64 * 2, kK16 = BKV * 16 * 2, kVtTma = HD * kRowP, kVt = VROWS * kRowP;   // 4096, 1024, 5120, 6144
-constexpr int kStage = kK64 + kK16 + kVt;                                // 11264
-constexpr int kP = BQ * kRowP;                                           // 8192
-constexpr int kOffQ16 = kQ64, kOffStage = kQ64 + kQ16, kOffP = kOffStage + STAGES * kStage, kOffBar = kOffP + kP;
+constexpr int kRowP = BKV * 2;                                            // bytes per V^T row in smem (64: 64B swizzle)
+constexpr int kK64 = BKV * 64 * 2, kK16 = BKV * 16 * 2, kVtTma = HD * kRowP, kVt = kVtTma;   // 4096, 1024, 5120
+constexpr int kStage = kK64 + kK16 + kVt;                                // 10240
+constexpr int kOffQ16 = kQ64, kOffStage = kQ64 + kQ16, kOffBar = kOffStage + STAGES * kStage;
 constexpr int kSmem = kOffBar + 256 + 1024;
-constexpr int kTmemCols = 128, kOCol = BKV;                              // S [0,32)  O [32,128): 80 dims + row sum + pad
+constexpr int kTmemCols = 128, kOCol = BKV, kPCol = BKV + HD;            // S [0,32)  O [32,112)  P [112,128): 16-bit pairs
 constexpr int kThreads = 192;
 constexpr uint32_t kSw128 = 2, kSw64 = 4, kSw32 = 6;                     // UMMA descriptor layout types
-static_assert(BKV == 32, "the P / V^T tiles are laid out for 64-byte rows (BKV = 32)");
-static_assert(kStage % 1024 == 0 && kOffStage % 1024 == 0 && (kK64 + kK16) % 512 == 0 && kOffP % 512 == 0, "swizzle atom alignment");
+static_assert(BKV == 32, "the V^T tiles are laid out for 64-byte rows (BKV = 32)");
+static_assert(kStage % 1024 == 0 && kOffStage % 1024 == 0 && (kK64 + kK16) % 512 == 0, "swizzle atom alignment");
+static_assert(kPCol + BKV / 2 <= kTmemCols, "TMEM budget");
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = 0;
@@ -96,6 +97,14 @@ __device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const void* tmap,
 __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+
+// D[tmem] (+)= A[tmem] * B[smem]^T: A = 128 rows (lanes) x 16 K-values packed two per 32-bit column
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 
 struct AttnArgs {
@@ -156,15 +165,6 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) attn_tc_kernel(const __g
     fence_mbar_init();
   }
   if (warp == 0) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
-  // rows 80..95 of every V^T stage: a row of ones (so that column 80 of O = P [V | 1] is the softmax row sum, computed
-  // by the tensor core from the same rounded P that multiplies V) and zero rows; constant rows are swizzle-invariant
-  for (int i = threadIdx.x; i < STAGES * 16 * (kRowP / 16); i += kThreads) {
-    const int per = 16 * (kRowP / 16);
-    const int st = i / per, r = (i % per) / (kRowP / 16), c = i % (kRowP / 16);
-    const uint32_t one2 = F16 ? 0x3C003C00u : 0x3F803F80u;
-    const uint32_t v = r == 0 ? one2 : 0u;
-    *reinterpret_cast<uint4*>(smem + kOffStage + st * kStage + kK64 + kK16 + (HD + r) * kRowP + c * 16) = make_uint4(v, v, v, v);
-  }
   fence_proxy_async();
   tc_fence_before();
   cluster_sync_all();                             // both CTAs' barriers exist before either multicasts into the other
@@ -214,8 +214,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) attn_tc_kernel(const __g
     if (elect_one()) {
       // ---- MMA issuer
       const uint32_t idesc_qk = umma_idesc_16bit(BQ, BKV, F16);
-      const uint32_t idesc_pv = umma_idesc_16bit(BQ, VROWS, F16);
-      const uint32_t sq = smem_u32(smem), sq16 = smem_u32(smem + kOffQ16), sp = smem_u32(smem + kOffP);
+      const uint32_t idesc_pv = umma_idesc_16bit(BQ, HD, F16);
+      const uint32_t sq = smem_u32(smem), sq16 = smem_u32(smem + kOffQ16);
       auto issue_qk = [&](int t) {
         const int st = t % STAGES;
         const uint32_t sk = smem_u32(smem + kOffStage + st * kStage);
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) attn_tc_kernel(const __g
         tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < BKV / 16; ++ks)
-          umma_bf16(tmem + kOCol, umma_desc(sp, 512, kSw64) + 2 * ks, umma_desc(sv, 512, kSw64) + 2 * ks, idesc_pv, (j | ks) != 0);
+          umma_ts(tmem + kOCol, tmem + kPCol + 8 * ks, umma_desc(sv, 512, kSw64) + 2 * ks, idesc_pv, (j | ks) != 0);
         if (shared_kv) umma_commit_mc(v_empty + st, 3); else umma_commit(v_empty + st);
         umma_commit(pv_done);
       }
@@ -254,18 +254,14 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) attn_tc_kernel(const __g
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const float sl2 = a.scale_log2;
-    float m_used = -INFINITY;               // scale in use (raw score units); the row sum lives in O column 80
-    // this thread's P row, K-major 64B swizzle: 16-byte chunk c of row r lives at chunk (c ^ ((r >> 1) & 3))
-    // (st.shared through the 32-bit shared address: the generic-pointer form compiles to ST.E, whose completion the
-    // proxy fence then waits on for several hundred cycles)
-    const uint32_t prow_s = smem_u32(smem + kOffP + row * kRowP);
-    const int psw = (row >> 1) & 3;
+    float m_used = -INFINITY;               // scale in use (raw score units)
+    float l_run = 0.f;                      // running sum of the row's probabilities, in that scale
 
-    // rescale the O row (and its sum column) by `factor` - warp-collective TMEM round trip
+    // rescale the O row by `factor` - warp-collective TMEM round trip
     auto rescale_o = [&](const float factor) {
       tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < VROWS; c += 16) {
+      for (int c = 0; c < HD; c += 16) {
         uint32_t t[16];
         tmem_ld_x16(tmem + lane_addr + kOCol + c, t);
         tmem_ld_wait();
@@ -313,18 +309,23 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) attn_tc_kernel(const __g
       // the exponentials only need registers: they run while the tensor core is still busy with P_{j-1} V_{j-1}
       const float ms = m_used * sl2;
       uint32_t pk[BKV / 2];
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int i = 0; i < BKV / 2; ++i) pk[i] = pack2<F16>(ex2_approx(s[2 * i] * sl2 - ms), ex2_approx(s[2 * i + 1] * sl2 - ms));
+      for (int i = 0; i < BKV / 2; ++i) {
+        const float p0 = ex2_approx(s[2 * i] * sl2 - ms), p1 = ex2_approx(s[2 * i + 1] * sl2 - ms);
+        sum4[(2 * i) & 3] += p0;
+        sum4[(2 * i + 1) & 3] += p1;
+        pk[i] = pack2<F16>(p0, p1);
+      }
+      l_run = l_run * factor + ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
       if (j > 0) {
-        mbar_wait(pv_done, (j - 1) & 1);                     // P buffer free, O_{j-1} accumulated
+        mbar_wait(pv_done, (j - 1) & 1);                     // the tensor core is done with P_{j-1}; O_{j-1} accumulated
         if (__any_sync(0xffffffffu, grow)) rescale_o(factor);
       }
-#pragma unroll
-      for (int c = 0; c < kRowP / 16; ++c)
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow_s + ((c ^ psw) << 4)), "r"(pk[4 * c]),
-                     "r"(pk[4 * c + 1]), "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3])
-                     : "memory");
-      fence_proxy_async();
+      tc_fence_after();
+      tmem_st_x16(tmem + lane_addr + kPCol, pk);             // P row -> TMEM, two 16-bit values per column
+      tmem_st_wait();
+      tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
     };
@@ -334,13 +335,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) attn_tc_kernel(const __g
     }
     mbar_wait(pv_done, (n_kv - 1) & 1);
     tc_fence_after();
-    float inv;
-    {
-      uint32_t t[16];
-      tmem_ld_x16(tmem + lane_addr + kOCol + HD, t);     // column 80 = sum of the row's probabilities
-      tmem_ld_wait();
-      inv = 1.f / __uint_as_float(t[0]);
-    }
+    const float inv = 1.f / l_run;
     uint16_t* dst = static_cast<uint16_t*>(a.out) + (int64_t)(q0 + row) * a.hidden + head * HD;
 #pragma unroll
     for (int c = 0; c < 80; c += 16) {
