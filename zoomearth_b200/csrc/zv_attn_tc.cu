@@ -1,27 +1,27 @@
 // K4: tcgen05 flash attention for the full-attention layers (whole-image segments; HF modeling_qwen2_5_vl.py
 // :207-287 with cu_seqlens, blocks 7/15/23/31).  One CTA = one 128-row q tile of one head; K/V stream through a
-// TMA ring in 32-row tiles.
-//   S_j = Q K_j^T   tcgen05.mma M=128 N=32, K = 80 = 4 x 16 (128B-swizzled [rows][64] block) + 16 (32B-swizzled
-//                   [rows][16] block), accumulator in TMEM (one S buffer: the softmax pulls a tile into registers as
-//                   soon as it is complete, which frees the buffer for Q K_{j+1}^T while the exponentials run)
+// TMA ring in 64-row tiles.  Both MMAs take their A operand from TENSOR memory:
+//   Q               loaded once by the softmax threads (one q row each, 160 contiguous bytes from global memory) and
+//                   parked in TMEM as 40 columns of 16-bit pairs
+//   S_j = Q K_j^T   tcgen05.mma M=128 N=64, A = Q (TMEM), B = K_j (smem: a 128B-swizzled [rows][64] block for k 0..63
+//                   and a 32B-swizzled [rows][16] block for k 64..79), fp32 accumulator in TMEM.  One S buffer: the
+//                   softmax pulls a tile into registers as soon as it is complete, which frees the buffer for
+//                   Q K_{j+1}^T while the exponentials run
 //   softmax         four warps, one thread per q row: tcgen05.ld of the row, online max/sum in fp32 with exp2,
-//                   P_j rounded to 16 bit and written back to TENSOR memory (tcgen05.st, two values per column)
-//   O += P_j V_j    tcgen05.mma M=128 N=80 K=32 with A = P straight from TMEM and B = V^T from shared memory (kv
-//                   contiguous: V is pre-transposed per head by transpose_v so that the B operand is K-major); O stays
-//                   in TMEM for the whole segment and is rescaled lazily (only when the row max grows by more than 2^8).
-//                   P never touches shared memory: the tensor core's operand reads from shared memory were the busiest
-//                   unit of the kernel (80 % with P in smem).
-// The kernel is bound by the softmax warps (one exp2 per score on a 16/clk/SM unit, plus the latency of each warp's
-// dependent chain), so the CTA is kept small - 128 TMEM columns, ~51 KB of shared memory, <= 85 registers - and FOUR
-// CTAs share an SM: four softmax warps per scheduler keep the SFU busy where two (64-row KV tiles, 256 TMEM columns)
-// left it idle half of the time.
-// K/V traffic: every q tile of a head streams the head's whole K and V, which made the kernel L2 -> SM bandwidth bound
-// (5.9 TB/s of TMA reads whatever the SM-side schedule).  CTAs therefore run as clusters of two neighbouring q tiles of
-// the same head: each CTA fetches half of every K / V^T tile and TMA-multicasts it into both CTAs' shared memory, which
-// halves the L2 reads; a stage is recycled when BOTH tensor cores are done with it (multicast tcgen05.commit).  Pairs
-// that straddle a segment boundary (or the odd last tile) fall back to private loads.
+//                   P_j rounded to 16 bit and written back to TMEM (tcgen05.st, two values per column)
+//   O += P_j V_j    tcgen05.mma M=128 N=80 K=64, A = P (TMEM), B = V^T (smem, kv contiguous: V is pre-transposed per
+//                   head by transpose_v so that the B operand is K-major); O stays in TMEM for the whole segment and
+//                   is rescaled lazily (only when the row max grows by more than 2^8).
+// Why TMEM operands: with A read from shared memory every K=16 step streams 4 KB of Q or P next to 1-3 KB of K/V and the
+// tensor pipe sat at 80 % busy on operand fetch alone (ncu sm__pipe_tc_cycles_active) while doing 40 % of its math rate;
+// with A in TMEM only the B tiles cross the shared-memory port.
+// K/V traffic: every q tile of a head streams the head's whole K and V.  CTAs run as clusters of two neighbouring q
+// tiles of the same head: each CTA fetches half of every K / V^T tile and TMA-multicasts it into both CTAs' shared
+// memory, which halves the L2 reads; a stage is recycled when BOTH tensor cores are done with it (multicast
+// tcgen05.commit).  Pairs that straddle a segment boundary (or the odd last tile) fall back to private loads.
 // Warp roles (192 threads): warp 0 = TMA producer + TMEM allocator, warp 1 = MMA issuer, warps 2-5 = softmax
-// (TMEM lane quarters 2,3,0,1).  Rotary is already applied to q,k by the QKV GEMM epilogue.
+// (TMEM lane quarters 2,3,0,1).  Two CTAs per SM (216 of 256 TMEM columns each).  Rotary is already applied to q,k by
+// the QKV GEMM epilogue.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -38,19 +38,19 @@ namespace zv {
 using namespace ptx;
 namespace {
 
-constexpr int HD = 80, BQ = 128, BKV = 32, STAGES = 2, kCtasPerSm = 4;
-constexpr int kQ64 = BQ * 64 * 2, kQ16 = BQ * 16 * 2;                   // 16384, 4096
-constexpr int kRowP = BKV * 2;                                            // bytes per V^T row in smem (64: 64B swizzle)
-constexpr int kK64 = BKV * 64 * 2, kK16 = BKV * 16 * 2, kVtTma = HD * kRowP, kVt = kVtTma;   // 4096, 1024, 5120
-constexpr int kStage = kK64 + kK16 + kVt;                                // 10240
-constexpr int kOffQ16 = kQ64, kOffStage = kQ64 + kQ16, kOffBar = kOffStage + STAGES * kStage;
+constexpr int HD = 80, BQ = 128, BKV = 64, STAGES = 3, kCtasPerSm = 2;
+constexpr int kRowV = BKV * 2;                                            // bytes per V^T row in smem (128: 128B swizzle)
+constexpr int kK64 = BKV * 64 * 2, kK16 = BKV * 16 * 2, kVt = HD * kRowV;   // 8192, 2048, 10240
+constexpr int kStage = kK64 + kK16 + kVt;                                // 20480
+constexpr int kOffBar = STAGES * kStage;
 constexpr int kSmem = kOffBar + 256 + 1024;
-constexpr int kTmemCols = 128, kOCol = BKV, kPCol = BKV + HD;            // S [0,32)  O [32,112)  P [112,128): 16-bit pairs
+// TMEM columns: S [0,64)  O [64,144)  P [144,176) 16-bit pairs  Q [176,216) 16-bit pairs
+constexpr int kTmemCols = 256, kOCol = BKV, kPCol = kOCol + HD, kQCol = kPCol + BKV / 2;
 constexpr int kThreads = 192;
-constexpr uint32_t kSw128 = 2, kSw64 = 4, kSw32 = 6;                     // UMMA descriptor layout types
-static_assert(BKV == 32, "the V^T tiles are laid out for 64-byte rows (BKV = 32)");
-static_assert(kStage % 1024 == 0 && kOffStage % 1024 == 0 && (kK64 + kK16) % 512 == 0, "swizzle atom alignment");
-static_assert(kPCol + BKV / 2 <= kTmemCols, "TMEM budget");
+constexpr uint32_t kSw128 = 2, kSw32 = 6;                                // UMMA descriptor layout types
+static_assert(BKV == 64, "the V^T tiles are laid out for 128-byte rows (BKV = 64)");
+static_assert(kStage % 1024 == 0 && (kK64 + kK16) % 1024 == 0 && kK64 % 1024 == 0, "swizzle atom alignment");
+static_assert(kQCol + HD / 2 <= kTmemCols, "TMEM budget");
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = 0;
@@ -67,6 +67,11 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[
       ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
         "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
+}
+__device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -109,6 +114,8 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
 
 struct AttnArgs {
   void* out;
+  const void* qkv;           // (S, 3 * hidden) 16-bit: the q rows are read directly, K goes through TMA
+  int64_t S;
   const int4* tiles;
   int n_tiles;
   int heads, hidden, f16;
@@ -116,13 +123,13 @@ struct AttnArgs {
 };
 
 template <bool F16>
-__global__ void __launch_bounds__(kThreads, kCtasPerSm) attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qk64,
-                                                                       const __grid_constant__ CUtensorMap tm_qk16,
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k64,
+                                                                       const __grid_constant__ CUtensorMap tm_k16,
                                                                        const __grid_constant__ CUtensorMap tm_vt, const AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
-  uint64_t* q_full = bars;             // 1
+  uint64_t* q_full = bars;             // Q parked in TMEM (4 softmax warps)
   uint64_t* k_full = bars + 1;         // STAGES (<= 3)
   uint64_t* v_full = bars + 4;
   uint64_t* k_empty = bars + 7;
@@ -156,8 +163,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) attn_tc_kernel(const __g
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    prefetch_tensormap(&tm_qk64); prefetch_tensormap(&tm_qk16); prefetch_tensormap(&tm_vt);
-    mbar_init(q_full, 1);
+    prefetch_tensormap(&tm_k64); prefetch_tensormap(&tm_k16); prefetch_tensormap(&tm_vt);
+    mbar_init(q_full, 4);
     const int users = shared_kv ? 2 : 1;          // tensor cores that must be done with a stage before it is refilled
     for (int s = 0; s < STAGES; ++s) { mbar_init(k_full + s, 1); mbar_init(v_full + s, 1); mbar_init(k_empty + s, users); mbar_init(v_empty + s, users); }
     mbar_init(s_full, 1); mbar_init(s_empty, 4);
@@ -165,7 +172,6 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) attn_tc_kernel(const __g
     fence_mbar_init();
   }
   if (warp == 0) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
-  fence_proxy_async();
   tc_fence_before();
   cluster_sync_all();                             // both CTAs' barriers exist before either multicasts into the other
   tc_fence_after();
@@ -173,40 +179,34 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) attn_tc_kernel(const __g
 
   if (warp == 0) {
     if (elect_one()) {
-      // ---- TMA producer: Q once, then the K / V^T ring.  Boxes are half tiles (16 K rows, 40 V^T rows): in a sharing
-      // pair CTA `rank` fetches half `rank` and multicasts it to both CTAs; a private CTA fetches both halves itself.
-      const int colq = head * HD, colk = a.hidden + head * HD;
-      mbar_arrive_expect_tx(q_full, kQ64 + kQ16);
-#pragma unroll
-      for (int i = 0; i < BQ / 16; ++i) {
-        tma_load_2d(smem + i * (16 * 128), &tm_qk64, q_full, colq, q0 + i * 16);
-        tma_load_2d(smem + kOffQ16 + i * (16 * 32), &tm_qk16, q_full, colq + 64, q0 + i * 16);
-      }
+      // ---- TMA producer: the K / V^T ring.  Boxes are half tiles (32 K rows, 40 V^T rows): in a sharing pair CTA
+      // `rank` fetches half `rank` and multicasts it to both CTAs; a private CTA fetches both halves itself.
+      const int colk = a.hidden + head * HD;
       for (int j = 0; j < n_kv; ++j) {
         const int st = j % STAGES;
         const uint32_t ph = (j / STAGES) & 1;
-        uint8_t* sk = smem + kOffStage + st * kStage;
+        uint8_t* sk = smem + st * kStage;
         const int row = kv_base + j * BKV;
         mbar_wait(k_empty + st, ph ^ 1);
         mbar_arrive_expect_tx(k_full + st, kK64 + kK16);
         if (shared_kv) {
-          tma_load_2d_mc(sk + rank * (kK64 / 2), &tm_qk64, k_full + st, colk, row + rank * 16, 3);
-          tma_load_2d_mc(sk + kK64 + rank * (kK16 / 2), &tm_qk16, k_full + st, colk + 64, row + rank * 16, 3);
+          tma_load_2d_mc(sk + rank * (kK64 / 2), &tm_k64, k_full + st, colk, row + rank * (BKV / 2), 3);
+          tma_load_2d_mc(sk + kK64 + rank * (kK16 / 2), &tm_k16, k_full + st, colk + 64, row + rank * (BKV / 2), 3);
         } else {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            tma_load_2d(sk + h * (kK64 / 2), &tm_qk64, k_full + st, colk, row + h * 16);
-            tma_load_2d(sk + kK64 + h * (kK16 / 2), &tm_qk16, k_full + st, colk + 64, row + h * 16);
+            tma_load_2d(sk + h * (kK64 / 2), &tm_k64, k_full + st, colk, row + h * (BKV / 2));
+            tma_load_2d(sk + kK64 + h * (kK16 / 2), &tm_k16, k_full + st, colk + 64, row + h * (BKV / 2));
           }
         }
         mbar_wait(v_empty + st, ph ^ 1);
-        mbar_arrive_expect_tx(v_full + st, kVtTma);
+        mbar_arrive_expect_tx(v_full + st, kVt);
         if (shared_kv) {
-          tma_load_2d_mc(sk + kK64 + kK16 + rank * (kVtTma / 2), &tm_vt, v_full + st, row, head * HD + rank * (HD / 2), 3);
+          tma_load_2d_mc(sk + kK64 + kK16 + rank * (kVt / 2), &tm_vt, v_full + st, row, head * HD + rank * (HD / 2), 3);
         } else {
 #pragma unroll
           for (int h = 0; h < 2; ++h)
-            tma_load_2d(sk + kK64 + kK16 + h * (kVtTma / 2), &tm_vt, v_full + st, row, head * HD + h * (HD / 2));
+            tma_load_2d(sk + kK64 + kK16 + h * (kVt / 2), &tm_vt, v_full + st, row, head * HD + h * (HD / 2));
         }
       }
     }
@@ -215,17 +215,16 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) attn_tc_kernel(const __g
       // ---- MMA issuer
       const uint32_t idesc_qk = umma_idesc_16bit(BQ, BKV, F16);
       const uint32_t idesc_pv = umma_idesc_16bit(BQ, HD, F16);
-      const uint32_t sq = smem_u32(smem), sq16 = smem_u32(smem + kOffQ16);
       auto issue_qk = [&](int t) {
         const int st = t % STAGES;
-        const uint32_t sk = smem_u32(smem + kOffStage + st * kStage);
+        const uint32_t sk = smem_u32(smem + st * kStage);
         mbar_wait(k_full + st, (t / STAGES) & 1);
         mbar_wait(s_empty, (t & 1) ^ 1);                     // the softmax holds S_{t-1} in registers
         tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
-          umma_bf16(tmem, umma_desc(sq, 1024, kSw128) + 2 * ks, umma_desc(sk, 1024, kSw128) + 2 * ks, idesc_qk, ks != 0);
-        umma_bf16(tmem, umma_desc(sq16, 256, kSw32), umma_desc(sk + kK64, 256, kSw32), idesc_qk, 1);
+          umma_ts(tmem, tmem + kQCol + 8 * ks, umma_desc(sk, 1024, kSw128) + 2 * ks, idesc_qk, ks != 0);
+        umma_ts(tmem, tmem + kQCol + 32, umma_desc(sk + kK64, 256, kSw32), idesc_qk, 1);
         if (shared_kv) umma_commit_mc(k_empty + st, 3); else umma_commit(k_empty + st);
         umma_commit(s_full);
       };
@@ -234,13 +233,13 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) attn_tc_kernel(const __g
       for (int j = 0; j < n_kv; ++j) {
         if (j + 1 < n_kv) issue_qk(j + 1);
         const int st = j % STAGES;
-        const uint32_t sv = smem_u32(smem + kOffStage + st * kStage + kK64 + kK16);
+        const uint32_t sv = smem_u32(smem + st * kStage + kK64 + kK16);
         mbar_wait(v_full + st, (j / STAGES) & 1);
         mbar_wait(p_full, j & 1);
         tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < BKV / 16; ++ks)
-          umma_ts(tmem + kOCol, tmem + kPCol + 8 * ks, umma_desc(sv, 512, kSw64) + 2 * ks, idesc_pv, (j | ks) != 0);
+          umma_ts(tmem + kOCol, tmem + kPCol + 8 * ks, umma_desc(sv, 1024, kSw128) + 2 * ks, idesc_pv, (j | ks) != 0);
         if (shared_kv) umma_commit_mc(v_empty + st, 3); else umma_commit(v_empty + st);
         umma_commit(pv_done);
       }
@@ -249,13 +248,37 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) attn_tc_kernel(const __g
     // ---- softmax warps: thread = q row.  O accumulates in TMEM across KV tiles; it is rescaled (tcgen05.ld ->
     // multiply -> tcgen05.st) only when the running row max grew by more than 2^8 since the scale in use was chosen
     // ("lazy rescale": P may then exceed 1 by at most 2^8, harmless in fp32 sums and 16-bit P), so the common tile
-    // costs one TMEM row load, 32 exp2 and one 64-byte row store per thread.
+    // costs one TMEM row load, 64 exp2 and one TMEM row store per thread.
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const float sl2 = a.scale_log2;
     float m_used = -INFINITY;               // scale in use (raw score units)
     float l_run = 0.f;                      // running sum of the row's probabilities, in that scale
+
+    // Q row -> TMEM (A operand of every Q K^T): 80 16-bit values = 40 columns.  Rows past the end of the tensor read as 0.
+    {
+      uint32_t qv[40];
+      const int64_t grow_ = (int64_t)q0 + row;
+      if (grow_ < a.S) {
+        const uint4* qp = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(a.qkv) + grow_ * 3 * a.hidden + head * HD);
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+          const uint4 v = __ldg(qp + i);
+          qv[4 * i] = v.x; qv[4 * i + 1] = v.y; qv[4 * i + 2] = v.z; qv[4 * i + 3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 40; ++i) qv[i] = 0u;
+      }
+      tmem_st_x16(tmem + lane_addr + kQCol, *reinterpret_cast<const uint32_t(*)[16]>(qv));
+      tmem_st_x16(tmem + lane_addr + kQCol + 16, *reinterpret_cast<const uint32_t(*)[16]>(qv + 16));
+      tmem_st_x8(tmem + lane_addr + kQCol + 32, qv + 32);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(q_full);
+    }
 
     // rescale the O row by `factor` - warp-collective TMEM round trip
     auto rescale_o = [&](const float factor) {
@@ -280,15 +303,16 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) attn_tc_kernel(const __g
       constexpr bool MASK = decltype(mask_tag)::value;
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      uint32_t r0[32];
+      uint32_t r0[32], r1[32];
       tmem_ld_x32(tmem + lane_addr, r0);
+      tmem_ld_x32(tmem + lane_addr + 32, r1);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_empty);
       float s[BKV];
 #pragma unroll
-      for (int i = 0; i < BKV; ++i) s[i] = __uint_as_float(r0[i]);
+      for (int i = 0; i < 32; ++i) { s[i] = __uint_as_float(r0[i]); s[32 + i] = __uint_as_float(r1[i]); }
       if constexpr (MASK) {
         const int lo = seg_b - (kv_base + j * BKV), hi = seg_e - (kv_base + j * BKV);   // valid columns: [lo, hi)
 #pragma unroll
@@ -323,7 +347,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) attn_tc_kernel(const __g
         if (__any_sync(0xffffffffu, grow)) rescale_o(factor);
       }
       tc_fence_after();
-      tmem_st_x16(tmem + lane_addr + kPCol, pk);             // P row -> TMEM, two 16-bit values per column
+      tmem_st_x16(tmem + lane_addr + kPCol, *reinterpret_cast<const uint32_t(*)[16]>(pk));        // P row -> TMEM
+      tmem_st_x16(tmem + lane_addr + kPCol + 16, *reinterpret_cast<const uint32_t(*)[16]>(pk + 16));
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -396,11 +421,11 @@ int attention_tc(const void* qkv, const void* vt, int64_t s_pad, void* out, int6
   if (n_tiles <= 0) return ZV_OK;
   const int hidden = heads * head_dim;
   CUtensorMap t64, t16, tvt;
-  int rc = make_tmap_2d(&t64, qkv, S, 3 * hidden, 3 * hidden, 64, 16, 128, f16);      // half K tiles (and 16-row Q pieces)
+  int rc = make_tmap_2d(&t64, qkv, S, 3 * hidden, 3 * hidden, 64, BKV / 2, 128, f16);     // half K tiles (32 rows)
   if (rc) return rc;
-  rc = make_tmap_2d(&t16, qkv, S, 3 * hidden, 3 * hidden, 16, 16, 32, f16);
+  rc = make_tmap_2d(&t16, qkv, S, 3 * hidden, 3 * hidden, 16, BKV / 2, 32, f16);
   if (rc) return rc;
-  rc = make_tmap_2d(&tvt, vt, hidden, S, s_pad, BKV, HD / 2, 64, f16);                    // half V^T tiles (40 head dims)
+  rc = make_tmap_2d(&tvt, vt, hidden, S, s_pad, BKV, HD / 2, 128, f16);                   // half V^T tiles (40 head dims)
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
@@ -410,7 +435,7 @@ int attention_tc(const void* qkv, const void* vt, int64_t s_pad, void* out, int6
     attr_set = true;
   }
   AttnArgs a{};
-  a.out = out; a.tiles = reinterpret_cast<const int4*>(tiles_dev); a.n_tiles = n_tiles; a.heads = heads; a.hidden = hidden; a.f16 = f16;
+  a.out = out; a.qkv = qkv; a.S = S; a.tiles = reinterpret_cast<const int4*>(tiles_dev); a.n_tiles = n_tiles; a.heads = heads; a.hidden = hidden; a.f16 = f16;
   a.scale_log2 = (float)(1.4426950408889634 / std::sqrt((double)head_dim));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)((n_tiles + 1) & ~1), (unsigned)heads);      // clusters of two neighbouring q tiles
