@@ -39,6 +39,11 @@ MIN_PIXELS = 56 * 56
 # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the four per-block GEMMs at this exact
 # workload (64 images, M = 313 600), from the ncu capture committed as profiles/r01_ncu_traffic_gemm_64img.csv
 NCU_TRAFFIC_GB = {"gemm_qkv": 3.77, "gemm_proj": 4.23, "gemm_swiglu": 3.42, "gemm_down": 6.82}
+# DRAM bytes per image of k1_hpass_fast<7> + k1_vpass_fast<7> (ncu, 8-image launch, profiles/r01_ncu_k1_summary.txt):
+# (608.8 + 108.3 + 118.0 + 53.8) MB / 8; algorithmic 86.52 MB - the uint8 intermediate (14.7 MB/image) makes one round trip
+NCU_K1_TRAFFIC_PER_IMAGE = 111.1e6
+WORKLOAD = ("BASELINE configs[1]: global view, 64 synthetic 5000x5000 uint8 images -> max_pixels=1280*28*28 "
+            "(980x980, grid 1x70x70, 1225 tokens/image) -> Qwen2.5-VL-3B vision tower (random init)")
 KCLASS = {"k1_hpass": 0, "k1_vpass": 1, "gemm_store": 2, "gemm_qkv": 3, "gemm_resid": 4, "gemm_swiglu": 5,
           "gemm_gelu": 6, "gemm_scatter": 7, "attn_window": 8, "attn_full": 9, "rmsnorm": 10, "gather": 11}
 
@@ -148,8 +153,8 @@ def run_reference(args):
         "impl": "reference", "metric": "vision tokens/s crop->patchify->ViT", "value": v, "unit": "tokens/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "global view: 5000x5000 uint8 -> max_pixels=1280*28*28 (980x980, 1225 tokens/image), "
-                               "Qwen2.5-VL-3B vision tower random init", "images_per_step": sample},
+        "config": {"workload": WORKLOAD, "images_per_step": sample,
+                   "sample": f"each step times {sample} of the 64 images on the host cores (bounded sample of the workload)"},
         "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": cores, "kind": "reference",
                          "sample": f"{sample} of the 64 images per step: PIL crop + HF Qwen2VLImageProcessorPil + HF "
                                    f"Qwen2_5_VisionTransformerPretrainedModel fp32 sdpa, {cores} torch threads"},
@@ -308,9 +313,7 @@ def run_ours(args):
             "metric": "vision tokens/s crop->patchify->ViT", "value": value, "unit": "tokens/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[1]: global view, 64 synthetic 5000x5000 uint8 images -> "
-                                   "max_pixels=1280*28*28 (980x980, grid 1x70x70, 1225 tokens/image) -> "
-                                   "Qwen2.5-VL-3B vision tower (random init)",
+            "config": {"workload": WORKLOAD,
                        "images_per_step_per_gpu": n_img, "tokens_per_step_per_gpu": tokens_step,
                        "l2": "inputs larger than L2 (4.8 GB of pixels, 5.5 GB of activations per step)",
                        "parallelism": f"dp{world} by image; embedding gather: {gather_kind}" if world > 1 else "single GPU"},
@@ -325,10 +328,15 @@ def run_ours(args):
                          "launches": gemm_n, "ms_total": gemm_ms, "share_of_step": gemm_ms / ms},
             "roofline_k1": {"bound": "hbm", "kernel": "k1_hpass + k1_vpass", "achieved": k1_gbs, "peak": pk["hbm"],
                             "unit": "GB/s", "frac": k1_gbs / pk["hbm"], "ms_total": k1_ms, "share_of_step": k1_ms / ms,
-                            "traffic": None},
-            "roofline_attn": {"bound": "tensor", "kernel": "attn_kernel (mma.sync)", "achieved": attn_tf,
+                            "traffic": NCU_K1_TRAFFIC_PER_IMAGE * n_img,
+                            "traffic_note": "hpass + vpass DRAM bytes per step (ncu per image x images); algorithmic "
+                                            f"{k1_bytes / 1e9:.2f} GB: the uint8 intermediate between the passes goes through DRAM once"},
+            "roofline_attn": {"bound": "tensor", "kernel": "attn_tc_kernel (tcgen05, full layers) + attn_window_kernel (mma.sync, window layers)", "achieved": attn_tf,
                               "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": attn_tf / pk["tf_sust"],
-                              "ms_total": attn_ms, "share_of_step": attn_ms / ms},
+                              "ms_total": attn_ms, "share_of_step": attn_ms / ms,
+                              "full_layers_tflops": (f_full * args.steps / (cls["attn_full"][0] / 1e3) / 1e12) if cls["attn_full"][0] else 0.0,
+                              "window_layers_gbps": (28 * n_img * S_img * 10240 * args.steps / (cls["attn_window"][0] / 1e3) / 1e9)
+                              if cls["attn_window"][0] else 0.0},
             "tower_tflops": tower_tf,
             "kernel_ms": {k: round(v[0] / args.steps, 3) for k, v in cls.items()},
             "cpu_baseline": cpu_base,
