@@ -75,6 +75,16 @@ __device__ __forceinline__ void load_bias32(const float* __restrict__ b, float (
   for (int j = 0; j < 8; ++j) { const float4 t = __ldg(p + j); v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w; }
 }
 
+// folded RMSNorm, consumer side: 1 / rms of accumulator row `row` from the partial sums its producer left (1 when unused)
+__device__ __forceinline__ float row_rscale(const GemmArgs& g, int row, bool valid) {
+  if (g.row_ss == nullptr || !valid) return 1.f;
+  const float2* p = reinterpret_cast<const float2*>(g.row_ss + (int64_t)row * kSsParts);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kSsParts / 2; ++i) { const float2 t = __ldg(p + i); s += t.x; s += t.y; }
+  return rsqrtf(s / (float)g.norm_dim + g.norm_eps);
+}
+
 // ---- epilogues.  Eight epilogue warps: lane quarter q = warp & 3 (the TMEM lanes a warp may read), column half
 // h = (warp - 4) >> 2.  One thread = one accumulator row, half of the tile's columns.  `taddr` carries the quarter.
 template <int BN, int EPI, typename WaitFn>
@@ -102,6 +112,12 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int m_blk, int n_b
         xv[i] = (row_base + r < g.M) ? *reinterpret_cast<const float4*>(xrow + (int64_t)r * g.ldo + c) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
+    // folded RMSNorm, producer side: 16-bit copy of the new rows + this thread's share of their sums of squares
+    const bool emit = g.x16_out != nullptr;
+    uint16_t* x16row = static_cast<uint16_t*>(g.x16_out) + (int64_t)row_base * g.N + n_blk * BN + half * HALF + cc;
+    float ssp[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ssp[i] = 0.f;
     load_x(0);
     wait_accumulator();
 #pragma unroll 1
@@ -122,10 +138,30 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int m_blk, int n_b
       for (int i = 0; i < 8; ++i) {
         const int rw = 4 * i + rr;
         const float4 a = *reinterpret_cast<const float4*>(xpose + rw * kXposePitch + cc);
-        if (row_base + rw < g.M)
-          *reinterpret_cast<float4*>(xrow + (int64_t)rw * g.ldo + c) = make_float4(xv[i].x + a.x, xv[i].y + a.y, xv[i].z + a.z, xv[i].w + a.w);
+        if (row_base + rw < g.M) {
+          const float4 nx = make_float4(xv[i].x + a.x, xv[i].y + a.y, xv[i].z + a.z, xv[i].w + a.w);
+          *reinterpret_cast<float4*>(xrow + (int64_t)rw * g.ldo + c) = nx;
+          if (emit) {
+            *reinterpret_cast<uint2*>(x16row + (int64_t)rw * g.N + c) = make_uint2(pack2(nx.x, nx.y, g.op_f16 != 0), pack2(nx.z, nx.w, g.op_f16 != 0));
+            ssp[i] += nx.x * nx.x + nx.y * nx.y + nx.z * nx.z + nx.w * nx.w;
+          }
+        }
       }
       if (c + 32 < HALF) load_x(c + 32);
+    }
+    if (emit) {
+      // the 8 lanes that share a row (lane >> 3) each hold 4 of every 32 columns: fixed-order butterfly, then one
+      // lane writes the row's partial for this 128-column half (deterministic: no atomics)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float v = ssp[i];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        const int rw = 4 * i + rr;
+        if ((lane & 7) == 0 && row_base + rw < g.M)
+          g.ss_out[(int64_t)(row_base + rw) * kSsParts + n_blk * (BN / 128) + half] = v;
+      }
     }
   } else if constexpr (EPI == EPI_STORE || EPI == EPI_GELU || EPI == EPI_SCATTER) {
     constexpr int HALF = BN / 2;
@@ -204,6 +240,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int m_blk, int n_b
     }
   } else if constexpr (EPI == EPI_SWIGLU) {
     static_assert(EPI != EPI_SWIGLU || BN == 256, "SwiGLU tiles hold 128 gate + 128 up columns");
+    const float rs = row_rscale(g, row, valid);
 #pragma unroll 1
     for (int c = half * 64; c < half * 64 + 64; c += 32) {
       uint32_t a[32], b[32];
@@ -217,8 +254,8 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int m_blk, int n_b
       uint32_t o[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const float g0 = __uint_as_float(a[2 * j]) + bg[2 * j], g1 = __uint_as_float(a[2 * j + 1]) + bg[2 * j + 1];
-        const float u0 = __uint_as_float(b[2 * j]) + bu[2 * j], u1 = __uint_as_float(b[2 * j + 1]) + bu[2 * j + 1];
+        const float g0 = fmaf(__uint_as_float(a[2 * j]), rs, bg[2 * j]), g1 = fmaf(__uint_as_float(a[2 * j + 1]), rs, bg[2 * j + 1]);
+        const float u0 = fmaf(__uint_as_float(b[2 * j]), rs, bu[2 * j]), u1 = fmaf(__uint_as_float(b[2 * j + 1]), rs, bu[2 * j + 1]);
         o[j] = pack2(silu(g0) * u0, silu(g1) * u1, of16);
       }
       if (valid) {
@@ -249,6 +286,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int m_blk, int n_b
         ropeS[d * 32 + lane] = pair < 20 ? __ldg(rope_h + pair) : __ldg(rope_w + (pair - 20));
       }
     }
+    const float rs = row_rscale(g, row, valid);
     wait_accumulator();
     const bool rot_heads_possible = n_blk * 3 < 2 * g.heads;
     const int row0 = m_blk * BM + q * 32;                  // first row of this quarter
@@ -274,9 +312,9 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int m_blk, int n_b
         }
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) { lo[j] += __uint_as_float(l16[j]); hi[j] += __uint_as_float(h16[j]); }
+        for (int j = 0; j < 16; ++j) { lo[j] = fmaf(__uint_as_float(l16[j]), rs, lo[j]); hi[j] = fmaf(__uint_as_float(h16[j]), rs, hi[j]); }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { lo[16 + j] += __uint_as_float(l8[j]); hi[16 + j] += __uint_as_float(h8[j]); }
+        for (int j = 0; j < 8; ++j) { lo[16 + j] = fmaf(__uint_as_float(l8[j]), rs, lo[16 + j]); hi[16 + j] = fmaf(__uint_as_float(h8[j]), rs, hi[16 + j]); }
       } else {
         uint32_t l16[16], h16[16];
         __syncwarp();
@@ -291,7 +329,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int m_blk, int n_b
         }
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) { lo[j] += __uint_as_float(l16[j]); hi[j] += __uint_as_float(h16[j]); }
+        for (int j = 0; j < 16; ++j) { lo[j] = fmaf(__uint_as_float(l16[j]), rs, lo[j]); hi[j] = fmaf(__uint_as_float(h16[j]), rs, hi[j]); }
       }
       if (rotate) {
 #pragma unroll

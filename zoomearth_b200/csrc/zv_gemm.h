@@ -23,7 +23,18 @@ struct GemmArgs {
   void* peers[8];
   int n_peers;
   int64_t peer_row_off;
+  // RMSNorm folded into the GEMMs around it (the norm gain is folded into the consumer's weight columns at pack time):
+  //   producer (EPI_RESID, N = hidden): besides X += ..., writes the new rows once more as 16-bit operands to `x16_out`
+  //     (row pitch N) and, per row, kSsParts partial sums of squares to `ss_out` [M][kSsParts] (one per 128 columns);
+  //   consumer (EPI_QKV_ROPE, EPI_SWIGLU): `row_ss` [M][kSsParts] of its A rows -> every accumulator row is scaled by
+  //     rsqrt(sum / norm_dim + norm_eps) before the bias is added:  (x / rms) W'^T = (x W'^T) / rms.
+  void* x16_out;
+  float* ss_out;
+  const float* row_ss;
+  float norm_eps;
+  int norm_dim;
 };
+constexpr int kSsParts = 10;   // hidden 1280 = 10 x 128 columns
 
 // C = A[M,K] * B[N,K]^T with the chosen epilogue, enqueued on `stream`.
 int gemm(int epi, const GemmArgs& g, const void* a, int64_t lda, const void* b, int64_t ldb, void* stream);
@@ -38,6 +49,9 @@ int attention_tc(const void* qkv, const void* vt, int64_t s_pad, void* out, int6
 // V heads of qkv -> vt [(heads*head_dim)][s_pad] (s_pad = S rounded up to 8)
 int transpose_v(const void* qkv, void* vt, int64_t S, int64_t s_pad, int heads, int head_dim, void* stream);
 
+// fp32 (S, H) -> 16-bit copy (S, H) + per-row sum of squares in ss[row][0] (ss[row][1..kSsParts) = 0): the producer side
+// of the folded RMSNorm for rows that no residual GEMM has written yet (the patch-embed output)
+int cast_rows_ss(const float* x, void* x16, int x16_f16, float* ss, int64_t rows, int hidden, void* stream);
 // fp32 (S, H) -> bf16 (S, H): y = w * (x * rsqrt(mean(x^2) + eps))   (HF Qwen2_5_VLRMSNorm :66-71)
 int rmsnorm(const float* x, const float* w, void* y, int y_f16, int64_t rows, int hidden, float eps, void* stream);
 // patches in HF order (f32 or bf16) -> bf16 in window order (groups of `unit` rows move together)

@@ -4,13 +4,15 @@
 // Precision policy: residual stream X stays fp32; RMSNorm, rotary, softmax and every
 // accumulation are fp32; only GEMM / attention operands are rounded to bf16.
 //
-// Per block (HF :290-321):   Y = rmsnorm(X)            zv_tower.cu  rmsnorm_kernel
-//                            QKV = rope(Y Wqkv^T + b)   zv_gemm.cu   EPI_QKV_ROPE
-//                            A = attention(QKV)         zv_attn.cu
-//                            X += A Wo^T + b            zv_gemm.cu   EPI_RESID
-//                            Y = rmsnorm(X)
-//                            H = silu(Y Wg^T+b)*(Y Wu^T+b)            EPI_SWIGLU (gate/up rows interleaved)
-//                            X += H Wd^T + b                          EPI_RESID
+// Per block (HF :290-321), with both RMSNorms folded into the GEMMs around them - rmsnorm(x) W^T =
+// (x (W diag(g))^T) / rms(x): the gain g is multiplied into the weight columns at pack time, the residual GEMM that
+// produces x also emits x as 16-bit operands (X16) and per-row partial sums of squares (SS), and the consumer GEMM
+// scales its accumulator rows by 1/rms in the epilogue.  No separate norm pass reads X back from HBM.
+//                            QKV = rope((X16 Wqkv'^T) / rms + b)      zv_gemm.cu   EPI_QKV_ROPE
+//                            A = attention(QKV)                       zv_attn.cu / zv_attn_tc.cu
+//                            X += A Wo^T + b ; X16, SS                zv_gemm.cu   EPI_RESID
+//                            H = silu((X16 Wg'^T)/rms+b)*((X16 Wu'^T)/rms+b)       EPI_SWIGLU (gate/up rows interleaved)
+//                            X += H Wd^T + b ; X16, SS                             EPI_RESID
 // Merger (HF :133-146):      Z = rmsnorm(X) viewed (T, 4H); G = gelu(Z W1^T + b); out[widx[i]] = G W2^T + b.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -75,6 +77,27 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ 
   }
 }
 
+// One warp per row: 16-bit copy of the row + its sum of squares (producer side of the folded RMSNorm for the patch-embed
+// output, which no residual GEMM has touched yet).
+__global__ void __launch_bounds__(256) cast_rows_ss_kernel(const float* __restrict__ x, uint16_t* __restrict__ y, bool f16,
+                                                           float* __restrict__ ss, int64_t rows, int hidden) {
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * hidden);
+  uint2* yr = reinterpret_cast<uint2*>(y + row * hidden);
+  const int nv = hidden / 4;
+  float s = 0.f;
+  for (int idx = lane; idx < nv; idx += 32) {
+    const float4 v = xr[idx];
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    yr[idx] = make_uint2(pack2(v.x, v.y, f16), pack2(v.z, v.w, f16));
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane < kSsParts) ss[row * kSsParts + lane] = lane == 0 ? s : 0.f;
+}
+
 // dst group i (unit rows x cols, 16-bit operand type) <- src group widx[i] (f32, or already the operand type).
 template <typename SrcT>
 __global__ void __launch_bounds__(256) gather_kernel(const SrcT* __restrict__ src, uint16_t* __restrict__ dst, bool f16,
@@ -104,9 +127,10 @@ __global__ void __launch_bounds__(256) compose_rows_kernel(const int64_t* __rest
 
 // Weight import: dst[row_map(r)][c] = src[r][c] (to bf16 or f32).  mode 0 identity, 1 gate, 2 up
 // (gate/up rows interleaved in blocks of 128 so one 256-wide GEMM tile holds both halves of 128 outputs).
+// `colscale` (fp32 [cols], may be null): the RMSNorm gain folded into the weight columns.
 template <typename SrcT, typename DstT>
 __global__ void pack_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst, int64_t rows, int64_t cols,
-                            int64_t dst_ld, int mode) {
+                            int64_t dst_ld, int mode, const float* __restrict__ colscale) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * cols) return;
   const int64_t r = i / cols, c = i % cols;
@@ -117,6 +141,7 @@ __global__ void pack_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst
   if constexpr (std::is_same<SrcT, float>::value) v = src[i];
   else if constexpr (std::is_same<SrcT, __half>::value) v = __half2float(src[i]);
   else v = __bfloat162float(src[i]);
+  if (colscale) v *= colscale[c];
   if constexpr (std::is_same<DstT, float>::value) dst[dr * dst_ld + c] = v;
   else if constexpr (std::is_same<DstT, __half>::value) dst[dr * dst_ld + c] = __float2half_rn(v);
   else dst[dr * dst_ld + c] = __float2bfloat16_rn(v);
@@ -170,7 +195,8 @@ int check_device(const char* who) {
 }
 
 template <typename DstT>
-int pack_one(const zv_tensor* t, DstT* dst, int64_t rows, int64_t cols, int64_t dst_ld, int mode, cudaStream_t s) {
+int pack_one(const zv_tensor* t, DstT* dst, int64_t rows, int64_t cols, int64_t dst_ld, int mode, cudaStream_t s,
+             const float* colscale = nullptr) {
   int64_t numel = 1;
   for (int i = 0; i < t->ndim; ++i) numel *= t->shape[i];
   if (numel != rows * cols)
@@ -178,11 +204,11 @@ int pack_one(const zv_tensor* t, DstT* dst, int64_t rows, int64_t cols, int64_t 
                 (long long)rows, (long long)cols);
   const unsigned blocks = (unsigned)((numel + 255) / 256);
   if (t->dtype == ZV_F32)
-    pack_kernel<float, DstT><<<blocks, 256, 0, s>>>(static_cast<const float*>(t->data), dst, rows, cols, dst_ld, mode);
+    pack_kernel<float, DstT><<<blocks, 256, 0, s>>>(static_cast<const float*>(t->data), dst, rows, cols, dst_ld, mode, colscale);
   else if (t->dtype == ZV_BF16)
-    pack_kernel<__nv_bfloat16, DstT><<<blocks, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(t->data), dst, rows, cols, dst_ld, mode);
+    pack_kernel<__nv_bfloat16, DstT><<<blocks, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(t->data), dst, rows, cols, dst_ld, mode, colscale);
   else if (t->dtype == ZV_F16)
-    pack_kernel<__half, DstT><<<blocks, 256, 0, s>>>(static_cast<const __half*>(t->data), dst, rows, cols, dst_ld, mode);
+    pack_kernel<__half, DstT><<<blocks, 256, 0, s>>>(static_cast<const __half*>(t->data), dst, rows, cols, dst_ld, mode, colscale);
   else
     return fail(ZV_EINVAL, "zv_weights_pack: %s has unsupported dtype %d", t->name, t->dtype);
   count_launch();
@@ -197,6 +223,17 @@ int rmsnorm(const float* x, const float* w, void* y, int y_f16, int64_t rows, in
     KernelTimer timer(KC_RMSNORM, stream);
     rmsnorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         x, w, static_cast<uint16_t*>(y), y_f16 != 0, rows, hidden, eps);
+  }
+  count_launch();
+  return ZV_OK;
+}
+
+int cast_rows_ss(const float* x, void* x16, int x16_f16, float* ss, int64_t rows, int hidden, void* stream) {
+  if (hidden % 4) return fail(ZV_EINVAL, "cast_rows_ss: hidden=%d unsupported", hidden);
+  {
+    KernelTimer timer(KC_RMSNORM, stream);
+    cast_rows_ss_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, static_cast<uint16_t*>(x16), x16_f16 != 0, ss, rows, hidden);
   }
   count_launch();
   return ZV_OK;
@@ -265,28 +302,33 @@ int zv_weights_pack(const zv_cfg* cfg, const zv_tensor* tensors, int32_t n, void
   uint8_t* base = static_cast<uint8_t*>(packed_dev);
   const int64_t H = cfg->hidden, I = cfg->inter, IP = ipad(cfg), O = cfg->out_hidden;
   const bool f16 = cfg->op_dtype == ZV_F16;
-#define ZV_PACK(NAME, TYPE, OFF, ROWS, COLS, LD, MODE)                                                     \
+#define ZV_PACK_S(NAME, TYPE, OFF, ROWS, COLS, LD, MODE, SCALE)                                            \
   do {                                                                                                      \
     const zv_tensor* t_ = get(NAME);                                                                        \
     if (!t_) return fail(ZV_EINVAL, "zv_weights_pack: missing tensor %s", std::string(NAME).c_str());      \
     if (std::is_same<TYPE, __nv_bfloat16>::value && f16)                                                    \
-      rc = pack_one<__half>(t_, reinterpret_cast<__half*>(base + (OFF)), ROWS, COLS, LD, MODE, s);          \
+      rc = pack_one<__half>(t_, reinterpret_cast<__half*>(base + (OFF)), ROWS, COLS, LD, MODE, s, SCALE);   \
     else                                                                                                    \
-      rc = pack_one<TYPE>(t_, reinterpret_cast<TYPE*>(base + (OFF)), ROWS, COLS, LD, MODE, s);              \
+      rc = pack_one<TYPE>(t_, reinterpret_cast<TYPE*>(base + (OFF)), ROWS, COLS, LD, MODE, s, SCALE);       \
     if (rc) return rc;                                                                                      \
   } while (0)
+#define ZV_PACK(NAME, TYPE, OFF, ROWS, COLS, LD, MODE) ZV_PACK_S(NAME, TYPE, OFF, ROWS, COLS, LD, MODE, nullptr)
   ZV_PACK("patch_embed.proj.weight", __nv_bfloat16, L.wpe, H, kPatchK, kPatchK, 0);
   for (int l = 0; l < cfg->depth; ++l) {
     const std::string p = "blocks." + std::to_string(l) + ".";
     const LayerOff& o = L.layers[l];
     ZV_PACK(p + "norm1.weight", float, o.n1, 1, H, H, 0);
     ZV_PACK(p + "norm2.weight", float, o.n2, 1, H, H, 0);
-    ZV_PACK(p + "attn.qkv.weight", __nv_bfloat16, o.wqkv, 3 * H, H, H, 0);
+    // norm1 / norm2 gains (fp32, packed just above on the same stream) are folded into the columns of the GEMM that
+    // consumes the normalised rows: W' = W diag(g), rounded once to the operand type
+    const float* g1 = reinterpret_cast<const float*>(base + o.n1);
+    const float* g2 = reinterpret_cast<const float*>(base + o.n2);
+    ZV_PACK_S(p + "attn.qkv.weight", __nv_bfloat16, o.wqkv, 3 * H, H, H, 0, g1);
     ZV_PACK(p + "attn.qkv.bias", float, o.bqkv, 1, 3 * H, 3 * H, 0);
     ZV_PACK(p + "attn.proj.weight", __nv_bfloat16, o.wo, H, H, H, 0);
     ZV_PACK(p + "attn.proj.bias", float, o.bo, 1, H, H, 0);
-    ZV_PACK(p + "mlp.gate_proj.weight", __nv_bfloat16, o.wgu, I, H, H, 1);
-    ZV_PACK(p + "mlp.up_proj.weight", __nv_bfloat16, o.wgu, I, H, H, 2);
+    ZV_PACK_S(p + "mlp.gate_proj.weight", __nv_bfloat16, o.wgu, I, H, H, 1, g2);
+    ZV_PACK_S(p + "mlp.up_proj.weight", __nv_bfloat16, o.wgu, I, H, H, 2, g2);
     ZV_PACK(p + "mlp.gate_proj.bias", float, o.bgu, I, 1, 1, 1);
     ZV_PACK(p + "mlp.up_proj.bias", float, o.bgu, I, 1, 1, 2);
     ZV_PACK(p + "mlp.down_proj.weight", __nv_bfloat16, o.wd, H, I, IP, 0);
@@ -298,13 +340,14 @@ int zv_weights_pack(const zv_cfg* cfg, const zv_tensor* tensors, int32_t n, void
   ZV_PACK("merger.mlp.2.weight", __nv_bfloat16, L.w2, O, 4 * H, 4 * H, 0);
   ZV_PACK("merger.mlp.2.bias", float, L.b2, 1, O, O, 0);
 #undef ZV_PACK
+#undef ZV_PACK_S
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(ZV_ECUDA, "zv_weights_pack: %s", cudaGetErrorString(e));
   return ZV_OK;
 }
 
 namespace {
-struct Workspace { int64_t p = 0, x = 0, y = 0, big = 0, vt = 0, comp = 0, s_pad = 0, bytes = 0; };
+struct Workspace { int64_t p = 0, x = 0, y = 0, x16 = 0, ss = 0, big = 0, vt = 0, comp = 0, s_pad = 0, bytes = 0; };
 Workspace workspace_layout(const zv_cfg* c, int64_t S) {
   Workspace w;
   const int64_t H = c->hidden;
@@ -314,6 +357,8 @@ Workspace workspace_layout(const zv_cfg* c, int64_t S) {
   w.p = take(S * kPatchK * 2);
   w.x = take(S * H * 4);
   w.y = take(S * H * 2);
+  w.x16 = take(S * H * 2);               // 16-bit copy of the residual stream (A operand of the QKV / gate-up GEMMs)
+  w.ss = take(S * kSsParts * 4);         // per-row partial sums of squares of X (folded RMSNorm)
   w.big = take(S * wide * 2);
   w.s_pad = (S + 7) / 8 * 8;
   w.vt = take(w.s_pad * H * 2);          // V^T per head for the tcgen05 full-attention kernel
@@ -417,15 +462,18 @@ int visual_forward_impl(const zv_cfg* cfg, const void* weights_dev, const zv_pla
   g.M = (int)S; g.N = (int)H; g.K = kPatchK; g.out = X; g.ldo = H; g.out_dtype = ZV_F32; g.bias = nullptr;
   ZV_TRY(gemm(EPI_STORE, g, P, kPatchK, wb + L.wpe, kPatchK, stream));
 
+  void* X16 = ws + W.x16;
+  float* SS = reinterpret_cast<float*>(ws + W.ss);
+  ZV_TRY(cast_rows_ss(X, X16, f16, SS, S, (int)H, stream));
   for (int l = 0; l < cfg->depth; ++l) {
     const LayerOff& o = L.layers[l];
     const bool full = (cfg->fullatt_mask_lo >> l) & 1;
-    ZV_TRY(rmsnorm(X, reinterpret_cast<const float*>(wb + o.n1), Y, f16, S, (int)H, cfg->eps, stream));
     g = GemmArgs{};
     g.op_f16 = f16;
     g.M = (int)S; g.N = (int)(3 * H); g.K = (int)H; g.out = BIG; g.ldo = 3 * H; g.out_dtype = op;
     g.bias = reinterpret_cast<const float*>(wb + o.bqkv); g.pos = d_pos; g.rope = d_rope; g.heads = cfg->heads;
-    ZV_TRY(gemm(EPI_QKV_ROPE, g, Y, H, wb + o.wqkv, H, stream));
+    g.row_ss = SS; g.norm_eps = cfg->eps; g.norm_dim = (int)H;               // norm1 (gain folded into Wqkv)
+    ZV_TRY(gemm(EPI_QKV_ROPE, g, X16, H, wb + o.wqkv, H, stream));
     if (full && !legacy_full) {
       ZV_TRY(transpose_v(BIG, ws + W.vt, S, W.s_pad, cfg->heads, (int)(H / cfg->heads), stream));
       ZV_TRY(attention_tc(BIG, ws + W.vt, W.s_pad, Y, S, cfg->heads, (int)(H / cfg->heads), d_full, p->n_full_tiles, stream, f16 != 0));
@@ -436,17 +484,19 @@ int visual_forward_impl(const zv_cfg* cfg, const void* weights_dev, const zv_pla
     g.op_f16 = f16;
     g.M = (int)S; g.N = (int)H; g.K = (int)H; g.out = X; g.ldo = H; g.out_dtype = ZV_F32;
     g.bias = reinterpret_cast<const float*>(wb + o.bo);
+    g.x16_out = X16; g.ss_out = SS;
     ZV_TRY(gemm(EPI_RESID, g, Y, H, wb + o.wo, H, stream));
-    ZV_TRY(rmsnorm(X, reinterpret_cast<const float*>(wb + o.n2), Y, f16, S, (int)H, cfg->eps, stream));
     g = GemmArgs{};
     g.op_f16 = f16;
     g.M = (int)S; g.N = (int)(2 * IP); g.K = (int)H; g.out = BIG; g.ldo = IP; g.out_dtype = op;
     g.bias = reinterpret_cast<const float*>(wb + o.bgu);
-    ZV_TRY(gemm(EPI_SWIGLU, g, Y, H, wb + o.wgu, H, stream));
+    g.row_ss = SS; g.norm_eps = cfg->eps; g.norm_dim = (int)H;               // norm2 (gain folded into Wgate / Wup)
+    ZV_TRY(gemm(EPI_SWIGLU, g, X16, H, wb + o.wgu, H, stream));
     g = GemmArgs{};
     g.op_f16 = f16;
     g.M = (int)S; g.N = (int)H; g.K = (int)IP; g.out = X; g.ldo = H; g.out_dtype = ZV_F32;
     g.bias = reinterpret_cast<const float*>(wb + o.bd);
+    if (l + 1 < cfg->depth) { g.x16_out = X16; g.ss_out = SS; }                // the merger normalises in fp32 itself
     ZV_TRY(gemm(EPI_RESID, g, BIG, IP, wb + o.wd, IP, stream));
   }
   if (hidden_out_dev) {
