@@ -206,3 +206,20 @@ def test_fused_peer_gather_equals_nccl_two_gpus():
                         "--master-addr", "127.0.0.1", "--master-port", "29561", os.path.join(root, "tools", "multi_gpu_check.py")],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and r.stdout.count("fused gather == nccl all_gather: True") == 2, r.stdout + r.stderr
+
+
+def test_encode_batched_equals_one_batch(cuda):
+    """Micro-batching a ragged crop list (bounded workspace) changes nothing: every crop is an independent sequence and
+    every GEMM row depends on its own A row only, so the embeddings are bitwise those of the single ragged batch."""
+    from zoomearth_b200 import synthetic
+    cfg = OT.small_cfg(depth=2, fullatt=(1,))
+    sd = OT.make_weights(17, cfg)
+    enc = _encoder(cuda, cfg, sd, 401408, operand_dtype=torch.bfloat16)
+    imgs = [np.random.default_rng(70 + i).integers(0, 256, (1600, 1600, 3), dtype=np.uint8) for i in range(2)]
+    dev = [enc.upload(i) for i in imgs]
+    boxes, index = synthetic.mixed_crop_boxes(9, n_images=2, img=1600, lo=200, hi=1200, seed=3)
+    whole, grid, crop = enc.encode(dev, boxes, image_index=index)
+    parts, grid2, crop2 = enc.encode_batched(dev, boxes, index, max_patches=1500)
+    assert len(enc.micro_batches(dev, boxes, index, max_patches=1500)) > 2
+    assert grid.tolist() == grid2.tolist() and np.array_equal(crop, crop2)
+    assert torch.equal(whole, parts)

@@ -184,3 +184,23 @@ def test_processor_host_surface(lib):
     assert fp.get_number_of_image_patches(5000, 5000, {"max_pixels": 1003520}) == 4900
     fp.max_pixels = 1003520
     assert fp.size["longest_edge"] == 1003520 and fp.min_pixels == 3136
+
+
+def test_micro_batches_split_a_ragged_crop_list_by_patch_budget():
+    """ZoomEncoder.micro_batches: host-only planning (geometry through the C ABI), no GPU involved."""
+    import types
+    import numpy as np
+    import torch
+    from zoomearth_b200.processor import FusedImageProcessor
+    from zoomearth_b200.zoom import ZoomEncoder
+    enc = ZoomEncoder.__new__(ZoomEncoder)
+    enc.processor = FusedImageProcessor(min_pixels=3136, max_pixels=12845056)
+    enc.visual = types.SimpleNamespace()
+    imgs = [torch.empty((5000, 5000, 3), dtype=torch.uint8, device="meta")]
+    boxes = [(0, 0, 512, 512), (0, 0, 2048, 2048), (100, 100, 400, 300), (0, 0, 5000, 5000), (10, 10, 1034, 1034)]
+    patches = [1296, 21316, 1296, 64516, 5476]                    # SURVEY 8 table; the 300x200 box becomes 512x512
+    groups = enc.micro_batches(imgs, boxes, [0] * 5, max_patches=25000)
+    assert groups == [[0, 1, 2], [3], [4]]                        # consecutive, in order; an oversize crop stands alone
+    assert [sum(patches[i] for i in g) for g in groups] == [23908, 64516, 5476]
+    assert enc.micro_batches(imgs, boxes, [0] * 5, max_patches=10 ** 9) == [[0, 1, 2, 3, 4]]
+    assert enc.micro_batches(imgs, None) == [[0]]                  # global view of every image
