@@ -209,8 +209,9 @@ def test_fused_peer_gather_equals_nccl_two_gpus():
 
 
 def test_encode_batched_equals_one_batch(cuda):
-    """Micro-batching a ragged crop list (bounded workspace) changes nothing: every crop is an independent sequence and
-    every GEMM row depends on its own A row only, so the embeddings are bitwise those of the single ragged batch."""
+    """Micro-batching a ragged crop list (bounded workspace) changes nothing but rounding: every crop is an independent
+    sequence (only the position of a segment inside its batch moves the KV tile boundaries of the full-attention
+    layers, i.e. the order of the fp32 sums)."""
     from zoomearth_b200 import synthetic
     cfg = OT.small_cfg(depth=2, fullatt=(1,))
     sd = OT.make_weights(17, cfg)
@@ -221,5 +222,6 @@ def test_encode_batched_equals_one_batch(cuda):
     whole, grid, crop = enc.encode(dev, boxes, image_index=index)
     parts, grid2, crop2 = enc.encode_batched(dev, boxes, index, max_patches=1500)
     assert len(enc.micro_batches(dev, boxes, index, max_patches=1500)) > 2
-    assert grid.tolist() == grid2.tolist() and np.array_equal(crop, crop2)
-    assert torch.equal(whole, parts)
+    assert grid.tolist() == grid2.tolist() and np.array_equal(crop, crop2) and parts.shape == whole.shape
+    cos, maxrel = _metrics(parts, whole)
+    assert cos >= 0.9999 and maxrel <= 5e-3, f"cos {cos} maxrel {maxrel}"
