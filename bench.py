@@ -176,9 +176,13 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    stdout_fd = None
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
+        # NCCL prints its version banner to stdout at communicator creation: keep stdout to the one JSON line by
+        # pointing fd 1 at stderr until the line is printed
+        sys.stdout.flush()
+        stdout_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.lib()
     n_img = args.images
@@ -341,7 +345,10 @@ def run_ours(args):
             "kernel_ms": {k: round(v[0] / args.steps, 3) for k, v in cls.items()},
             "cpu_baseline": cpu_base,
         }
-        print(json.dumps(line))
+        if stdout_fd is not None:
+            sys.stdout.flush()
+            os.dup2(stdout_fd, 1)
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

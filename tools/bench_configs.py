@@ -55,8 +55,11 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    stdout_fd = None
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        sys.stdout.flush()
+        stdout_fd = os.dup(1)                      # NCCL's version banner goes to stdout: park fd 1 on stderr meanwhile
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.lib()
     visual = FusedVisual(synthetic.random_vision_state_dict(0, device=dev), device=dev, dtype=torch.bfloat16)
@@ -147,6 +150,10 @@ def main():
                                                               int(tokens / len(boxes)),
                                                               int((grid_all[:, 1] * grid_all[:, 2]).max() // 4)]})
         if rank == 0:
+            if stdout_fd is not None:
+                sys.stdout.flush()
+                os.dup2(stdout_fd, 1)
+                stdout_fd = None
             print(json.dumps({
                 "workload": what, "n_gpus": world, "tokens": tot_tokens, "ms": round(tot_ms, 2),
                 "tokens_per_s": tot_tokens / tot_ms * 1e3,
