@@ -38,7 +38,7 @@ MAX_PIXELS = 1280 * 28 * 28
 MIN_PIXELS = 56 * 56
 # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the four per-block GEMMs at this exact
 # workload (64 images, M = 313 600), from the ncu capture committed as profiles/r01_ncu_traffic_gemm_64img.csv
-NCU_TRAFFIC_GB = {"gemm_qkv": 3.77, "gemm_proj": 4.23, "gemm_swiglu": 3.42, "gemm_down": 6.82}
+NCU_TRAFFIC_GB = {"gemm_qkv": 3.20, "gemm_proj": 4.97, "gemm_swiglu": 3.23, "gemm_down": 6.86}
 # DRAM bytes per image of k1_hpass_fast<7> + k1_vpass_fast<7> (ncu, 8-image launch, profiles/r01_ncu_k1_summary.txt):
 # (608.8 + 108.3 + 118.0 + 53.8) MB / 8; algorithmic 86.52 MB - the uint8 intermediate (14.7 MB/image) makes one round trip
 NCU_K1_TRAFFIC_PER_IMAGE = 111.1e6
@@ -328,7 +328,8 @@ def run_ours(args):
                          "frac_of_burst": gemm_tf / pk["tf_burst"], "peak_source": pk["src"] + ", sustained",
                          "traffic": (sum(NCU_TRAFFIC_GB.values()) * 32 / 128 * 1e9) if n_img == 64 else None,
                          "traffic_note": "mean DRAM bytes per launch over the 128 per-block GEMM launches, ncu at this "
-                                         "workload (profiles/r01_ncu_traffic_gemm_64img.csv); algorithmic mean 3.9e9",
+                                         "workload (profiles/r01_ncu_traffic_gemm_64img.csv); algorithmic mean 4.3e9 (A + W + out, + X read-modify-write and the "
+                                         "16-bit copy for the residual GEMMs)",
                          "launches": gemm_n, "ms_total": gemm_ms, "share_of_step": gemm_ms / ms},
             "roofline_k1": {"bound": "hbm", "kernel": "k1_hpass + k1_vpass", "achieved": k1_gbs, "peak": pk["hbm"],
                             "unit": "GB/s", "frac": k1_gbs / pk["hbm"], "ms_total": k1_ms, "share_of_step": k1_ms / ms,
