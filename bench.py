@@ -348,6 +348,7 @@ def run_ours(args):
         }
         if stdout_fd is not None:
             sys.stdout.flush()
+            C.CDLL(None).fflush(None)           # NCCL's banner may still sit in the C stdio buffer of stdout
             os.dup2(stdout_fd, 1)
         print(json.dumps(line), flush=True)
     if world > 1:

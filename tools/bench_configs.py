@@ -152,6 +152,7 @@ def main():
         if rank == 0:
             if stdout_fd is not None:
                 sys.stdout.flush()
+                C.CDLL(None).fflush(None)       # NCCL's banner may still sit in the C stdio buffer of stdout
                 os.dup2(stdout_fd, 1)
                 stdout_fd = None
             print(json.dumps({

@@ -12,9 +12,10 @@ python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit 
 timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"; tail -3 gpurun_out/bench.err
 python -c "
 import json; d=json.load(open('gpurun_out/bench.json')); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['clocks'], d['kernel_ms'], d['roofline']['frac'], d['roofline_k1']['frac'], d['cpu_baseline'])"
+python tools/latency.py > gpurun_out/latency.json 2> gpurun_out/latency.err; echo "latency exit $?"
 python tools/bench_configs.py --config 3 4 5 > gpurun_out/configs_n1.jsonl 2> gpurun_out/configs_n1.err; echo "configs exit $?"
 if [ "${NCU:-1}" = "1" ]; then
-  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"gemm_tc|attn_|k1_|rmsnorm|transpose_v|gather|compose" -s 702 -c 234 --csv --log-file gpurun_out/launches.csv \
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"gemm_tc|attn_|k1_|rmsnorm|transpose_v|gather|compose|cast_rows" -s 513 -c 171 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --images 8 > gpurun_out/ncu_list.log 2>&1; echo "ncu list exit $?"
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:"attn_tc_kernel" -s 4 -c 1 -o gpurun_out/prof_attn_tc -f \
     python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --images 8 > gpurun_out/ncu_attn.log 2>&1; echo "ncu attn_tc exit $?"
