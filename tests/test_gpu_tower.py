@@ -60,6 +60,7 @@ def test_tower_full_depth_fp16_operands_vs_oracle(cuda, full_depth_case):
     out = fv(pv.to(cuda), torch.from_numpy(grid))
     assert out.dtype == torch.float16 and out.shape == (ref.shape[0], 2048)
     cos, maxrel = _metrics(out, ref)
+    print(f"PARITY full tower, fp16 operands vs fp32 oracle: cosine {cos:.6f}, max rel err {maxrel:.3e}")
     assert cos >= 0.999 and maxrel <= 1e-2, f"cos {cos} maxrel {maxrel}"
     assert maxrel <= 5e-3, f"fp16 operands should sit near 2.5e-3, got {maxrel}"
 
@@ -73,6 +74,7 @@ def test_tower_full_depth_bf16_operands_vs_oracle(cuda, full_depth_case):
     out = fv(pv.to(cuda), torch.from_numpy(grid))
     assert out.dtype == torch.bfloat16
     cos, maxrel = _metrics(out, ref)
+    print(f"PARITY full tower, bf16 operands vs fp32 oracle: cosine {cos:.6f}, max rel err {maxrel:.3e}")
     assert cos >= 0.999 and maxrel <= 1.5e-2, f"cos {cos} maxrel {maxrel}"
 
 

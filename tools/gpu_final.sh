@@ -5,9 +5,10 @@ mkdir -p gpurun_out
 rc=0
 for f in tests/test_gpu_gemm.py tests/test_gpu_k1.py tests/test_gpu_attn.py tests/test_gpu_tower.py tests/test_gpu_configs.py tests/test_gpu_handoff.py; do
   n=$(basename $f .py)
-  timeout 600 python -m pytest $f -q -m gpu --timeout 300 -p no:cacheprovider > gpurun_out/$n.log 2>&1
+  timeout 600 python -m pytest $f -q -s -m gpu --timeout 300 -p no:cacheprovider > gpurun_out/$n.log 2>&1
   r=$?; echo "== $f exit $r: $(tail -n 1 gpurun_out/$n.log)"; [ $r -ne 0 ] && rc=1
 done
+grep -h PARITY gpurun_out/test_gpu_*.log > gpurun_out/parity.txt; cat gpurun_out/parity.txt
 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit $?"; tail -1 gpurun_out/smoke.log
 timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"; tail -3 gpurun_out/bench.err
 python -c "
