@@ -101,7 +101,8 @@ __device__ __forceinline__ uint32_t pack4_sat(int v0, int v1, int v2, int v3) {
 // Position of merge group (my, mx) in the tower's window order (closed form of argsort(window_index),
 // HF modeling_qwen2_5_vl.py:411-451): windows of ws x ws merge groups, row-major over windows, row-major inside.
 __device__ __forceinline__ int window_pos(int my, int mx, int lh, int lw, int ws) {
-  const int wy = my / ws, wx = mx / ws;
+  // ws = 4 for every Qwen2.5-VL tower (window 112 / merge 2 / patch 14): shifts instead of two runtime divisions
+  const int wy = ws == 4 ? my >> 2 : my / ws, wx = ws == 4 ? mx >> 2 : mx / ws;
   const int bh = min(ws, lh - wy * ws), bw = min(ws, lw - wx * ws);
   return wy * ws * lw + wx * ws * bh + (my - wy * ws) * bw + (mx - wx * ws);
 }
@@ -389,11 +390,11 @@ __global__ void __launch_bounds__(256) k1_vpass_fast(const K1Crop* __restrict__ 
       const int chunks = (min(2, lw - mx0) * 84) >> 2;                   // 16-byte chunks per quad row (21 or 42)
       const uint32_t* __restrict__ g = tmp + (int64_t)q_lo * qpitch + mx0 * 84;
       uint32_t* t = tile + buf * tile_quads_max * 168;
-      for (int i = threadIdx.x; i < nq * chunks; i += blockDim.x) {
-        const int r = i / chunks, ck = i - r * chunks;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(t + r * 168 + ck * 4)),
-                     "l"(g + (int64_t)r * qpitch + ck * 4) : "memory");
-      }
+      const int ck = threadIdx.x & 63;                                   // 64 threads per quad row, 4 rows per sweep
+      if (ck < chunks)
+        for (int r = threadIdx.x >> 6; r < nq; r += 4)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(t + r * 168 + ck * 4)),
+                       "l"(g + (int64_t)r * qpitch + ck * 4) : "memory");
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
