@@ -49,8 +49,9 @@ template <int BN, int CG, int EPI = 0> struct Cfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   // the residual epilogue transposes its tile through shared memory (8 warps x 4.5 KB): one pipeline stage less
   // ... and the QKV epilogue keeps each row's rotary (cos, sin) pairs and a 32 x 80 output tile per lane quarter there
-  static constexpr int kXposeBytes = EPI == EPI_RESID ? 8 * kXposeBytesPerWarp : EPI == EPI_QKV_ROPE ? kQkvStageBytes : 0;
-  static constexpr int kStages = ((kBRows > 128) ? 4 : 6) - ((EPI == EPI_RESID || EPI == EPI_QKV_ROPE) ? 1 : 0);
+  // ... and the scatter epilogue regroups its 16-bit rows there so that four lanes store 64 contiguous bytes of a row
+  static constexpr int kXposeBytes = (EPI == EPI_RESID || EPI == EPI_SCATTER) ? 8 * kXposeBytesPerWarp : EPI == EPI_QKV_ROPE ? kQkvStageBytes : 0;
+  static constexpr int kStages = ((kBRows > 128) ? 4 : 6) - ((EPI == EPI_RESID || EPI == EPI_QKV_ROPE || EPI == EPI_SCATTER) ? 1 : 0);
   static constexpr int kBarBytes = 256;
   static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kXposeBytes + 1024;   // +1024: manual alignment slack
 };
@@ -219,18 +220,38 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int m_blk, int n_b
           for (int j = 0; j < 4; ++j)
             pk[j] = make_uint4(pack2(v[8 * j], v[8 * j + 1], of16), pack2(v[8 * j + 2], v[8 * j + 3], of16),
                                pack2(v[8 * j + 4], v[8 * j + 5], of16), pack2(v[8 * j + 6], v[8 * j + 7], of16));
-          uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(g.out) + orow * g.ldo + n0);
+          if constexpr (EPI != EPI_SCATTER) {
+            uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(g.out) + orow * g.ldo + n0);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) o[j] = pk[j];
-          if constexpr (EPI == EPI_SCATTER) {
-            // fused embedding gather: the same 64 bytes go straight into every peer's gather buffer (P2P stores over
-            // NVLink / NVSwitch), so the transfer rides along with the GEMM tile by tile instead of a collective after it
-            for (int p = 0; p < g.n_peers; ++p) {
-              uint4* po = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(g.peers[p]) + (g.peer_row_off + orow) * g.ldo + n0);
+            for (int j = 0; j < 4; ++j) o[j] = pk[j];
+          } else {
+            // this row's 64 bytes -> the warp's staging tile (row pitch 80 B: conflict-free 16-byte accesses)
+            uint4* st = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(xpose) + (row_local & 31) * 80);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) po[j] = pk[j];
+            for (int j = 0; j < 4; ++j) st[j] = pk[j];
+          }
+        }
+      }
+      if constexpr (EPI == EPI_SCATTER) {
+        if (g.out_dtype != ZV_F32) {
+          // Scattered 16-bit rows leave in 64-byte runs: four lanes per row, eight rows per store instruction, instead
+          // of 32 lanes x 16 bytes of 32 different rows.  The same runs go straight into every peer's gather buffer
+          // (P2P stores over NVLink / NVSwitch) - the fused embedding gather - where small scattered stores cost most.
+          __syncwarp();
+          const int ln = row_local & 31, piece = ln & 3;
+          const int row_base = m_blk * BM + (row_local & ~31);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rw = 8 * i + (ln >> 2);
+            if (row_base + rw < g.M) {
+              const int64_t dr = (int64_t)__ldg(g.scatter + row_base + rw);
+              const uint4 val = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(xpose) + rw * 80 + piece * 16);
+              *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(g.out) + dr * g.ldo + n0 + piece * 8) = val;
+              for (int p = 0; p < g.n_peers; ++p)
+                *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(g.peers[p]) + (g.peer_row_off + dr) * g.ldo + n0 + piece * 8) = val;
             }
           }
+          __syncwarp();
         }
       }
       if constexpr (EPI == EPI_RESID) {
@@ -501,7 +522,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc(const __grid_constant__ C
   } else if (warp >= 4) {
     const int q = warp & 3, half = (warp - 4) >> 2;
     float* xpose = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes + C::kBarBytes) +
-                   (EPI == EPI_RESID ? (warp - 4) * (kXposeBytesPerWarp / 4) : 0);   // RESID: per-warp area; QKV: the CTA's area
+                   ((EPI == EPI_RESID || EPI == EPI_SCATTER) ? (warp - 4) * (kXposeBytesPerWarp / 4) : 0);   // per-warp area; QKV: the CTA's area
     int it = 0;
     for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
       const int m_blk = (tile / n_blocks) * CG + (int)rank, n_blk = tile % n_blocks;
