@@ -184,7 +184,8 @@ ZV_API int64_t zv_last_launch_count(void);
 
 /* Optional per-kernel-class device timing (CUDA events on the launching stream around every launch of that
  * class).  Classes: 0 k1 hpass, 1 k1 vpass, 2 gemm store, 3 gemm qkv+rope, 4 gemm residual, 5 gemm swiglu,
- * 6 gemm gelu, 7 gemm scatter, 8 attention (window layers), 9 attention (full layers), 10 rmsnorm, 11 gather. */
+ * 6 gemm gelu, 7 gemm scatter, 8 attention (window layers), 9 attention (full layers), 10 rmsnorm + cast_rows_ss,
+ * 11 gather. */
 ZV_API void zv_timing_enable(int on);
 ZV_API void zv_timing_reset(void);
 ZV_API int zv_timing_read(int kernel_class, double* ms_total, int64_t* count);
