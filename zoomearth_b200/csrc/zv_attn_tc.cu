@@ -38,7 +38,7 @@ namespace zv {
 using namespace ptx;
 namespace {
 
-constexpr int HD = 80, BQ = 128, BKV = 64, STAGES = 3, kCtasPerSm = 2;
+constexpr int HD = 80, BQ = 128, BKV = 64, STAGES = 4, kCtasPerSm = 2;
 constexpr int kRowV = BKV * 2;                                            // bytes per V^T row in smem (128: 128B swizzle)
 constexpr int kK64 = BKV * 64 * 2, kK16 = BKV * 16 * 2, kVt = HD * kRowV;   // 8192, 2048, 10240
 constexpr int kStage = kK64 + kK16 + kVt;                                // 20480
@@ -51,6 +51,7 @@ constexpr uint32_t kSw128 = 2, kSw32 = 6;                                // UMMA
 static_assert(BKV == 64, "the V^T tiles are laid out for 128-byte rows (BKV = 64)");
 static_assert(kStage % 1024 == 0 && (kK64 + kK16) % 1024 == 0 && kK64 % 1024 == 0, "swizzle atom alignment");
 static_assert(kQCol + HD / 2 <= kTmemCols, "TMEM budget");
+static_assert(STAGES <= 4, "mbarrier slots");
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = 0;
@@ -130,15 +131,15 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) attn_tc_kernel(const __g
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t* q_full = bars;             // Q parked in TMEM (4 softmax warps)
-  uint64_t* k_full = bars + 1;         // STAGES (<= 3)
-  uint64_t* v_full = bars + 4;
-  uint64_t* k_empty = bars + 7;
-  uint64_t* v_empty = bars + 10;
-  uint64_t* s_full = bars + 13;
-  uint64_t* s_empty = bars + 14;
-  uint64_t* p_full = bars + 15;
-  uint64_t* pv_done = bars + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* k_full = bars + 1;         // STAGES (<= 4)
+  uint64_t* v_full = bars + 5;
+  uint64_t* k_empty = bars + 9;
+  uint64_t* v_empty = bars + 13;
+  uint64_t* s_full = bars + 17;
+  uint64_t* s_empty = bars + 18;
+  uint64_t* p_full = bars + 19;
+  uint64_t* pv_done = bars + 20;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
 
   // the pair shares K/V when both q tiles exist and belong to the same segment; otherwise each CTA loads privately
   const uint32_t rank = cluster_ctarank();
