@@ -9,14 +9,15 @@
 //                   Q K_{j+1}^T while the exponentials run
 //   softmax         four warps, one thread per q row: tcgen05.ld of the row, online max/sum in fp32 with exp2,
 //                   P_j rounded to 16 bit and written back to TMEM (tcgen05.st, two values per column)
-//   O += P_j V_j    tcgen05.mma M=128 N=80 K=64, A = P (TMEM), B = V^T (smem, kv contiguous: V is pre-transposed per
-//                   head by transpose_v so that the B operand is K-major); O stays in TMEM for the whole segment and
-//                   is rescaled lazily (only when the row max grows by more than 2^8).
+//   O += P_j V_j    tcgen05.mma M=128 K=64, A = P (TMEM), B = V_j straight from the V rows of qkv as an MN-major
+//                   operand (head dim contiguous; the same 64 + 16 column TMA boxes as K, one N = 64 and one N = 16
+//                   MMA per K step): no transposed copy of V exists.  O stays in TMEM for the whole segment and is
+//                   rescaled lazily (only when the row max grows by more than 2^8).
 // Why TMEM operands: with A read from shared memory every K=16 step streams 4 KB of Q or P next to 1-3 KB of K/V and the
 // tensor pipe sat at 80 % busy on operand fetch alone (ncu sm__pipe_tc_cycles_active) while doing 40 % of its math rate;
-// with A in TMEM only the B tiles cross the shared-memory port.
+// with A in TMEM only the K and V tiles cross the shared-memory port.
 // K/V traffic: every q tile of a head streams the head's whole K and V.  CTAs run as clusters of two neighbouring q
-// tiles of the same head: each CTA fetches half of every K / V^T tile and TMA-multicasts it into both CTAs' shared
+// tiles of the same head: each CTA fetches half of every K / V tile and TMA-multicasts it into both CTAs' shared
 // memory, which halves the L2 reads; a stage is recycled when BOTH tensor cores are done with it (multicast
 // tcgen05.commit).  Pairs that straddle a segment boundary (or the odd last tile) fall back to private loads.
 // Warp roles (192 threads): warp 0 = TMA producer + TMEM allocator, warp 1 = MMA issuer, warps 2-5 = softmax
@@ -39,16 +40,14 @@ using namespace ptx;
 namespace {
 
 constexpr int HD = 80, BQ = 128, BKV = 64, STAGES = 4, kCtasPerSm = 2;
-constexpr int kRowV = BKV * 2;                                            // bytes per V^T row in smem (128: 128B swizzle)
-constexpr int kK64 = BKV * 64 * 2, kK16 = BKV * 16 * 2, kVt = HD * kRowV;   // 8192, 2048, 10240
-constexpr int kStage = kK64 + kK16 + kVt;                                // 20480
+constexpr int kK64 = BKV * 64 * 2, kK16 = BKV * 16 * 2;                   // 8192, 2048: [rows][64] and [rows][16] blocks
+constexpr int kStage = 2 * (kK64 + kK16);                                // 20480: K and V tiles have the same shape
 constexpr int kOffBar = STAGES * kStage;
 constexpr int kSmem = kOffBar + 256 + 1024;
 // TMEM columns: S [0,64)  O [64,144)  P [144,176) 16-bit pairs  Q [176,216) 16-bit pairs
 constexpr int kTmemCols = 256, kOCol = BKV, kPCol = kOCol + HD, kQCol = kPCol + BKV / 2;
 constexpr int kThreads = 192;
 constexpr uint32_t kSw128 = 2, kSw32 = 6;                                // UMMA descriptor layout types
-static_assert(BKV == 64, "the V^T tiles are laid out for 128-byte rows (BKV = 64)");
 static_assert(kStage % 1024 == 0 && (kK64 + kK16) % 1024 == 0 && kK64 % 1024 == 0, "swizzle atom alignment");
 static_assert(kQCol + HD / 2 <= kTmemCols, "TMEM budget");
 static_assert(STAGES <= 4, "mbarrier slots");
@@ -125,8 +124,7 @@ struct AttnArgs {
 
 template <bool F16>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k64,
-                                                                       const __grid_constant__ CUtensorMap tm_k16,
-                                                                       const __grid_constant__ CUtensorMap tm_vt, const AttnArgs a) {
+                                                                       const __grid_constant__ CUtensorMap tm_k16, const AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
@@ -157,14 +155,13 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) attn_tc_kernel(const __g
     shared_kv = to.z == seg_b && to.w == seg_e;
   }
   const int head = blockIdx.y;
-  // K/V tiles start at the segment start rounded down to 8 rows: the V^T tile's inner TMA coordinate must be
-  // 16-byte aligned.  Columns before seg_b (first tile) and from seg_e on (last tile) are masked in the softmax.
-  const int kv_base = seg_b & ~7;
+  // K/V tiles start at the segment start; columns from seg_e on (last tile) are masked in the softmax.
+  const int kv_base = seg_b;
   const int n_kv = (seg_e - kv_base + BKV - 1) / BKV;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    prefetch_tensormap(&tm_k64); prefetch_tensormap(&tm_k16); prefetch_tensormap(&tm_vt);
+    prefetch_tensormap(&tm_k64); prefetch_tensormap(&tm_k16);
     mbar_init(q_full, 4);
     const int users = shared_kv ? 2 : 1;          // tensor cores that must be done with a stage before it is refilled
     for (int s = 0; s < STAGES; ++s) { mbar_init(k_full + s, 1); mbar_init(v_full + s, 1); mbar_init(k_empty + s, users); mbar_init(v_empty + s, users); }
@@ -180,8 +177,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) attn_tc_kernel(const __g
 
   if (warp == 0) {
     if (elect_one()) {
-      // ---- TMA producer: the K / V^T ring.  Boxes are half tiles (32 K rows, 40 V^T rows): in a sharing pair CTA
-      // `rank` fetches half `rank` and multicasts it to both CTAs; a private CTA fetches both halves itself.
+      // ---- TMA producer: the K / V ring.  Boxes are half tiles (32 rows): in a sharing pair CTA `rank` fetches half
+      // `rank` and multicasts it to both CTAs; a private CTA fetches both halves itself.
       const int colk = a.hidden + head * HD;
       for (int j = 0; j < n_kv; ++j) {
         const int st = j % STAGES;
@@ -200,14 +197,20 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) attn_tc_kernel(const __g
             tma_load_2d(sk + kK64 + h * (kK16 / 2), &tm_k16, k_full + st, colk + 64, row + h * (BKV / 2));
           }
         }
+        // V rows [kv][hd] exactly as they lie in qkv: the P V product reads them as an MN-major B operand
+        const int colv = 2 * a.hidden + head * HD;
+        uint8_t* sv = sk + kK64 + kK16;
         mbar_wait(v_empty + st, ph ^ 1);
-        mbar_arrive_expect_tx(v_full + st, kVt);
+        mbar_arrive_expect_tx(v_full + st, kK64 + kK16);
         if (shared_kv) {
-          tma_load_2d_mc(sk + kK64 + kK16 + rank * (kVt / 2), &tm_vt, v_full + st, row, head * HD + rank * (HD / 2), 3);
+          tma_load_2d_mc(sv + rank * (kK64 / 2), &tm_k64, v_full + st, colv, row + rank * (BKV / 2), 3);
+          tma_load_2d_mc(sv + kK64 + rank * (kK16 / 2), &tm_k16, v_full + st, colv + 64, row + rank * (BKV / 2), 3);
         } else {
 #pragma unroll
-          for (int h = 0; h < 2; ++h)
-            tma_load_2d(sk + kK64 + kK16 + h * (kVt / 2), &tm_vt, v_full + st, row, head * HD + h * (HD / 2));
+          for (int h = 0; h < 2; ++h) {
+            tma_load_2d(sv + h * (kK64 / 2), &tm_k64, v_full + st, colv, row + h * (BKV / 2));
+            tma_load_2d(sv + kK64 + h * (kK16 / 2), &tm_k16, v_full + st, colv + 64, row + h * (BKV / 2));
+          }
         }
       }
     }
@@ -215,7 +218,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) attn_tc_kernel(const __g
     if (elect_one()) {
       // ---- MMA issuer
       const uint32_t idesc_qk = umma_idesc_16bit(BQ, BKV, F16);
-      const uint32_t idesc_pv = umma_idesc_16bit(BQ, HD, F16);
+      // P V: B = V is MN-major (head dim contiguous): transpose-B bit 16 of the instruction descriptor; canonical layout
+      // ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units = rows of one kv, 8-row groups SBO apart (CUTLASS make_umma_desc)
+      const uint32_t idesc_pv64 = umma_idesc_16bit(BQ, 64, F16) | (1u << 16);
+      const uint32_t idesc_pv16 = umma_idesc_16bit(BQ, 16, F16) | (1u << 16);
       auto issue_qk = [&](int t) {
         const int st = t % STAGES;
         const uint32_t sk = smem_u32(smem + st * kStage);
@@ -239,8 +245,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) attn_tc_kernel(const __g
         mbar_wait(p_full, j & 1);
         tc_fence_after();
 #pragma unroll
-        for (int ks = 0; ks < BKV / 16; ++ks)
-          umma_ts(tmem + kOCol, tmem + kPCol + 8 * ks, umma_desc(sv, 1024, kSw128) + 2 * ks, idesc_pv, (j | ks) != 0);
+        for (int ks = 0; ks < BKV / 16; ++ks) {
+          // 16 kv rows per step: 2048 B of the [64][64] block, 512 B of the [64][16] block
+          umma_ts(tmem + kOCol, tmem + kPCol + 8 * ks, umma_desc(sv, 1024, kSw128) + 128 * ks, idesc_pv64, (j | ks) != 0);
+          umma_ts(tmem + kOCol + 64, tmem + kPCol + 8 * ks, umma_desc(sv + kK64, 256, kSw32) + 32 * ks, idesc_pv16, (j | ks) != 0);
+        }
         if (shared_kv) umma_commit_mc(v_empty + st, 3); else umma_commit(v_empty + st);
         umma_commit(pv_done);
       }
@@ -385,48 +394,17 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) attn_tc_kernel(const __g
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, kTmemCols); }
 }
 
-// V heads of qkv (S, 3*hidden), columns [2*hidden, 3*hidden) -> vt [hidden][s_pad] (32x32 tiles through smem)
-__global__ void __launch_bounds__(256) transpose_v_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ vt,
-                                                          int64_t S, int64_t s_pad, int hidden) {
-  __shared__ uint16_t tile[32][34];
-  const int64_t s0 = (int64_t)blockIdx.x * 32;
-  const int c0 = blockIdx.y * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int r = ty; r < 32; r += 8) {
-    const int64_t srow = s0 + r;
-    tile[r][tx] = (srow < S) ? qkv[srow * 3 * hidden + 2 * hidden + c0 + tx] : (uint16_t)0;
-  }
-  __syncthreads();
-  for (int r = ty; r < 32; r += 8) {
-    const int64_t scol = s0 + tx;
-    if (scol < s_pad) vt[(int64_t)(c0 + r) * s_pad + scol] = tile[tx][r];
-  }
-}
-
 }  // namespace
 
-int transpose_v(const void* qkv, void* vt, int64_t S, int64_t s_pad, int heads, int head_dim, void* stream) {
-  const int hidden = heads * head_dim;
-  if (hidden % 32) return fail(ZV_EINVAL, "transpose_v: hidden must be a multiple of 32");
-  dim3 grid((unsigned)((s_pad + 31) / 32), (unsigned)(hidden / 32));
-  KernelTimer timer(KC_ATTN_FULL, stream);
-  transpose_v_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint16_t*>(qkv),
-                                                                          static_cast<uint16_t*>(vt), S, s_pad, hidden);
-  count_launch();
-  return ZV_OK;
-}
-
-int attention_tc(const void* qkv, const void* vt, int64_t s_pad, void* out, int64_t S, int heads, int head_dim,
+int attention_tc(const void* qkv, void* out, int64_t S, int heads, int head_dim,
                  const int32_t* tiles_dev, int n_tiles, void* stream_, bool f16) {
   if (head_dim != HD) return fail(ZV_EINVAL, "attention_tc: only head_dim=80 is built (got %d)", head_dim);
   if (n_tiles <= 0) return ZV_OK;
   const int hidden = heads * head_dim;
-  CUtensorMap t64, t16, tvt;
-  int rc = make_tmap_2d(&t64, qkv, S, 3 * hidden, 3 * hidden, 64, BKV / 2, 128, f16);     // half K tiles (32 rows)
+  CUtensorMap t64, t16;
+  int rc = make_tmap_2d(&t64, qkv, S, 3 * hidden, 3 * hidden, 64, BKV / 2, 128, f16);     // half K / V tiles (32 rows)
   if (rc) return rc;
   rc = make_tmap_2d(&t16, qkv, S, 3 * hidden, 3 * hidden, 16, BKV / 2, 32, f16);
-  if (rc) return rc;
-  rc = make_tmap_2d(&tvt, vt, hidden, S, s_pad, BKV, HD / 2, 128, f16);                   // half V^T tiles (40 head dims)
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
@@ -451,8 +429,8 @@ int attention_tc(const void* qkv, const void* vt, int64_t s_pad, void* out, int6
   cudaError_t le;
   {
     KernelTimer timer(KC_ATTN_FULL, stream_);
-    le = f16 ? cudaLaunchKernelEx(&cfg, attn_tc_kernel<true>, t64, t16, tvt, a)
-             : cudaLaunchKernelEx(&cfg, attn_tc_kernel<false>, t64, t16, tvt, a);
+    le = f16 ? cudaLaunchKernelEx(&cfg, attn_tc_kernel<true>, t64, t16, a)
+             : cudaLaunchKernelEx(&cfg, attn_tc_kernel<false>, t64, t16, a);
   }
   if (le != cudaSuccess) return fail(ZV_ECUDA, "attention_tc: launch: %s", cudaGetErrorString(le));
   count_launch();

@@ -42,12 +42,10 @@ int gemm(int epi, const GemmArgs& g, const void* a, int64_t lda, const void* b, 
 // cuTensorMapEncodeTiled wrapper (tm points at a CUtensorMap): 16-bit 2-D tensor, box_cols x box_rows box.
 int make_tmap_2d(void* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
                  int swizzle_bytes, bool f16);
-// tcgen05 flash attention for long segments (zv_attn_tc.cu): qkv (S, 3*H) 16-bit with rotary applied, vt = V
-// transposed per head [(heads*80)][s_pad]; tiles (q0, q_len, seg_begin, seg_end) with q_len <= 128.
-int attention_tc(const void* qkv, const void* vt, int64_t s_pad, void* out, int64_t S, int heads, int head_dim,
-                 const int32_t* tiles_dev, int n_tiles, void* stream, bool f16);
-// V heads of qkv -> vt [(heads*head_dim)][s_pad] (s_pad = S rounded up to 8)
-int transpose_v(const void* qkv, void* vt, int64_t S, int64_t s_pad, int heads, int head_dim, void* stream);
+// tcgen05 flash attention for long segments (zv_attn_tc.cu): qkv (S, 3*H) 16-bit with rotary applied; tiles
+// (q0, q_len, seg_begin, seg_end) with q_len <= 128.
+int attention_tc(const void* qkv, void* out, int64_t S, int heads, int head_dim, const int32_t* tiles_dev, int n_tiles,
+                 void* stream, bool f16);
 
 // fp32 (S, H) -> 16-bit copy (S, H) + per-row sum of squares in ss[row][0] (ss[row][1..kSsParts) = 0): the producer side
 // of the folded RMSNorm for rows that no residual GEMM has written yet (the patch-embed output)

@@ -347,7 +347,7 @@ int zv_weights_pack(const zv_cfg* cfg, const zv_tensor* tensors, int32_t n, void
 }
 
 namespace {
-struct Workspace { int64_t p = 0, x = 0, y = 0, x16 = 0, ss = 0, big = 0, vt = 0, comp = 0, s_pad = 0, bytes = 0; };
+struct Workspace { int64_t p = 0, x = 0, y = 0, x16 = 0, ss = 0, big = 0, comp = 0, bytes = 0; };
 Workspace workspace_layout(const zv_cfg* c, int64_t S) {
   Workspace w;
   const int64_t H = c->hidden;
@@ -360,8 +360,6 @@ Workspace workspace_layout(const zv_cfg* c, int64_t S) {
   w.x16 = take(S * H * 2);               // 16-bit copy of the residual stream (A operand of the QKV / gate-up GEMMs)
   w.ss = take(S * kSsParts * 4);         // per-row partial sums of squares of X (folded RMSNorm)
   w.big = take(S * wide * 2);
-  w.s_pad = (S + 7) / 8 * 8;
-  w.vt = take(w.s_pad * H * 2);          // V^T per head for the tcgen05 full-attention kernel
   w.comp = take((S / 4 + 1) * 4);        // int32 [T]: composed scatter rows of zv_visual_forward_into
   w.bytes = off;
   return w;
@@ -475,8 +473,7 @@ int visual_forward_impl(const zv_cfg* cfg, const void* weights_dev, const zv_pla
     g.row_ss = SS; g.norm_eps = cfg->eps; g.norm_dim = (int)H;               // norm1 (gain folded into Wqkv)
     ZV_TRY(gemm(EPI_QKV_ROPE, g, X16, H, wb + o.wqkv, H, stream));
     if (full && !legacy_full) {
-      ZV_TRY(transpose_v(BIG, ws + W.vt, S, W.s_pad, cfg->heads, (int)(H / cfg->heads), stream));
-      ZV_TRY(attention_tc(BIG, ws + W.vt, W.s_pad, Y, S, cfg->heads, (int)(H / cfg->heads), d_full, p->n_full_tiles, stream, f16 != 0));
+      ZV_TRY(attention_tc(BIG, Y, S, cfg->heads, (int)(H / cfg->heads), d_full, p->n_full_tiles, stream, f16 != 0));
     } else {
       ZV_TRY(attention(BIG, Y, cfg->heads, (int)(H / cfg->heads), full ? d_full : d_win, full ? p->n_full_tiles : p->n_win_tiles, stream, full, f16 != 0));
     }
@@ -548,22 +545,15 @@ int zv_attention(const void* qkv_dev, void* out_dev, int32_t heads, int32_t head
       tiles.push_back(q0); tiles.push_back(std::min(bq, cu_host[s + 1] - q0));
       tiles.push_back(cu_host[s]); tiles.push_back(cu_host[s + 1]);
     }
-  const int hidden = heads * head_dim;
   int64_t S = cu_host[n_seg];
-  const int64_t s_pad = (S + 7) / 8 * 8;
   const bool use_tc = full && std::getenv("ZV_ATTN_LEGACY") == nullptr;
-  const int64_t tiles_bytes = ((int64_t)tiles.size() * 4 + 255) / 256 * 256;
-  const int64_t need = tiles_bytes + (use_tc ? s_pad * hidden * 2 : 0);
+  const int64_t need = ((int64_t)tiles.size() * 4 + 255) / 256 * 256;
   if (work_bytes < need) return fail(ZV_ENOMEM, "zv_attention: work buffer %lld B < required %lld B", (long long)work_bytes, (long long)need);
   cudaError_t e = cudaMemcpyAsync(work_dev, tiles.data(), tiles.size() * 4, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return fail(ZV_ECUDA, "zv_attention: %s", cudaGetErrorString(e));
-  if (use_tc) {
-    void* vt = static_cast<uint8_t*>(work_dev) + tiles_bytes;
-    rc = transpose_v(qkv_dev, vt, S, s_pad, heads, head_dim, stream);
-    if (rc) return rc;
-    return attention_tc(qkv_dev, vt, s_pad, out_dev, S, heads, head_dim, static_cast<const int32_t*>(work_dev),
-                        (int)(tiles.size() / 4), stream, dtype == ZV_F16);
-  }
+  if (use_tc)
+    return attention_tc(qkv_dev, out_dev, S, heads, head_dim, static_cast<const int32_t*>(work_dev), (int)(tiles.size() / 4), stream,
+                        dtype == ZV_F16);
   return attention(qkv_dev, out_dev, heads, head_dim, static_cast<const int32_t*>(work_dev), (int)(tiles.size() / 4), stream, full, dtype == ZV_F16);
 }
 
