@@ -16,7 +16,7 @@ import json; d=json.load(open('gpurun_out/bench.json')); print(d['value'], d['ms
 python tools/latency.py > gpurun_out/latency.json 2> gpurun_out/latency.err; echo "latency exit $?"
 python tools/bench_configs.py --config 3 4 5 > gpurun_out/configs_n1.jsonl 2> gpurun_out/configs_n1.err; echo "configs exit $?"
 if [ "${NCU:-1}" = "1" ]; then
-  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"gemm_tc|attn_|k1_|rmsnorm|transpose_v|gather|compose|cast_rows" -s 513 -c 171 --csv --log-file gpurun_out/launches.csv \
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"gemm_tc|attn_|k1_|rmsnorm|gather|compose|cast_rows" -s 501 -c 167 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --images 8 > gpurun_out/ncu_list.log 2>&1; echo "ncu list exit $?"
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:"attn_tc_kernel" -s 4 -c 1 -o gpurun_out/prof_attn_tc -f \
     python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --images 8 > gpurun_out/ncu_attn.log 2>&1; echo "ncu attn_tc exit $?"
