@@ -189,7 +189,7 @@ def run_ours(args):
     pk = peaks()
 
     sd = random_vision_state_dict(0, device=dev)
-    visual = FusedVisual(sd, device=dev, dtype=torch.bfloat16)
+    visual = FusedVisual(sd, device=dev, dtype=torch.float16)
     del sd
     enc = ZoomEncoder(visual, FusedImageProcessor(min_pixels=MIN_PIXELS, max_pixels=MAX_PIXELS, device=dev))
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -203,7 +203,7 @@ def run_ours(args):
         if not args.nccl_gather:
             try:
                 from zoomearth_b200.sharding import PeerGather
-                pg = PeerGather(world * tokens_step, 2048, torch.bfloat16, dev)
+                pg = PeerGather(world * tokens_step, 2048, torch.float16, dev)
                 gather_kind = "fused: merger GEMM epilogue stores into every rank's buffer over NVLink (symmetric memory)"
             except Exception as e:          # symmetric memory unavailable on this box: the NCCL collective still gathers
                 pg = None
@@ -280,7 +280,7 @@ def run_ours(args):
     if not args.no_e2e:
         n_e2e = min(n_img, args.e2e_images)
         host = [im.cpu().pin_memory() for im in images[:n_e2e]]
-        out_host = torch.empty((n_e2e * T_img, 2048), dtype=torch.bfloat16).pin_memory()
+        out_host = torch.empty((n_e2e * T_img, 2048), dtype=torch.float16).pin_memory()
 
         def step_e2e():
             # H2D of this step's pixels and D2H of its embeddings, pipelined in chunks behind the compute

@@ -123,8 +123,58 @@ def _mm(x, w, emulate_bf16):
     return x @ w.t()
 
 
-def forward(sd, pixel_values, grid_thw, cfg=CFG, emulate_bf16=False, return_hidden=False):
-    """pixel_values (S,1176) f32 in HF row order, grid_thw (N,3) -> (T, out_hidden) f32 in HF output order."""
+def _attend(qs, ks, vs, hd, q_chunk):
+    """softmax(q k^T / sqrt(hd)) v for one segment, (heads, n, hd) each; q rows in chunks so that a 65 536-patch
+    segment (configs[4]) does not materialise a heads x n x n score tensor.  Same arithmetic chunked or not."""
+    n = qs.shape[1]
+    if n <= q_chunk:
+        return torch.softmax(qs @ ks.transpose(1, 2) / math.sqrt(hd), -1) @ vs
+    outs = []
+    for a in range(0, n, q_chunk):
+        outs.append(torch.softmax(qs[:, a:a + q_chunk] @ ks.transpose(1, 2) / math.sqrt(hd), -1) @ vs)
+    return torch.cat(outs, 1)
+
+
+def _attend_grouped(q, k, v, seg, hd, q_chunk):
+    """Same per-segment attention with the segments of equal length stacked into one batched matmul (GPU checker only:
+    thousands of 64-row windows would otherwise be a Python loop of tiny launches)."""
+    S, heads, _ = q.shape
+    starts = torch.tensor(seg[:-1], device=q.device)
+    lens = torch.tensor(seg[1:], device=q.device) - starts
+    out = torch.empty(S, heads * hd, dtype=q.dtype, device=q.device)
+    for n in torch.unique(lens).tolist():
+        st = starts[lens == n]
+        for c0 in range(0, st.numel(), 4096):
+            idx = (st[c0:c0 + 4096, None] + torch.arange(n, device=q.device)[None, :]).reshape(-1)
+            qs, ks, vs = (t[idx].view(-1, n, heads, hd).permute(0, 2, 1, 3).reshape(-1, n, hd) for t in (q, k, v))
+            o = _attend(qs, ks, vs, hd, q_chunk)                                                 # (G * heads, n, hd)
+            out[idx] = o.view(-1, heads, n, hd).permute(0, 2, 1, 3).reshape(-1, heads * hd)
+    return out
+
+
+def forward(sd, pixel_values, grid_thw, cfg=CFG, emulate_bf16=False, return_hidden=False, device=None, q_chunk=4096):
+    """pixel_values (S,1176) f32 in HF row order, grid_thw (N,3) -> (T, out_hidden) f32 in HF output order.
+
+    ``device``: run the same fp32 arithmetic on that device (the GPU tests use ``cuda`` as the checker for shapes the
+    CPU cannot finish: TF32 is switched off for the call, so every matmul is IEEE fp32); the result comes back on
+    the CPU.  Weights are moved per call - the caller may pass a state dict that already lives on the device."""
+    if device is not None and torch.device(device).type == "cuda":
+        old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32, torch.get_float32_matmul_precision())
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        torch.set_float32_matmul_precision("highest")
+        try:
+            sd_d = {k: v.to(device) for k, v in sd.items()}
+            out = _forward(sd_d, pixel_values.to(device), grid_thw, cfg, emulate_bf16, return_hidden, q_chunk)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old[0], old[1]
+            torch.set_float32_matmul_precision(old[2])
+        return tuple(t.cpu() for t in out) if return_hidden else out.cpu()
+    return _forward(sd, pixel_values, grid_thw, cfg, emulate_bf16, return_hidden, q_chunk)
+
+
+def _forward(sd, pixel_values, grid_thw, cfg, emulate_bf16, return_hidden, q_chunk):
+    dev = pixel_values.device
     H, heads = cfg["hidden"], cfg["heads"]
     hd = H // heads
     eps = cfg["eps"]
@@ -132,11 +182,11 @@ def forward(sd, pixel_values, grid_thw, cfg=CFG, emulate_bf16=False, return_hidd
     bf = emulate_bf16
     x = _mm(pixel_values.float(), sd["patch_embed.proj.weight"].reshape(H, -1), bf)
     S = x.shape[0]
-    pos = torch.from_numpy(rot_pos_ids(grid_thw, cfg["merge"]))
-    inv_freq = 1.0 / (10000.0 ** (torch.arange(0, hd // 2, 2, dtype=torch.float) / (hd // 2)))
+    pos = torch.from_numpy(rot_pos_ids(grid_thw, cfg["merge"])).to(dev)
+    inv_freq = (1.0 / (10000.0 ** (torch.arange(0, hd // 2, 2, dtype=torch.float) / (hd // 2)))).to(dev)
     rot = torch.cat([pos[:, 0:1].float() * inv_freq, pos[:, 1:2].float() * inv_freq], -1)       # (S, hd/2)
     widx_np, cu_win = window_index(grid_thw, cfg["window"], cfg["merge"], cfg["patch"])
-    widx = torch.from_numpy(widx_np)
+    widx = torch.from_numpy(widx_np).to(dev)
     cu_win = unique_consecutive(cu_win)
     cu_full = cu_seqlens_full(grid_thw)
     x = x.view(S // unit, unit, H)[widx].reshape(S, H)
@@ -158,12 +208,14 @@ def forward(sd, pixel_values, grid_thw, cfg=CFG, emulate_bf16=False, return_hidd
         q, k = rope(q), rope(k)
         if bf:
             q, k, v = (t.to(torch.bfloat16).float() for t in (q, k, v))
-        outs = []
-        for a, b in zip(seg[:-1], seg[1:]):
-            qs, ks, vs = (t[a:b].transpose(0, 1) for t in (q, k, v))                             # (heads, n, hd)
-            att = torch.softmax(qs @ ks.transpose(1, 2) / math.sqrt(hd), -1)
-            outs.append((att @ vs).transpose(0, 1).reshape(b - a, H))
-        att = torch.cat(outs, 0)
+        if dev.type == "cuda" and len(seg) > 65:
+            att = _attend_grouped(q, k, v, seg, hd, q_chunk)
+        else:
+            outs = []
+            for a, b in zip(seg[:-1], seg[1:]):
+                qs, ks, vs = (t[a:b].transpose(0, 1) for t in (q, k, v))                         # (heads, n, hd)
+                outs.append(_attend(qs, ks, vs, hd, q_chunk).transpose(0, 1).reshape(b - a, H))
+            att = torch.cat(outs, 0)
         x = x + _mm(att, sd[p + "attn.proj.weight"], bf) + sd[p + "attn.proj.bias"]
         y = _rms(x, sd[p + "norm2.weight"], eps)
         gate = _mm(y, sd[p + "mlp.gate_proj.weight"], bf) + sd[p + "mlp.gate_proj.bias"]

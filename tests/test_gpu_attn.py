@@ -20,11 +20,19 @@ def test_attention_vs_sdpa(cuda, lib, segs, dtype):
     _lib.check(lib.zv_attention(qkv.data_ptr(), out.data_ptr(), heads, hd, cu.ctypes.data, len(segs), work.data_ptr(),
                                 work.numel(), 2 if dtype == torch.float16 else 1, torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
-    q, k, v = (t.float().transpose(0, 1) for t in qkv.unbind(1))            # (heads, S, hd)
+    q, k, v = (t.float().cpu().transpose(0, 1) for t in qkv.unbind(1))      # (heads, S, hd)
     refs = []
     for a, b in zip(cu[:-1], cu[1:]):
         refs.append(torch.nn.functional.scaled_dot_product_attention(q[:, a:b], k[:, a:b], v[:, a:b]))
     ref = torch.cat(refs, 1).transpose(0, 1).reshape(S, heads * hd)
-    err = (out.float() - ref).abs().max().item()
-    assert err < 2e-2, f"max err {err}"
-    assert torch.nn.functional.cosine_similarity(out.float().flatten(), ref.flatten(), dim=0) > 0.9999
+    # relative bounds: outputs of a long segment are averages of thousands of values (magnitude ~ 0.03), so an absolute
+    # bound has no teeth there.  The error budget is the 16-bit rounding of P and of the output: 2^-9 (bf16) / 2^-12 (fp16)
+    # relative to the row's largest value.
+    out = out.float().cpu()
+    scale = ref.abs().max().item()
+    err = (out - ref).abs().max().item() / scale
+    tol = 6e-3 if dtype == torch.bfloat16 else 1e-3
+    assert err < tol, f"max err / max|ref| = {err} (tolerance {tol})"
+    rel_fro = ((out - ref).norm() / ref.norm()).item()
+    assert rel_fro < (3.5e-3 if dtype == torch.bfloat16 else 5e-4), f"relative Frobenius error {rel_fro}"
+    assert torch.nn.functional.cosine_similarity(out.flatten(), ref.flatten(), dim=0) > 0.9999

@@ -125,6 +125,81 @@ def test_config5_max_resolution_crop(cuda):
     assert cos >= 0.9999 and maxrel <= 5e-3, f"cos {cos} maxrel {maxrel}"
 
 
+def _k1_both(enc, images, boxes=None, image_index=None, apply_cut_image=True):
+    """K1 twice over the same crops: fp32 patches in HF order (= the HF processor's pixel_values, the oracle tower's
+    input) and the 16-bit window-ordered patches the fused path feeds the tower."""
+    hf, grid, crop = enc.processor.preprocess_crops(images, boxes, torch.float32, False, image_index=image_index,
+                                                    apply_cut_image=apply_cut_image and boxes is not None)
+    return hf, grid, crop
+
+
+def test_config2_bench_workload_full_depth_vs_gpu_oracle(cuda, full_sd_cuda, full_visual):
+    """configs[1], the workload bench.py times, at its full size and depth: 64 synthetic 5000x5000 images -> global view
+    980x980 (grid 1x70x70) -> all 32 blocks, fp16 operands, against the fp32 oracle tower run on the GPU (TF32 off).
+    Image 0's pixel_values are pinned bit-exact to the live HF PIL processor; the oracle consumes K1's fp32 output."""
+    from oracle import hf_live
+    from zoomearth_b200 import FusedImageProcessor, ZoomEncoder
+    n_img = 64
+    enc = ZoomEncoder(full_visual, FusedImageProcessor(min_pixels=3136, max_pixels=1280 * 28 * 28, device=cuda))
+    g = torch.Generator(device=cuda).manual_seed(99)
+    images = [torch.randint(0, 256, (5000, 5000, 3), generator=g, dtype=torch.uint8, device=cuda) for _ in range(n_img)]
+    pv_hf, grid, _ = _k1_both(enc, images)
+    assert grid.tolist() == [[1, 70, 70]] * n_img
+    ref_pv0, ref_grid0 = hf_live.hf_preprocess([images[0].cpu().numpy()], 3136, 1280 * 28 * 28)
+    assert torch.equal(pv_hf[:4900].cpu(), ref_pv0) and ref_grid0.tolist() == [[1, 70, 70]]
+    emb, grid2, _ = enc.encode(images, None)                       # the timed path: fp16 window-ordered patches -> tower
+    del images
+    assert emb.shape == (n_img * 1225, 2048) and grid2.tolist() == grid.tolist()
+    ref = OT.forward(full_sd_cuda, pv_hf, grid.numpy(), device=cuda)
+    cos, maxrel = _metrics(emb, ref)
+    worst = max(_metrics(emb[i * 1225:(i + 1) * 1225], ref[i * 1225:(i + 1) * 1225])[1] for i in range(n_img))
+    print(f"PARITY configs[1] 64 x 70x70, depth 32, fp16 operands vs fp32 oracle (GPU): cosine {cos:.6f}, "
+          f"max rel err {maxrel:.3e} (worst single image {worst:.3e})")
+    assert cos >= 0.999 and maxrel <= 1e-2 and worst <= 1e-2, f"cos {cos} maxrel {maxrel} worst image {worst}"
+
+
+def test_config4_mixed_crops_full_depth_crop_by_crop_vs_oracle(cuda, full_sd_cuda, full_visual):
+    """configs[3] in miniature at full depth: 12 mixed-size crops (256-1400 px per side, cut_image rule) as ONE ragged
+    batch; every crop's embeddings against the fp32 oracle of that crop (not against another run of the CUDA path)."""
+    from zoomearth_b200 import FusedImageProcessor, ZoomEncoder
+    enc = ZoomEncoder(full_visual, FusedImageProcessor(min_pixels=3136, max_pixels=12845056, device=cuda))
+    img = np.random.default_rng(4).integers(0, 256, (2400, 2400, 3), dtype=np.uint8)
+    dev = enc.upload(img)
+    rng = np.random.default_rng(44)
+    boxes = []
+    for _ in range(12):
+        w, h = int(rng.integers(256, 1400)), int(rng.integers(256, 1400))
+        x, y = int(rng.integers(0, 2400 - w)), int(rng.integers(0, 2400 - h))
+        boxes.append((x, y, x + w, y + h))
+    emb, grid, crop = enc.encode([dev], boxes, image_index=[0] * 12)
+    tokens = enc.tokens_per_crop(grid.numpy())
+    starts = np.concatenate([[0], np.cumsum(tokens)])
+    for i, b in enumerate(boxes):
+        box, pv, g = OP.zoom_step_u8(img, b, 512, 3136, 12845056)
+        assert tuple(int(v) for v in crop[i]) == box and grid[i].tolist() == g[0].tolist()
+        ref = OT.forward(full_sd_cuda, torch.from_numpy(pv), g, device=cuda)
+        cos, maxrel = _metrics(emb[starts[i]:starts[i + 1]], ref)
+        assert cos >= 0.999 and maxrel <= 1e-2, f"crop {i} {box}: cos {cos} maxrel {maxrel}"
+
+
+def test_config5_max_resolution_full_depth_vs_gpu_oracle(cuda, full_sd_cuda, full_visual):
+    """configs[4]: one 3584x3584 crop at max_pixels = 16384*28*28 -> grid (1,256,256): a single full-attention segment
+    of 65 536 patches through all 32 blocks, against the fp32 oracle on the GPU (q rows in chunks of 2048)."""
+    from zoomearth_b200 import FusedImageProcessor, ZoomEncoder
+    enc = ZoomEncoder(full_visual, FusedImageProcessor(min_pixels=3136, max_pixels=16384 * 28 * 28, device=cuda))
+    g = torch.Generator(device=cuda).manual_seed(5)
+    img = torch.randint(0, 256, (3700, 3700, 3), generator=g, dtype=torch.uint8, device=cuda)
+    box = (50, 60, 3634, 3644)
+    pv_hf, grid, crop = _k1_both(enc, [img], [box])
+    assert grid.tolist() == [[1, 256, 256]] and tuple(int(v) for v in crop[0]) == box
+    emb, _, _ = enc.encode([img], [box])
+    ref = OT.forward(full_sd_cuda, pv_hf, grid.numpy(), device=cuda, q_chunk=2048)
+    cos, maxrel = _metrics(emb, ref)
+    print(f"PARITY configs[4] one 65 536-patch segment, depth 32, fp16 operands vs fp32 oracle (GPU): cosine {cos:.6f}, "
+          f"max rel err {maxrel:.3e}")
+    assert emb.shape == (16384, 2048) and cos >= 0.999 and maxrel <= 1e-2, f"cos {cos} maxrel {maxrel}"
+
+
 def test_install_swaps_hf_visual_and_matches_it(cuda):
     """Drop-in through HF's own call path: install() replaces model.visual of a (tiny-LM) Qwen2.5-VL model; the HF
     get_image_features() then returns what the original HF tower returned, within the stated tolerance."""
@@ -149,12 +224,29 @@ def test_install_swaps_hf_visual_and_matches_it(cuda):
     with torch.no_grad():
         ref = hf_visual(pv, grid_thw=grid)
     ref = ref.pooler_output if hasattr(ref, "pooler_output") else ref
+    with torch.no_grad():
+        ref_feat = owner.get_image_features(pv, grid) if hasattr(owner, "get_image_features") else None
     fv, _ = install(model, device=cuda, dtype=torch.float32)
     assert owner.visual is fv and fv.dtype == torch.float32 and fv.spatial_merge_size == 2
     out = owner.visual(pv.to(cuda), grid_thw=grid)
     out = out.pooler_output if hasattr(out, "pooler_output") else out
     cos, maxrel = _metrics(out, ref)
     assert cos >= 0.999 and maxrel <= 1e-2, f"cos {cos} maxrel {maxrel}"
+    # ... and through HF's own call path: get_image_features() casts pixel_values to visual.dtype, calls
+    # self.visual(pixel_values, grid_thw=...) and splits the result per image (HF modeling_qwen2_5_vl.py:1159-1177)
+    if ref_feat is not None:
+        with torch.no_grad():
+            feat = owner.get_image_features(pv.to(cuda), grid.to(cuda))
+
+        def _per_image(f):
+            f = f.pooler_output if hasattr(f, "pooler_output") else f
+            return list(f) if isinstance(f, (list, tuple)) else [f]
+        got, want = _per_image(feat), _per_image(ref_feat)
+        assert len(got) == len(want)
+        for a, b in zip(got, want):
+            assert a.shape == b.shape
+            cos, maxrel = _metrics(a, b)
+            assert cos >= 0.999 and maxrel <= 1e-2, f"get_image_features: cos {cos} maxrel {maxrel}"
 
 
 def test_zoom_session_caches_global_view_and_batches_crops(cuda):

@@ -58,7 +58,7 @@ def test_embed_images_from_fused_preprocess(cuda):
     """Zoom fast path end to end: resident image -> K1 (window-ordered patches) -> tower -> inputs_embeds rows."""
     from zoomearth_b200 import FusedImageProcessor, FusedVisual, embed_images
     cfg = OT.small_cfg(depth=2, fullatt=(1,))
-    fv = FusedVisual(OT.make_weights(22, cfg), device=cuda, dtype=torch.bfloat16, depth=cfg["depth"], fullatt=list(cfg["fullatt"]))
+    fv = FusedVisual(OT.make_weights(22, cfg), device=cuda, dtype=torch.bfloat16, operand_dtype=torch.bfloat16, depth=cfg["depth"], fullatt=list(cfg["fullatt"]))
     proc = FusedImageProcessor(min_pixels=3136, max_pixels=200704, device=cuda)
     img = torch.from_numpy(np.random.default_rng(9).integers(0, 256, (700, 900, 3), dtype=np.uint8)).to(cuda)
     pv, grid, _ = proc.preprocess_crops([img], [(10, 20, 600, 500)], out_dtype=torch.bfloat16, window_order=True)

@@ -62,7 +62,7 @@ def main():
         os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.lib()
-    visual = FusedVisual(synthetic.random_vision_state_dict(0, device=dev), device=dev, dtype=torch.bfloat16)
+    visual = FusedVisual(synthetic.random_vision_state_dict(0, device=dev), device=dev, dtype=torch.float16)
     enc = ZoomEncoder(visual, FusedImageProcessor(min_pixels=3136, max_pixels=16384 * 28 * 28, device=dev))
     g = torch.Generator(device=dev).manual_seed(7)          # same pool on every rank (images are replicated)
     pool = [torch.randint(0, 256, (5000, 5000, 3), generator=g, dtype=torch.uint8, device=dev) for _ in range(args.pool)]

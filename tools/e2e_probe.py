@@ -9,12 +9,12 @@ from zoomearth_b200 import FusedImageProcessor, FusedVisual, ZoomEncoder
 from zoomearth_b200.synthetic import random_vision_state_dict
 
 dev = torch.device("cuda", 0)
-visual = FusedVisual(random_vision_state_dict(0, device=dev), device=dev, dtype=torch.bfloat16)
+visual = FusedVisual(random_vision_state_dict(0, device=dev), device=dev, dtype=torch.float16)
 enc = ZoomEncoder(visual, FusedImageProcessor(min_pixels=3136, max_pixels=1280 * 28 * 28, device=dev))
 g = torch.Generator(device=dev).manual_seed(1)
 images = [torch.randint(0, 256, (5000, 5000, 3), generator=g, dtype=torch.uint8, device=dev) for _ in range(64)]
 host = [im.cpu().pin_memory() for im in images]
-out_host = torch.empty((64 * 1225, 2048), dtype=torch.bfloat16).pin_memory()
+out_host = torch.empty((64 * 1225, 2048), dtype=torch.float16).pin_memory()
 
 
 def timed(fn, n=3):

@@ -11,7 +11,7 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 sd = random_vision_state_dict(0, device=dev, depth=2)
-fv = FusedVisual(sd, device=dev, dtype=torch.bfloat16, depth=2, fullatt=[1])
+fv = FusedVisual(sd, device=dev, dtype=torch.float16, depth=2, fullatt=[1])
 enc = ZoomEncoder(fv, FusedImageProcessor(min_pixels=3136, max_pixels=200704, device=dev))
 g = torch.Generator(device=dev).manual_seed(100 + rank)
 imgs = [torch.randint(0, 256, (700, 900, 3), generator=g, dtype=torch.uint8, device=dev) for _ in range(3)]
@@ -19,7 +19,7 @@ emb, grid, _ = enc.encode(imgs, None)
 T = emb.shape[0]
 ref = torch.empty((world * T, emb.shape[1]), dtype=emb.dtype, device=dev)
 dist.all_gather_into_tensor(ref, emb)
-pg = PeerGather(world * T, emb.shape[1], torch.bfloat16, dev)
+pg = PeerGather(world * T, emb.shape[1], torch.float16, dev)
 pg.buffer.zero_()
 pg.barrier()
 enc.encode(imgs, None, gather=pg, gather_row=rank * T)

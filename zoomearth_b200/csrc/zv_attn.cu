@@ -328,18 +328,17 @@ __global__ void __launch_bounds__(128, 3) attn_window_kernel(const __nv_bfloat16
 template <bool F16>
 int launch_window(const void* qkv, void* out, int heads, const int32_t* tiles_dev, int n_tiles, float scale_log2, void* stream_) {
   constexpr int kSmem = 2 * 3 * kTileElems * 2;
-  static bool attr_set = false;
-  static int n_sm = 0;
-  if (!attr_set) {
+  static std::atomic<uint64_t> attr_set{0};
+  const int dev = current_device();
+  if (device_needs_setup(attr_set, dev)) {
     cudaError_t e = cudaFuncSetAttribute(attn_window_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (e != cudaSuccess) return fail(ZV_ECUDA, "attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    attr_set = true;
+    mark_device(attr_set, dev);
   }
+  const int n_sm = num_sms();
   const int n_items = n_tiles * heads;
   const int grid = n_items < 3 * n_sm ? n_items : 3 * n_sm;
+  NvtxRange nvtx("zv:K3 window attention");
   KernelTimer timer(KC_ATTN_WINDOW, stream_);
   attn_window_kernel<F16><<<grid, 128, kSmem, static_cast<cudaStream_t>(stream_)>>>(
       static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), reinterpret_cast<const int4*>(tiles_dev),
@@ -350,11 +349,12 @@ int launch_window(const void* qkv, void* out, int heads, const int32_t* tiles_de
 template <int NW, bool F16>
 int launch_attn(const void* qkv, void* out, int heads, const int32_t* tiles_dev, int n_tiles, float scale_log2,
                 void* stream_, int cls) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<uint64_t> attr_set{0};
+  const int dev = current_device();
+  if (device_needs_setup(attr_set, dev)) {
     cudaError_t e = cudaFuncSetAttribute(attn_kernel<NW, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<NW>());
     if (e != cudaSuccess) return fail(ZV_ECUDA, "attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
+    mark_device(attr_set, dev);
   }
   dim3 grid((unsigned)n_tiles, (unsigned)heads);
   KernelTimer timer(cls, stream_);

@@ -406,12 +406,13 @@ int attention_tc(const void* qkv, void* out, int64_t S, int heads, int head_dim,
   if (rc) return rc;
   rc = make_tmap_2d(&t16, qkv, S, 3 * hidden, 3 * hidden, 16, BKV / 2, 32, f16);
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<uint64_t> attr_set{0};
+  const int dev = current_device();
+  if (device_needs_setup(attr_set, dev)) {
     cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (e != cudaSuccess) return fail(ZV_ECUDA, "attention_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
+    mark_device(attr_set, dev);
   }
   AttnArgs a{};
   a.out = out; a.qkv = qkv; a.S = S; a.tiles = reinterpret_cast<const int4*>(tiles_dev); a.n_tiles = n_tiles; a.heads = heads; a.hidden = hidden; a.f16 = f16;
@@ -428,6 +429,7 @@ int attention_tc(const void* qkv, void* out, int64_t S, int heads, int head_dim,
   cfg.numAttrs = 1;
   cudaError_t le;
   {
+    NvtxRange nvtx("zv:K4 full attention (tcgen05)");
     KernelTimer timer(KC_ATTN_FULL, stream_);
     le = f16 ? cudaLaunchKernelEx(&cfg, attn_tc_kernel<true>, t64, t16, a)
              : cudaLaunchKernelEx(&cfg, attn_tc_kernel<false>, t64, t16, a);

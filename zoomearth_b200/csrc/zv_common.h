@@ -1,5 +1,6 @@
 // Shared internals of libzoomvit (not part of the C ABI).
 #pragma once
+#include <atomic>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -13,6 +14,23 @@ namespace zv {
 int fail(int code, const char* fmt, ...);   // records the thread-local message, returns code
 void count_launch(int64_t n = 1);
 void reset_launch_count();
+
+// Per-device one-time setup (cudaFuncSetAttribute is a per-device property): `mask` holds one bit per device ordinal.
+// Returns true when the current device has not been marked yet; the caller does its setup and then calls mark_device.
+// Two threads may both see "not yet" and both run the (idempotent) setup - harmless.
+int current_device();
+inline bool device_needs_setup(const std::atomic<uint64_t>& mask, int dev) {
+  return (mask.load(std::memory_order_acquire) & (1ull << (dev & 63))) == 0;
+}
+inline void mark_device(std::atomic<uint64_t>& mask, int dev) { mask.fetch_or(1ull << (dev & 63), std::memory_order_release); }
+int num_sms();                              // SM count of the current device (cached per device ordinal)
+
+// NVTX range around one stage of the path (nvtx3 is header-only; a no-op unless a profiler is attached)
+class NvtxRange {
+ public:
+  explicit NvtxRange(const char* name);
+  ~NvtxRange();
+};
 
 // Kernel classes for the optional event timing (zv_timing_*): one id per kernel template.
 enum KernelClass { KC_K1_HPASS = 0, KC_K1_VPASS = 1, KC_GEMM_STORE = 2, KC_GEMM_QKV = 3, KC_GEMM_RESID = 4,

@@ -167,31 +167,15 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int m_blk, int n_b
   } else if constexpr (EPI == EPI_STORE || EPI == EPI_GELU || EPI == EPI_SCATTER) {
     constexpr int HALF = BN / 2;
     int64_t orow = row;
-    if constexpr (EPI == EPI_SCATTER) orow = valid ? (int64_t)__ldg(g.scatter + row) : 0;
+    bool keep = valid;
+    if constexpr (EPI == EPI_SCATTER) { orow = valid ? (int64_t)__ldg(g.scatter + row) : 0; keep = valid && orow >= 0; }
     const int c_begin = half * HALF;
-    float4 xprev[8];
-    if constexpr (EPI == EPI_RESID) {       // residual values of the first chunk: fetched before the accumulator is needed
-      if (valid) {
-        const float4* o = reinterpret_cast<const float4*>(static_cast<const float*>(g.out) + orow * g.ldo + n_blk * BN + c_begin);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) xprev[j] = o[j];
-      }
-      wait_accumulator();
-    }
 #pragma unroll 1
     for (int c = c_begin; c < c_begin + HALF; c += 32) {
       uint32_t r[32];
       __syncwarp();
       tmem_ld_x32(taddr + c, r);
       const int n0 = n_blk * BN + c;
-      float4 xnext[8];
-      if constexpr (EPI == EPI_RESID) {     // prefetch the next chunk's residual while this one is processed
-        if (valid && c + 32 < c_begin + HALF) {
-          const float4* o = reinterpret_cast<const float4*>(static_cast<const float*>(g.out) + orow * g.ldo + n0 + 32);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) xnext[j] = o[j];
-        }
-      }
       float v[32];
       if (g.bias) load_bias32(g.bias + n0, v);
       else {
@@ -205,15 +189,11 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int m_blk, int n_b
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
       }
-      if (valid) {
-        if (EPI == EPI_RESID || g.out_dtype == ZV_F32) {
+      if (keep) {
+        if (g.out_dtype == ZV_F32) {
           float4* o = reinterpret_cast<float4*>(static_cast<float*>(g.out) + orow * g.ldo + n0);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 x = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            if constexpr (EPI == EPI_RESID) { x.x += xprev[j].x; x.y += xprev[j].y; x.z += xprev[j].z; x.w += xprev[j].w; }
-            o[j] = x;
-          }
+          for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         } else {
           uint4 pk[4];
 #pragma unroll
@@ -243,8 +223,8 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int m_blk, int n_b
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int rw = 8 * i + (ln >> 2);
-            if (row_base + rw < g.M) {
-              const int64_t dr = (int64_t)__ldg(g.scatter + row_base + rw);
+            const int64_t dr = row_base + rw < g.M ? (int64_t)__ldg(g.scatter + row_base + rw) : -1;
+            if (dr >= 0) {                 // dr < 0: a destination row the caller's index put out of range (dropped)
               const uint4 val = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(xpose) + rw * 80 + piece * 16);
               *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(g.out) + dr * g.ldo + n0 + piece * 8) = val;
               for (int p = 0; p < g.n_peers; ++p)
@@ -253,10 +233,6 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int m_blk, int n_b
           }
           __syncwarp();
         }
-      }
-      if constexpr (EPI == EPI_RESID) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) xprev[j] = xnext[j];
       }
     }
   } else if constexpr (EPI == EPI_SWIGLU) {
@@ -575,16 +551,6 @@ int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int
   return make_tmap_2d(tm, base, rows, cols, ld, BK, box_rows, 128, f16);
 }
 
-int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return n;
-}
-
 template <int BN, int EPI, int CG>
 int launch(const GemmArgs& g, const void* a, int64_t lda, const void* b, int64_t ldb, cudaStream_t stream) {
   using C = Cfg<BN, CG, EPI>;
@@ -594,11 +560,12 @@ int launch(const GemmArgs& g, const void* a, int64_t lda, const void* b, int64_t
   if (rc) return rc;
   rc = make_tmap(&tb, b, g.N, g.K, ldb, C::kBRows, g.op_f16 != 0);
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<uint64_t> attr_set{0};
+  const int dev = current_device();
+  if (device_needs_setup(attr_set, dev)) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc<BN, EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) return fail(ZV_ECUDA, "gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
+    mark_device(attr_set, dev);
   }
   const int tiles = ((g.M + BM * CG - 1) / (BM * CG)) * (g.N / BN);
   const int slots = num_sms() / CG;
@@ -615,6 +582,9 @@ int launch(const GemmArgs& g, const void* a, int64_t lda, const void* b, int64_t
   cfg.numAttrs = 1;
   cudaError_t e;
   {
+    static const char* const kNames[] = {"zv:K2 gemm store", "zv:K2 gemm qkv+rope", "zv:K2 gemm residual", "zv:K2 gemm swiglu",
+                                         "zv:K2 gemm gelu", "zv:K2 gemm scatter"};
+    NvtxRange nvtx(kNames[EPI]);
     KernelTimer timer(KC_GEMM_STORE + EPI, stream);
     e = cudaLaunchKernelEx(&cfg, gemm_tc<BN, EPI, CG>, ta, tb, g);
   }
@@ -651,8 +621,8 @@ int make_tmap_2d(void* tm_, const void* base, int64_t rows, int64_t cols, int64_
 int gemm(int epi, const GemmArgs& g, const void* a, int64_t lda, const void* b, int64_t ldb, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return fail(ZV_EINVAL, "gemm: empty problem %dx%dx%d", g.M, g.N, g.K);
-  static const bool pair = std::getenv("ZV_GEMM_1CTA") == nullptr;     // debug switch: single-CTA kernels everywhere
-  if (!pair) {
+#ifdef ZV_DEBUG_GEMM_1CTA               // compile-time debug build: single-CTA kernels everywhere
+  {
     switch (epi) {
       case EPI_STORE:
         return g.N % 256 == 0 ? launch<256, EPI_STORE, 1>(g, a, lda, b, ldb, stream)
@@ -664,6 +634,7 @@ int gemm(int epi, const GemmArgs& g, const void* a, int64_t lda, const void* b, 
       case EPI_SCATTER: return launch<256, EPI_SCATTER, 1>(g, a, lda, b, ldb, stream);
     }
   }
+#endif
   switch (epi) {
     case EPI_STORE:
       return g.N % 256 == 0 ? launch<256, EPI_STORE, 2>(g, a, lda, b, ldb, stream)

@@ -578,17 +578,17 @@ int build_layout(int32_t n, const int32_t* crop_box, const int32_t* resized_hw, 
 // grid of a persistent kernel: every CTA slot of the GPU, or one CTA per item when there are fewer items
 template <typename K>
 int persistent_grid(K kernel, int smem, int64_t n_items) {
-  int dev = 0, sms = 148, per_sm = 1;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int per_sm = 1;
+  const int sms = zv::num_sms();
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
   return (int)std::min<int64_t>(n_items, (int64_t)sms * per_sm);
 }
 template <int NW>
 void launch_hfast(int n_items, cudaStream_t s, const K1Crop* d, const int4* items, const int32_t* coef, uint8_t* ws, int seg_words) {
   const int smem = kHRows * 3 * seg_words * 4 + 2 * kHRows * ((seg_words * 12 + 32 + 15) & ~15);
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(k1_hpass_fast<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+  static std::atomic<uint64_t> attr{0};
+  const int dev = zv::current_device();
+  if (zv::device_needs_setup(attr, dev)) { cudaFuncSetAttribute(k1_hpass_fast<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); zv::mark_device(attr, dev); }
   k1_hpass_fast<NW><<<persistent_grid(k1_hpass_fast<NW>, smem, n_items), 256, smem, s>>>(d, items, n_items, coef, ws, seg_words);
 }
 inline int vfast_smem(int nw, int tile_quads, int out_bytes) {
@@ -598,8 +598,9 @@ template <int NW, typename OutT>
 void launch_vfast(int n_items, cudaStream_t s, const K1Crop* d, const int4* items, const int32_t* coef, const uint8_t* ws,
                   const float* lut, OutT* out, int row_order, int wsz, int tile_quads) {
   const int smem = vfast_smem(NW, tile_quads, (int)sizeof(OutT));
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(k1_vpass_fast<NW, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+  static std::atomic<uint64_t> attr{0};
+  const int dev = zv::current_device();
+  if (zv::device_needs_setup(attr, dev)) { cudaFuncSetAttribute(k1_vpass_fast<NW, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); zv::mark_device(attr, dev); }
   k1_vpass_fast<NW, OutT><<<persistent_grid(k1_vpass_fast<NW, OutT>, smem, n_items), 256, smem, s>>>(
       d, items, n_items, coef, ws, lut, out, row_order, wsz, tile_quads);
 }
@@ -635,6 +636,7 @@ int zv_preprocess(const zv_cfg* cfg, int32_t n, const uint8_t* const* src_dev, c
                   const int64_t* row_off, void* out_dev, int32_t out_dtype, int32_t row_order, void* workspace_dev,
                   int64_t workspace_bytes, void* stream_) {
   zv::reset_launch_count();
+  zv::NvtxRange nvtx_k1("zv:K1 crop+resize+normalize+patchify");
   if (!cfg || n <= 0 || !src_dev || !src_hw || !src_pitch || !crop_box || !resized_hw || !out_dev || !workspace_dev)
     return zv::fail(ZV_EINVAL, "zv_preprocess: null argument");
   if (cfg->patch != 14 || cfg->merge != 2 || cfg->temporal != 2)
@@ -653,7 +655,11 @@ int zv_preprocess(const zv_cfg* cfg, int32_t n, const uint8_t* const* src_dev, c
   // host image of [descriptors | LUT | coefficient tables | launch lists]
   std::vector<uint8_t> host((size_t)L.off_tmp, 0);
   K1Crop* d = reinterpret_cast<K1Crop*>(host.data() + L.off_desc);
-  const bool generic_only = std::getenv("ZV_K1_GENERIC") != nullptr;    // debug: force the per-tap kernels
+#ifdef ZV_DEBUG_K1_GENERIC              // compile-time debug build: force the per-tap kernels
+  const bool generic_only = true;
+#else
+  const bool generic_only = false;
+#endif
   std::vector<int32_t> seg_h(n, 0), tq_v(n, 0);
   int64_t row = 0;
   for (int32_t i = 0; i < n; ++i) {

@@ -1,6 +1,7 @@
 // Optional per-kernel-class device timing (CUDA events on the launching stream), used by bench.py to report
 // the roofline of each kernel class from inside the timed region.  Off by default: zero overhead.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <mutex>
 #include <vector>
@@ -21,6 +22,24 @@ cudaEvent_t get_event() {
   return e;
 }
 }  // namespace
+
+int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev;
+}
+int num_sms() {
+  static std::atomic<int> cache[64];
+  const int dev = current_device() & 63;
+  int n = cache[dev].load(std::memory_order_relaxed);
+  if (!n) {
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cache[dev].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
+NvtxRange::NvtxRange(const char* name) { nvtxRangePushA(name); }
+NvtxRange::~NvtxRange() { nvtxRangePop(); }
 
 KernelTimer::KernelTimer(int cls, void* stream) : stream_(stream), idx_(-1) {
   if (!g_on) return;

@@ -19,7 +19,6 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
-#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -119,10 +118,14 @@ __global__ void __launch_bounds__(256) gather_kernel(const SrcT* __restrict__ sr
 
 // LM hand-off: comp[i] = dest[widx[i]] - the inputs_embeds row of the embedding the merger computes at window
 // position i (widx: window position -> HF merge-group index; dest: HF embedding index -> placeholder row).
+// A destination outside [0, rows) becomes -1: the scatter epilogue drops that row instead of storing out of bounds.
 __global__ void __launch_bounds__(256) compose_rows_kernel(const int64_t* __restrict__ dest, const int32_t* __restrict__ widx,
-                                                           int32_t* __restrict__ comp, int64_t n) {
+                                                           int32_t* __restrict__ comp, int64_t n, int64_t rows) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) comp[i] = (int32_t)dest[widx[i]];
+  if (i < n) {
+    const int64_t d = dest[widx[i]];
+    comp[i] = (d >= 0 && d < rows) ? (int32_t)d : -1;
+  }
 }
 
 // Weight import: dst[row_map(r)][c] = src[r][c] (to bf16 or f32).  mode 0 identity, 1 gate, 2 up
@@ -378,7 +381,7 @@ int visual_forward_impl(const zv_cfg* cfg, const void* weights_dev, const zv_pla
                         const void* patches_dev, int32_t in_dtype, int32_t in_order, void* merged_out_dev,
                         int32_t out_dtype, void* hidden_out_dev, void* workspace_dev, int64_t workspace_bytes,
                         void* const* peer_out_dev, int32_t n_peers, int64_t peer_row_off, const int64_t* dest_rows_dev,
-                        void* stream);
+                        int64_t dest_rows_limit, void* stream);
 }
 
 int zv_visual_forward(const zv_cfg* cfg, const void* weights_dev, const zv_plan* p, const void* plan_dev,
@@ -386,7 +389,7 @@ int zv_visual_forward(const zv_cfg* cfg, const void* weights_dev, const zv_plan*
                       int32_t out_dtype, void* hidden_out_dev, void* workspace_dev, int64_t workspace_bytes,
                       void* stream) {
   return visual_forward_impl(cfg, weights_dev, p, plan_dev, patches_dev, in_dtype, in_order, merged_out_dev, out_dtype,
-                             hidden_out_dev, workspace_dev, workspace_bytes, nullptr, 0, 0, nullptr, stream);
+                             hidden_out_dev, workspace_dev, workspace_bytes, nullptr, 0, 0, nullptr, 0, stream);
 }
 
 int zv_visual_forward_into(const zv_cfg* cfg, const void* weights_dev, const zv_plan* p, const void* plan_dev,
@@ -396,7 +399,7 @@ int zv_visual_forward_into(const zv_cfg* cfg, const void* weights_dev, const zv_
   if (!dest_rows_dev || !embeds_dev) return fail(ZV_EINVAL, "zv_visual_forward_into: null argument");
   if (embeds_rows <= 0 || embeds_rows > INT32_MAX) return fail(ZV_EINVAL, "zv_visual_forward_into: inputs_embeds has %lld rows (1 .. 2^31-1 supported)", (long long)embeds_rows);
   return visual_forward_impl(cfg, weights_dev, p, plan_dev, patches_dev, in_dtype, in_order, embeds_dev, embeds_dtype,
-                             nullptr, workspace_dev, workspace_bytes, nullptr, 0, 0, dest_rows_dev, stream);
+                             nullptr, workspace_dev, workspace_bytes, nullptr, 0, 0, dest_rows_dev, embeds_rows, stream);
 }
 
 int zv_visual_forward_gather(const zv_cfg* cfg, const void* weights_dev, const zv_plan* p, const void* plan_dev,
@@ -406,7 +409,7 @@ int zv_visual_forward_gather(const zv_cfg* cfg, const void* weights_dev, const z
   if (n_peers < 0 || n_peers > 8 || (n_peers > 0 && !peer_out_dev)) return fail(ZV_EINVAL, "zv_visual_forward_gather: bad peer list");
   if (n_peers > 0 && out_dtype == ZV_F32) return fail(ZV_EINVAL, "zv_visual_forward_gather: the fused gather writes 16-bit embeddings");
   return visual_forward_impl(cfg, weights_dev, p, plan_dev, patches_dev, in_dtype, in_order, merged_out_dev, out_dtype,
-                             nullptr, workspace_dev, workspace_bytes, peer_out_dev, n_peers, peer_row_off, nullptr, stream);
+                             nullptr, workspace_dev, workspace_bytes, peer_out_dev, n_peers, peer_row_off, nullptr, 0, stream);
 }
 
 namespace {
@@ -414,8 +417,9 @@ int visual_forward_impl(const zv_cfg* cfg, const void* weights_dev, const zv_pla
                         const void* patches_dev, int32_t in_dtype, int32_t in_order, void* merged_out_dev,
                         int32_t out_dtype, void* hidden_out_dev, void* workspace_dev, int64_t workspace_bytes,
                         void* const* peer_out_dev, int32_t n_peers, int64_t peer_row_off, const int64_t* dest_rows_dev,
-                        void* stream) {
+                        int64_t dest_rows_limit, void* stream) {
   reset_launch_count();
+  NvtxRange nvtx_tower("zv:tower");
   int rc = check_cfg(cfg, "zv_visual_forward");
   if (rc) return rc;
   if (!weights_dev || !p || !plan_dev || !patches_dev || !merged_out_dev || !workspace_dev)
@@ -442,8 +446,11 @@ int visual_forward_impl(const zv_cfg* cfg, const void* weights_dev, const zv_pla
   float* X = reinterpret_cast<float*>(ws + W.x);
   void* Y = ws + W.y;
   void* BIG = ws + W.big;
-  int64_t launches = 0;
-  const bool legacy_full = std::getenv("ZV_ATTN_LEGACY") != nullptr;   // debug: mma.sync kernel for the full layers too
+#ifdef ZV_DEBUG_ATTN_LEGACY             // compile-time debug build: mma.sync kernel for the full layers too
+  const bool legacy_full = true;
+#else
+  const bool legacy_full = false;
+#endif
 #define ZV_TRY(expr) do { rc = (expr); if (rc) return rc; } while (0)
 
   // patches -> bf16, window order
@@ -514,7 +521,7 @@ int visual_forward_impl(const zv_cfg* cfg, const void* weights_dev, const zv_pla
   if (dest_rows_dev) {
     // LM hand-off (HF :1301-1307 masked_scatter): the un-reorder and the scatter into inputs_embeds are one index map
     int32_t* comp = reinterpret_cast<int32_t*>(ws + W.comp);
-    compose_rows_kernel<<<(unsigned)((T + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dest_rows_dev, d_widx, comp, T);
+    compose_rows_kernel<<<(unsigned)((T + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dest_rows_dev, d_widx, comp, T, dest_rows_limit);
     count_launch();
     g.scatter = comp;
   }
@@ -522,7 +529,6 @@ int visual_forward_impl(const zv_cfg* cfg, const void* weights_dev, const zv_pla
   for (int i = 0; i < n_peers; ++i) g.peers[i] = peer_out_dev[i];
   ZV_TRY(gemm(EPI_SCATTER, g, BIG, 4 * H, wb + L.w2, 4 * H, stream));
 #undef ZV_TRY
-  (void)launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(ZV_ECUDA, "zv_visual_forward: %s", cudaGetErrorString(e));
   return ZV_OK;
@@ -546,7 +552,11 @@ int zv_attention(const void* qkv_dev, void* out_dev, int32_t heads, int32_t head
       tiles.push_back(cu_host[s]); tiles.push_back(cu_host[s + 1]);
     }
   int64_t S = cu_host[n_seg];
-  const bool use_tc = full && std::getenv("ZV_ATTN_LEGACY") == nullptr;
+#ifdef ZV_DEBUG_ATTN_LEGACY
+  const bool use_tc = false;
+#else
+  const bool use_tc = full;
+#endif
   const int64_t need = ((int64_t)tiles.size() * 4 + 255) / 256 * 256;
   if (work_bytes < need) return fail(ZV_ENOMEM, "zv_attention: work buffer %lld B < required %lld B", (long long)work_bytes, (long long)need);
   cudaError_t e = cudaMemcpyAsync(work_dev, tiles.data(), tiles.size() * 4, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream));

@@ -28,7 +28,7 @@ def install(model=None, processor=None, device=None, dtype=None):
         returns_struct = int(transformers.__version__.split(".")[0]) >= 5
         p = next(hf_visual.parameters())
         fv = FusedVisual.from_hf(hf_visual, device=device or (p.device if p.device.type == "cuda" else None),
-                                 dtype=dtype or (p.dtype if p.dtype in (torch.float32, torch.bfloat16, torch.float16) else torch.bfloat16),
+                                 dtype=dtype or (p.dtype if p.dtype in (torch.float32, torch.bfloat16, torch.float16) else torch.float16),
                                  return_pooling_output=returns_struct)
         owner.visual = fv
     if processor is not None:

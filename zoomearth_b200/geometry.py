@@ -7,6 +7,7 @@ Names, argument meaning and error behaviour follow the reference:
   smart_resize   HF models/qwen2_vl/image_processing_pil_qwen2_vl.py:57-83
 """
 import ctypes as C
+import math
 import re
 
 import numpy as np
@@ -30,7 +31,18 @@ def extract_bbox(completion_content, scale, integer_only=False):
 
 
 def cut_box(img_w, img_h, bbox, min_size=512):
-    b = (C.c_double * 4)(*[float(v) for v in bbox])
+    """The box ``cut_image(image, bbox, min_size)`` crops (infer.py:41-76).  Like the reference's
+    ``x1, y1, x2, y2 = map(int, bbox)``: anything but four numbers raises ValueError, a NaN raises ValueError and an
+    infinity OverflowError (what ``int()`` raises)."""
+    vals = [float(v) for v in bbox]
+    if len(vals) != 4:
+        raise ValueError(f"{'too many values to unpack (expected 4)' if len(vals) > 4 else f'not enough values to unpack (expected 4, got {len(vals)})'}")
+    for v in vals:
+        if math.isnan(v):
+            raise ValueError("cannot convert float NaN to integer")
+        if math.isinf(v):
+            raise OverflowError("cannot convert float infinity to integer")
+    b = (C.c_double * 4)(*vals)
     out = (C.c_int32 * 4)()
     _lib.check(_lib.lib().zv_cut_box(int(img_w), int(img_h), b, int(min_size), out))
     return tuple(out)

@@ -53,7 +53,19 @@ def _to_u8_hwc(image):
     if not isinstance(image, torch.Tensor):
         raise TypeError(f"unsupported image type {type(image)}")
     if image.dtype != torch.uint8:
-        raise TypeError("FusedImageProcessor takes uint8 pixels (PIL RGB, or uint8 arrays); got " + str(image.dtype))
+        # HF's PIL backend (image_transforms.py:127-151,196-202) takes any array whose values are whole numbers in
+        # [0, 255] and casts it to uint8; arrays of floats in [0, 1] go through a rescale round trip there that the
+        # reference never exercises (it feeds PIL images) - not part of the fused path
+        f = image.to(torch.float64)
+        if not torch.equal(f, f.round()):
+            if bool((f >= 0).all()) and bool((f <= 1).all()):
+                raise NotImplementedError("float images in [0, 1] are not part of the fused path; pass uint8 pixels")
+            raise ValueError("The image to be converted to a PIL image contains values outside the range [0, 1], "
+                             f"got [{f.min().item()}, {f.max().item()}] which cannot be converted to uint8.")
+        if bool((f < 0).any()) or bool((f > 255).any()):
+            raise ValueError("The image to be converted to a PIL image contains values outside the range [0, 255], "
+                             f"got [{f.min().item()}, {f.max().item()}] which cannot be converted to uint8.")
+        image = image.to(torch.uint8)
     if image.ndim == 2:
         image = image[..., None].expand(-1, -1, 3)
     if image.ndim != 3:
@@ -151,7 +163,8 @@ class FusedImageProcessor:
         elif apply_cut_image:
             crop, rhw, grid = geometry.geometry(cfg, img_hw, np.asarray(boxes, np.float64))
         else:
-            bx = np.asarray(boxes, np.int64).reshape(n, 4)
+            # final crop boxes, PIL.Image.crop semantics: int(round(v)) with Python's round-half-even
+            bx = np.rint(np.asarray(boxes, np.float64)).astype(np.int64).reshape(n, 4)
             cfg0 = self._cfg(min_pixels, max_pixels)
             cfg0.min_size = -1                     # boxes are final crop boxes: no cut_image rule
             crop, rhw, grid = geometry.geometry(cfg0, img_hw, bx.astype(np.float64))

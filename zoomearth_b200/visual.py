@@ -27,13 +27,15 @@ def _vision_cfg_from_hf(config):
 
 
 class FusedVisual(nn.Module):
-    def __init__(self, state_dict, device=None, dtype=torch.bfloat16, operand_dtype=None,
+    def __init__(self, state_dict, device=None, dtype=torch.float16, operand_dtype=None,
                  return_pooling_output=False, **cfg_overrides):
         """state_dict: HF names relative to the tower (``visual.`` / ``model.visual.`` prefixes are accepted).
-        ``dtype`` is the dtype of the returned embeddings (what callers read as ``visual.dtype``).
-        ``operand_dtype`` is the 16-bit type of the GEMM / attention operands: bfloat16 (default) or float16 (the
-        dtype the reference's eval loop loads the model in, src/eval/infer.py:149; 8x smaller rounding error).
-        Default: float16 when ``dtype`` is float16, else bfloat16.  Accumulation and the residual stream are fp32."""
+        ``dtype`` is the dtype of the returned embeddings (what callers read as ``visual.dtype``); default float16,
+        the dtype the reference's eval loop loads the model in (src/eval/infer.py:149).
+        ``operand_dtype`` is the 16-bit type of the GEMM / attention operands: float16 (default: 11-bit mantissa,
+        max rel err 1.4e-3 against the fp32 tower at full depth) or bfloat16 (opt-in: 8x the rounding error, 1.15e-2,
+        outside the 1e-2 tolerance north_star states - same tensor-core rate).  Accumulation, RMSNorm, rotary, softmax
+        and the residual stream are fp32 either way."""
         super().__init__()
         if not torch.cuda.is_available():
             raise RuntimeError("FusedVisual needs a CUDA device (sm_100); there is no CPU fallback")
@@ -42,7 +44,7 @@ class FusedVisual(nn.Module):
         if dtype not in _DT:
             raise ValueError("FusedVisual returns float32, bfloat16 or float16 embeddings")
         if operand_dtype is None:
-            operand_dtype = torch.float16 if dtype == torch.float16 else torch.bfloat16
+            operand_dtype = torch.float16
         if operand_dtype not in (torch.bfloat16, torch.float16):
             raise ValueError("operand_dtype must be torch.bfloat16 or torch.float16")
         self.operand_dtype = operand_dtype
@@ -61,7 +63,7 @@ class FusedVisual(nn.Module):
     def from_hf(cls, hf_visual, **kw):
         """Build from an instantiated HF vision tower (weights are read from its state_dict)."""
         cfg = _vision_cfg_from_hf(hf_visual.config)
-        kw.setdefault("dtype", torch.bfloat16)
+        kw.setdefault("dtype", torch.float16)
         return cls(hf_visual.state_dict(), **cfg, **kw)
 
 
@@ -144,7 +146,10 @@ class FusedVisual(nn.Module):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._forward_impl(x, plan, window_order, False, None, 0, out=out)
-            ent = (g, x, out, self._ws)          # the workspace captured in the graph must stay alive
+            # everything the captured kernels point at must outlive the graph: the workspace, and the plan with its
+            # device tables (rotary ids, rope table, window index, attention tiles) - the plan LRU may evict the plan
+            # long before the graph is replayed again
+            ent = (g, x, out, self._ws, plan, plan._dev)
             self._graphs[key] = ent
             if len(self._graphs) > 16:
                 self._graphs.popitem(last=False)
@@ -159,17 +164,19 @@ class FusedVisual(nn.Module):
             x = hidden_states
             if x.dtype not in _DT or (x.dtype != torch.float32 and x.dtype != self.operand_dtype):
                 x = x.float()
-            g, xin, out, _ = self.graph_buffers(grid_thw, x.dtype, window_order)
+            g, xin, out = self.graph_buffers(grid_thw, x.dtype, window_order)[:3]
             if x.data_ptr() != xin.data_ptr():
                 xin.copy_(x, non_blocking=True)
             g.replay()
             self.last_launches = 1
-            return out
+            # `out` is the graph's static buffer: the next replay for this grid overwrites it, so hand out a copy
+            # (0.3 MB for a 512-px crop) unless the caller asked for the buffer itself
+            return out if kwargs.get("graph_static_output") else out.clone()
         plan = self.plan_for(grid_thw)
         return self._forward_impl(hidden_states, plan, window_order, return_hidden, gather, gather_row)
 
     @torch.no_grad()
-    def forward_into(self, inputs_embeds, dest_rows, hidden_states, grid_thw, window_order=False):
+    def forward_into(self, inputs_embeds, dest_rows, hidden_states, grid_thw, window_order=False, validate_rows=True):
         """Tower forward with the LM hand-off fused into the last GEMM (``zv_visual_forward_into``): embedding k (HF
         order) lands in row ``dest_rows[k]`` of the flattened ``inputs_embeds`` (B, L, out_hidden) - in place, the
         result of ``inputs_embeds.masked_scatter(image_mask, self(hidden_states, grid_thw))`` (HF modeling_qwen2_5_vl.py
@@ -182,6 +189,11 @@ class FusedVisual(nn.Module):
                              f"tensor on {self._device}")
         if dest_rows.dtype != torch.int64 or dest_rows.device != self._device or dest_rows.numel() != plan.num_tokens:
             raise ValueError(f"dest_rows must be {plan.num_tokens} int64 row indices on {self._device}")
+        n_rows = e.numel() // e.shape[-1]
+        if validate_rows and dest_rows.numel():
+            lo, hi = torch.aminmax(dest_rows)                         # one host sync; the kernel also drops bad rows
+            if int(lo) < 0 or int(hi) >= n_rows:
+                raise IndexError(f"dest_rows spans [{int(lo)}, {int(hi)}] but inputs_embeds has {n_rows} rows")
         x = self._check_input(hidden_states, plan, window_order)
         stream = torch.cuda.current_stream(self._device).cuda_stream
         with torch.cuda.device(self._device):
@@ -190,7 +202,7 @@ class FusedVisual(nn.Module):
             _lib.check(lib.zv_visual_forward_into(
                 C.byref(self.cfg), self.packed_weights.data_ptr(), plan.handle, tables.data_ptr(), x.data_ptr(),
                 _DT[x.dtype], _lib.ORDER_WINDOW if window_order else _lib.ORDER_HF, e.data_ptr(),
-                e.numel() // e.shape[-1], _DT[e.dtype], dest_rows.contiguous().data_ptr(), ws.data_ptr(), ws.numel(), stream))
+                n_rows, _DT[e.dtype], dest_rows.contiguous().data_ptr(), ws.data_ptr(), ws.numel(), stream))
         self.last_launches = lib.zv_last_launch_count()
         return inputs_embeds
 
