@@ -7,7 +7,7 @@
 
 Workload = BASELINE.json configs[1]: "Global view: 64 synthetic 5000x5000 images downscaled to
 max_pixels=1280*28*28" -> per image 980x980, grid (1,70,70), 4900 patches, 1225 vision tokens.  One step =
-one pass of the hot path over that batch: zv_preprocess (K1, bf16 patches in window order) then
+one pass of the hot path over that batch: zv_preprocess (K1, fp16 patches in window order) then
 zv_visual_forward (32-block tower + merger), random-init Qwen2.5-VL-3B vision weights, synthetic pixels.
 
 `value`   : tokens/s with the uint8 images already resident in HBM (device-timed, CUDA events, max over ranks).
@@ -36,12 +36,17 @@ sys.path.insert(0, ROOT)
 IMG = 5000
 MAX_PIXELS = 1280 * 28 * 28
 MIN_PIXELS = 56 * 56
-# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the four per-block GEMMs at this exact
-# workload (64 images, M = 313 600), from the ncu capture committed as profiles/r01_ncu_traffic_gemm_64img.csv
-NCU_TRAFFIC_GB = {"gemm_qkv": 3.20, "gemm_proj": 4.97, "gemm_swiglu": 3.23, "gemm_down": 6.86}
-# DRAM bytes per image of k1_hpass_fast<7> + k1_vpass_fast<7> (ncu, 8-image launch, profiles/r01_ncu_k1_summary.txt):
-# (608.8 + 108.3 + 118.0 + 53.8) MB / 8; algorithmic 86.52 MB - the uint8 intermediate (14.7 MB/image) makes one round trip
-NCU_K1_TRAFFIC_PER_IMAGE = 111.1e6
+# DRAM traffic of the dominant kernels (ncu dram__bytes_read.sum + dram__bytes_write.sum per launch at this workload) is
+# NOT typed in here: tools/ncu_traffic.py turns the ncu CSV of the current tree into profiles/ncu_traffic.json (with the
+# commit it was captured at) and this file is read at run time; without it the `traffic` fields are null.
+def ncu_traffic():
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
+
+
 WORKLOAD = ("BASELINE configs[1]: global view, 64 synthetic 5000x5000 uint8 images -> max_pixels=1280*28*28 "
             "(980x980, grid 1x70x70, 1225 tokens/image) -> Qwen2.5-VL-3B vision tower (random init)")
 KCLASS = {"k1_hpass": 0, "k1_vpass": 1, "gemm_store": 2, "gemm_qkv": 3, "gemm_resid": 4, "gemm_swiglu": 5,
@@ -137,8 +142,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = max(1, args.ref_images)
-    best = None
+    # bounded sample of the workload per step (4 items), shrunk so that K steps stay within a few minutes
+    # (one 5000x5000 image takes ~4 s of the reference's CPU path on 16 cores)
+    sample = max(1, min(args.ref_images, 48 // max(1, args.steps)))
     for _ in range(max(0, args.warmup if args.warmup < 2 else 1)):
         reference_step(1)
     times = []
@@ -161,6 +167,28 @@ def run_reference(args):
         "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+def zoom_step_latency(visual, dev, reps=30):
+    """The reference's own regime (infer.py:17 BATCH_SIZE = 1): one 512-px zoom crop (324 tokens) and four crops of
+    512-1024 px, each as one call of the public fast path with CUDA-graph replay of the tower; wall clock per call."""
+    from zoomearth_b200 import FusedImageProcessor, ZoomEncoder
+    enc = ZoomEncoder(visual, FusedImageProcessor(min_pixels=3136, max_pixels=128 * 128 * 28 * 28, device=dev))
+    img = torch.randint(0, 256, (IMG, IMG, 3), dtype=torch.uint8, device=dev)
+    out = {}
+    for name, boxes in (("one_512px_zoom_step_ms", [(2000, 2000, 2512, 2512)]),
+                        ("four_crops_512_to_1024px_ms", [(100, 100, 612, 612), (900, 900, 1700, 1500), (2000, 100, 3024, 1124),
+                                                        (3000, 3000, 3700, 3600)])):
+        for _ in range(5):
+            enc.encode([img], boxes, image_index=[0] * len(boxes), use_graph=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            emb, _, _ = enc.encode([img], boxes, image_index=[0] * len(boxes), use_graph=True)
+        torch.cuda.synchronize()
+        out[name] = (time.perf_counter() - t0) / reps * 1e3
+        out[name.replace("_ms", "_tokens")] = int(emb.shape[0])
+    return out
 
 
 # ------------------------------------------------------------------------------------------- our arm (CUDA)
@@ -189,7 +217,8 @@ def run_ours(args):
     pk = peaks()
 
     sd = random_vision_state_dict(0, device=dev)
-    visual = FusedVisual(sd, device=dev, dtype=torch.float16)
+    op_dtype = torch.float16 if args.operand_dtype == "fp16" else torch.bfloat16
+    visual = FusedVisual(sd, device=dev, dtype=op_dtype, operand_dtype=op_dtype)
     del sd
     enc = ZoomEncoder(visual, FusedImageProcessor(min_pixels=MIN_PIXELS, max_pixels=MAX_PIXELS, device=dev))
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -203,7 +232,7 @@ def run_ours(args):
         if not args.nccl_gather:
             try:
                 from zoomearth_b200.sharding import PeerGather
-                pg = PeerGather(world * tokens_step, 2048, torch.float16, dev)
+                pg = PeerGather(world * tokens_step, 2048, op_dtype, dev)
                 gather_kind = "fused: merger GEMM epilogue stores into every rank's buffer over NVLink (symmetric memory)"
             except Exception as e:          # symmetric memory unavailable on this box: the NCCL collective still gathers
                 pg = None
@@ -234,6 +263,20 @@ def run_ours(args):
     for _ in range(max(3, args.warmup)):
         step()
     barrier()
+    gather_check = None
+    if world > 1:
+        # correctness of the data path being timed: what step() leaves on every rank must be, bit for bit, NCCL's
+        # all_gather_into_tensor of the per-rank embeddings (checked once, outside the timed region)
+        got = step().clone()
+        barrier()
+        emb, _, _ = enc.encode(images, None)
+        want = torch.empty((world * emb.shape[0], emb.shape[1]), dtype=emb.dtype, device=dev)
+        dist.all_gather_into_tensor(want, emb)
+        same = torch.tensor([1 if torch.equal(got, want) else 0], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        gather_check = bool(same.item())
+        del got, want, emb
+        barrier()
     sampler = ClockSampler(local)
     sampler.start()
     lib.zv_timing_reset()
@@ -280,7 +323,7 @@ def run_ours(args):
     if not args.no_e2e:
         n_e2e = min(n_img, args.e2e_images)
         host = [im.cpu().pin_memory() for im in images[:n_e2e]]
-        out_host = torch.empty((n_e2e * T_img, 2048), dtype=torch.float16).pin_memory()
+        out_host = torch.empty((n_e2e * T_img, 2048), dtype=op_dtype).pin_memory()
 
         def step_e2e():
             # H2D of this step's pixels and D2H of its embeddings, pipelined in chunks behind the compute
@@ -312,11 +355,16 @@ def run_ours(args):
                     "sample": f"{args.ref_images} of the {n_img} images of one step ({tokens} tokens, {dt:.1f} s): PIL crop + "
                               f"HF Qwen2VLImageProcessorPil + HF vision tower fp32 sdpa on {cores} threads"}
 
+    latency = None
+    if rank == 0 and world == 1 and not args.no_latency:
+        latency = zoom_step_latency(visual, dev)
+
+    traffic = ncu_traffic() or {}
     if rank == 0:
         line = {
             "metric": "vision tokens/s crop->patchify->ViT", "value": value, "unit": "tokens/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": args.operand_dtype, "data": "synthetic",
             "config": {"workload": WORKLOAD,
                        "images_per_step_per_gpu": n_img, "tokens_per_step_per_gpu": tokens_step,
                        "l2": "inputs larger than L2 (4.8 GB of pixels, 5.5 GB of activations per step)",
@@ -326,16 +374,14 @@ def run_ours(args):
             "roofline": {"bound": "tensor", "kernel": "gemm_tc (tcgen05, all epilogues)", "achieved": gemm_tf,
                          "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": gemm_tf / pk["tf_sust"],
                          "frac_of_burst": gemm_tf / pk["tf_burst"], "peak_source": pk["src"] + ", sustained",
-                         "traffic": (sum(NCU_TRAFFIC_GB.values()) * 32 / 128 * 1e9) if n_img == 64 else None,
-                         "traffic_note": "mean DRAM bytes per launch over the 128 per-block GEMM launches, ncu at this "
-                                         "workload (profiles/r01_ncu_traffic_gemm_64img.csv); algorithmic mean 4.3e9 (A + W + out, + X read-modify-write and the "
-                                         "16-bit copy for the residual GEMMs)",
+                         "traffic": traffic.get("gemm_bytes_per_launch") if n_img == 64 else None,
+                         "traffic_note": traffic.get("gemm_note", "no ncu capture of this tree under profiles/ncu_traffic.json"),
                          "launches": gemm_n, "ms_total": gemm_ms, "share_of_step": gemm_ms / ms},
             "roofline_k1": {"bound": "hbm", "kernel": "k1_hpass + k1_vpass", "achieved": k1_gbs, "peak": pk["hbm"],
                             "unit": "GB/s", "frac": k1_gbs / pk["hbm"], "ms_total": k1_ms, "share_of_step": k1_ms / ms,
-                            "traffic": NCU_K1_TRAFFIC_PER_IMAGE * n_img,
-                            "traffic_note": "hpass + vpass DRAM bytes per step (ncu per image x images); algorithmic "
-                                            f"{k1_bytes / 1e9:.2f} GB: the uint8 intermediate between the passes goes through DRAM once"},
+                            "traffic": (traffic.get("k1_bytes_per_image") * n_img) if traffic.get("k1_bytes_per_image") else None,
+                            "traffic_note": traffic.get("k1_note", "no ncu capture of this tree under profiles/ncu_traffic.json"),
+                            "algorithmic_bytes": k1_bytes},
             "roofline_attn": {"bound": "tensor", "kernel": "attn_tc_kernel (tcgen05, full layers) + attn_window_kernel (mma.sync, window layers)", "achieved": attn_tf,
                               "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": attn_tf / pk["tf_sust"],
                               "ms_total": attn_ms, "share_of_step": attn_ms / ms,
@@ -345,7 +391,10 @@ def run_ours(args):
             "tower_tflops": tower_tf,
             "kernel_ms": {k: round(v[0] / args.steps, 3) for k, v in cls.items()},
             "cpu_baseline": cpu_base,
+            "latency": latency,
         }
+        if gather_check is not None:
+            line["gather_check"] = gather_check
         if stdout_fd is not None:
             sys.stdout.flush()
             C.CDLL(None).fflush(None)           # NCCL's banner may still sit in the C stdio buffer of stdout
@@ -364,7 +413,10 @@ def main():
     ap.add_argument("--images", type=int, default=64, help="images per step per GPU (BASELINE configs[1]: 64)")
     ap.add_argument("--e2e-images", type=int, default=64)
     ap.add_argument("--e2e-chunk", type=int, default=8, help="images per pipelined upload/compute chunk in the e2e leg")
-    ap.add_argument("--ref-images", type=int, default=1, help="images in the CPU reference sample")
+    ap.add_argument("--ref-images", type=int, default=4, help="images in the CPU reference sample (BASELINE.md 3: 4 items)")
+    ap.add_argument("--operand-dtype", default="fp16", choices=["fp16", "bf16"],
+                    help="16-bit type of the GEMM / attention operands (fp16 = the shipped default; same tensor-core rate)")
+    ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--nccl-gather", action="store_true", help="gather embeddings with NCCL instead of the fused peer stores")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
