@@ -11,6 +11,11 @@
  *
  *   zv_cut_box            src/eval/infer.py:41-76   cut_image() box arithmetic (= src/demo.py:30-70)
  *   zv_resize_dims        src/eval/infer.py:78-85   resize_image() size arithmetic
+ *   zv_resize_dims_ex     resize_image() variants: src/demo.py:86-93 (1024), src/train/SFT.py:76-81 (always resizes),
+ *                         src/train/RL/.../open_r1/custom/customized_funcs.py:76-85 (min_scale = 30 / min side)
+ *   zv_cut_box_sft        src/train/SFT.py:83-125 cut_image() (else-branch: resize to min side 512 + centre crop)
+ *   zv_resize_u8          infer.py:72-75 + 78-85: PIL.Image.crop(box).resize((w, h), Image.BICUBIC) on the device, uint8 out
+ *                         (resize_image(cut_image(...)) of infer.py:215,239, demo.py:133,140) - feeds zv_preprocess
  *   zv_smart_resize       HF:models/qwen2_vl/image_processing_pil_qwen2_vl.py:57-83
  *   zv_geometry           infer.py:41-76 + HF smart_resize + grid computation (pil_qwen2_vl.py:186-187)
  *   zv_resample_*         Pillow ImagingResample coefficient tables (reached from infer.py:84,
@@ -67,7 +72,7 @@ typedef struct zv_cfg {
   int32_t inter;        /* 3420 */
   int32_t out_hidden;   /* 2048 */
   int32_t fullatt_mask_lo; /* bit l set = block l uses full attention (blocks 0..31) */
-  int32_t op_dtype;     /* GEMM / attention operand type: 0 or ZV_BF16 = bf16 (default), ZV_F16 = fp16 */
+  int32_t op_dtype;     /* GEMM / attention operand type: ZV_F16 = fp16 (zv_default_cfg), ZV_BF16 or 0 = bf16 (opt-in) */
   int64_t min_pixels;   /* 3136 */
   int64_t max_pixels;   /* per call site */
   double  rescale;      /* 1/255 */
@@ -84,6 +89,13 @@ ZV_API void zv_default_cfg(zv_cfg* cfg);
 /* ---------------------------------------------------------------- host geometry (pure, no device) */
 ZV_API int zv_cut_box(int32_t img_w, int32_t img_h, const double* bbox_xyxy, int32_t min_size, int32_t* box_out4);
 ZV_API int zv_resize_dims(int32_t w, int32_t h, int32_t max_size, int32_t* new_wh2, double* inv_scale);
+/* mode 0: infer.py / demo.py (resize only when scale < 1); 1: SFT.py (always, may upscale); 2: customized_funcs.py
+ * (scale = max(30 / min(w, h), max_size / max(w, h)), resize only when < 1).  new_wh2 = (w, h) after the resize. */
+ZV_API int zv_resize_dims_ex(int32_t w, int32_t h, int32_t max_size, int32_t mode, int32_t* new_wh2, double* inv_scale);
+/* SFT.py cut_image: box_out4 = the box Image.crop gets.  When both box sides are >= min_size the crop is then resized to
+ * resized_wh2 (shorter side = min_size) and centre_box4 (a min_size square inside it) is cut out; otherwise resized_wh2 = 0. */
+ZV_API int zv_cut_box_sft(int32_t img_w, int32_t img_h, const double* bbox_xyxy, int32_t min_size, int32_t* box_out4,
+                          int32_t* resized_wh2, int32_t* centre_box4);
 ZV_API int zv_smart_resize(int32_t height, int32_t width, int32_t factor, int64_t min_pixels, int64_t max_pixels,
                            int32_t* out_hw2);
 /* n crops: img_hw[n][2] (h,w), bbox_xyxy[n][4] -> crop_box[n][4] (x0,y0,x1,y1), resized_hw[n][2], grid_thw[n][3].
@@ -109,6 +121,16 @@ ZV_API int zv_preprocess(const zv_cfg* cfg, int32_t n, const uint8_t* const* src
                          const int64_t* src_pitch, const int32_t* crop_box, const int32_t* resized_hw,
                          const int64_t* row_off, void* out_dev, int32_t out_dtype, int32_t row_order,
                          void* workspace_dev, int64_t workspace_bytes, void* stream);
+
+/* Device form of the reference's resize_image(cut_image(...)): crop i = PIL.Image.crop(crop_box[i]) of image i (zero
+ * fill outside the image), resized with Pillow-exact bicubic to out_hw[i] = (h, w) and written as a plain (h, w, 3) uint8
+ * image at dst_dev[i] with row pitch dst_pitch[i] bytes.  Same-size axes are copied (Pillow skips the pass).  The result is
+ * bit-identical to Pillow and can be handed to zv_preprocess as a source image (the reference's two-resample flow:
+ * resize_image to <= 512 / 1024 px, then the processor's smart_resize, uint8 rounding in between). */
+ZV_API int64_t zv_resize_u8_workspace_bytes(int32_t n, const int32_t* crop_box, const int32_t* out_hw);
+ZV_API int zv_resize_u8(int32_t n, const uint8_t* const* src_dev, const int32_t* src_hw, const int64_t* src_pitch,
+                        const int32_t* crop_box, const int32_t* out_hw, uint8_t* const* dst_dev, const int64_t* dst_pitch,
+                        void* workspace_dev, int64_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------- plan: per-batch integer bookkeeping */
 typedef struct zv_plan zv_plan;

@@ -11,10 +11,10 @@ pytestmark = pytest.mark.gpu
 
 
 def _metrics(got, ref):
-    got, ref = got.float().cpu(), ref.float().cpu()
-    cos = torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0).item()
-    maxrel = ((got - ref).abs().max() / ref.abs().max()).item()
-    return cos, maxrel
+    """(cosine of the flattened tensors, max|a-b| / max|b|), accumulated in float64 (fp32 sums over 1e8 elements drift)."""
+    got, ref = got.detach().double().cpu().flatten(), ref.detach().double().cpu().flatten()
+    cos = (torch.dot(got, ref) / (got.norm() * ref.norm())).item()
+    return cos, ((got - ref).abs().max() / ref.abs().max()).item()
 
 
 def _fused(sd, cfg, cuda, dtype=torch.float32, operand_dtype=None):

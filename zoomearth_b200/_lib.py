@@ -43,6 +43,11 @@ _PROTOS = {
     "zv_default_cfg": (None, [_P(ZvCfg)]),
     "zv_cut_box": (C.c_int, [C.c_int32, C.c_int32, _P(C.c_double), C.c_int32, _P(C.c_int32)]),
     "zv_resize_dims": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P(C.c_int32), _P(C.c_double)]),
+    "zv_resize_dims_ex": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P(C.c_int32), _P(C.c_double)]),
+    "zv_cut_box_sft": (C.c_int, [C.c_int32, C.c_int32, _P(C.c_double), C.c_int32, _P(C.c_int32), _P(C.c_int32), _P(C.c_int32)]),
+    "zv_resize_u8_workspace_bytes": (C.c_int64, [C.c_int32, C.c_void_p, C.c_void_p]),
+    "zv_resize_u8": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                              C.c_void_p, C.c_int64, C.c_void_p]),
     "zv_smart_resize": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, _P(C.c_int32)]),
     "zv_geometry": (C.c_int, [_P(ZvCfg), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "zv_resample_ksize": (C.c_int32, [C.c_int32, C.c_int32]),

@@ -125,6 +125,7 @@ void zv_default_cfg(zv_cfg* c) {
   c->mean[0] = 0.48145466f; c->mean[1] = 0.4578275f; c->mean[2] = 0.40821073f;
   c->std[0] = 0.26862954f; c->std[1] = 0.26130258f; c->std[2] = 0.27577711f;
   c->eps = 1e-6f;
+  c->op_dtype = ZV_F16;      // the dtype the reference's eval loop runs in (infer.py:149); bf16 operands are opt-in
 }
 
 int zv_cut_box(int32_t img_w, int32_t img_h, const double* b, int32_t min_size, int32_t* out) {
@@ -159,6 +160,45 @@ int zv_resize_dims(int32_t w, int32_t h, int32_t max_size, int32_t* wh, double* 
     wh[0] = w; wh[1] = h;
   }
   if (inv_scale) *inv_scale = 1 / scale;
+  return ZV_OK;
+}
+
+// resize_image() variants of the reference: 0 infer.py:78-85 / demo.py:86-93, 1 SFT.py:76-81, 2 customized_funcs.py:76-85
+int zv_resize_dims_ex(int32_t w, int32_t h, int32_t max_size, int32_t mode, int32_t* wh, double* inv_scale) {
+  if (!wh || w <= 0 || h <= 0 || max_size <= 0) return fail(ZV_EINVAL, "zv_resize_dims_ex: bad argument");
+  if (mode < 0 || mode > 2) return fail(ZV_EINVAL, "zv_resize_dims_ex: mode %d (0 infer/demo, 1 SFT, 2 customized_funcs)", mode);
+  double scale = (double)max_size / (double)std::max(w, h);
+  if (mode == 2) {
+    const double min_scale = 30.0 / (double)std::min(w, h);      // customized_funcs.py:79-80
+    scale = std::max(min_scale, scale);
+  }
+  if (mode == 1 || scale < 1) {                                   // SFT.py resizes unconditionally (may upscale)
+    wh[0] = (int32_t)((double)w * scale);
+    wh[1] = (int32_t)((double)h * scale);
+  } else {
+    wh[0] = w; wh[1] = h;
+  }
+  if (inv_scale) *inv_scale = 1 / scale;
+  return ZV_OK;
+}
+
+// SFT.py:83-125 cut_image: small boxes take the 512-square rule of infer.py; boxes with both sides >= min_size are cropped,
+// resized so that the shorter side is min_size, and centre-cropped to min_size x min_size.
+int zv_cut_box_sft(int32_t img_w, int32_t img_h, const double* b, int32_t min_size, int32_t* box, int32_t* resized_wh,
+                   int32_t* center_box) {
+  if (!b || !box || !resized_wh || !center_box) return fail(ZV_EINVAL, "zv_cut_box_sft: null argument");
+  int rc = zv_cut_box(img_w, img_h, b, min_size, box);
+  if (rc) return rc;
+  const int64_t x1 = py_int(b[0]), y1 = py_int(b[1]), x2 = py_int(b[2]), y2 = py_int(b[3]);
+  resized_wh[0] = resized_wh[1] = 0;
+  center_box[0] = center_box[1] = center_box[2] = center_box[3] = 0;
+  if (x2 - x1 < min_size || y2 - y1 < min_size) return ZV_OK;   // the square branch: the crop is the result
+  const int32_t w = box[2] - box[0], h = box[3] - box[1];
+  const double scale = (double)min_size / (double)std::min(w, h);
+  const int32_t nw = (int32_t)((double)w * scale), nh = (int32_t)((double)h * scale);
+  resized_wh[0] = nw; resized_wh[1] = nh;
+  const int32_t left = (int32_t)floordiv(nw - min_size, 2), top = (int32_t)floordiv(nh - min_size, 2);
+  center_box[0] = left; center_box[1] = top; center_box[2] = left + min_size; center_box[3] = top + min_size;
   return ZV_OK;
 }
 

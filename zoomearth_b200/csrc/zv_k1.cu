@@ -41,7 +41,7 @@ namespace {
 
 constexpr int kPrecisionBits = 22;
 constexpr int kPatchElems = 1176;   // 3 * 2 * 14 * 14
-constexpr int kMaxNW = 10;          // fast path: taps <= 4 * kMaxNW - 3 = 37
+constexpr int kMaxNW = 12;          // fast path: taps <= 4 * kMaxNW - 3 = 45 (5000 px -> 512 px is 41 taps)
 constexpr int kHRows = 8;           // hpass_fast: source rows per CTA (two row quads)
 constexpr int kHCols = 128;         // hpass_fast: output columns per CTA
 
@@ -62,6 +62,8 @@ struct K1Crop {
   int32_t lh, lw;          // merge-group grid (gh/2, gw/2)
   int32_t fast;            // 1: tmp is row-quad packed (fast path), 0: plain rows
   int32_t pad_;
+  uint8_t* dst;            // uint8 output mode (zv_resize_u8): (oh, ow, 3) image, row pitch dst_pitch bytes
+  int64_t dst_pitch;
 };
 
 // Block -> (crop, local block) through the launch's own prefix array (crops of one kernel class only).
@@ -449,11 +451,70 @@ __global__ void __launch_bounds__(256) k1_vpass_fast(const K1Crop* __restrict__ 
   }
 }
 
+// ------------------------------------------------------------------------------------------------ uint8 output
+// zv_resize_u8: the vertical pass writes a plain (oh, ow, 3) uint8 image instead of normalised patches - the device form
+// of the reference's resize_image() (PIL.Image.resize(BICUBIC), infer.py:78-85), whose result feeds K1 as a source image.
+// Fast layout: item = (crop, first output row, rows <= 8); a warp owns one output row with its limb words in registers
+// and sweeps the row's (pixel, channel) columns; the row-quad words of the intermediate are dp4a operands as they lie.
+// The output is small next to the source (a 5000 x 5000 image becomes 512 x 512), so no staging is needed.
+template <int NW>
+__global__ void __launch_bounds__(256) k1_vpass_u8_fast(const K1Crop* __restrict__ crops, const int4* __restrict__ items,
+                                                        int n_items, const int32_t* __restrict__ coef,
+                                                        const uint8_t* __restrict__ ws) {
+  constexpr int kStride = 1 + 3 * NW;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+    const int4 item = __ldg(items + it);
+    if (warp >= item.z) continue;
+    const K1Crop& c = crops[item.x];
+    const int yy = item.y + warp;
+    const int qpitch = c.ow * 3;                                         // words per row quad = bytes per output row
+    const uint32_t* __restrict__ tmp = reinterpret_cast<const uint32_t*>(ws + c.tmp_off);
+    const int32_t* __restrict__ e = coef + c.off_lv + (int64_t)yy * kStride;
+    const int q0 = __ldg(e) - (c.ybox0 >> 2);
+    uint32_t l0[NW], l1[NW], l2[NW];
+#pragma unroll
+    for (int k = 0; k < NW; ++k) { l0[k] = __ldg(e + 1 + k); l1[k] = __ldg(e + 1 + NW + k); l2[k] = __ldg(e + 1 + 2 * NW + k); }
+    const uint32_t* __restrict__ base = tmp + (int64_t)q0 * qpitch;
+    uint8_t* __restrict__ drow = c.dst + (int64_t)yy * c.dst_pitch;
+#pragma unroll 2
+    for (int col = lane; col < qpitch; col += 32) {
+      int a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll
+      for (int k = 0; k < NW; ++k) {
+        const uint32_t v = __ldg(base + (int64_t)k * qpitch + col);
+        a0 = dp4a_uu(v, l0[k], a0);
+        a1 = dp4a_uu(v, l1[k], a1);
+        a2 = dp4a_us(v, l2[k], a2);
+      }
+      drow[col] = (uint8_t)finish8(a0, a1, a2);
+    }
+  }
+}
+
+// Per-tap form over the plain-row intermediate (more than 45 taps, or unaligned source rows): one thread = one output byte.
+__global__ void __launch_bounds__(256) k1_vpass_u8(const K1Crop* __restrict__ crops, const int32_t* __restrict__ ids,
+                                                   const int32_t* __restrict__ blk0, int n_cls,
+                                                   const int32_t* __restrict__ coef, const uint8_t* __restrict__ ws) {
+  const int slot = find_slot(blk0, n_cls, blockIdx.x);
+  const K1Crop c = crops[ids[slot]];
+  const int64_t tpitch = (int64_t)c.ow * 3;
+  const int64_t item = (int64_t)(blockIdx.x - blk0[slot]) * blockDim.x + threadIdx.x;
+  if (item >= (int64_t)c.oh * tpitch) return;
+  const int yy = (int)(item / tpitch), col = (int)(item % tpitch);
+  const int ymin = coef[c.off_bv + 2 * yy] - c.ybox0, cnt = coef[c.off_bv + 2 * yy + 1];
+  const int32_t* __restrict__ k = coef + c.off_kv + (int64_t)yy * c.ksv;
+  const uint8_t* __restrict__ p = ws + c.tmp_off + (int64_t)ymin * tpitch + col;
+  int acc = 1 << (kPrecisionBits - 1);
+  for (int t = 0; t < cnt; ++t) acc += (int)__ldg(p + (int64_t)t * tpitch) * __ldg(k + t);
+  c.dst[(int64_t)yy * c.dst_pitch + col] = (uint8_t)clip8(acc >> kPrecisionBits);
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 inline int nw_class(int ksize) {                   // words per tap window (<= 3 samples of misalignment + ksize taps)
   const int need = (ksize + 3 + 3) / 4;
-  for (int c : {2, 3, 4, 5, 7, 10}) if (need <= c) return c;
+  for (int c : {2, 3, 4, 5, 7, 10, 12}) if (need <= c) return c;
   return 0;
 }
 
@@ -473,15 +534,16 @@ struct Layout {
 constexpr int kItemsTarget = 148 * 8;        // aim for at least this many work items per launch
 
 // Workspace layout shared by zv_preprocess_workspace_bytes and zv_preprocess.
-int build_layout(int32_t n, const int32_t* crop_box, const int32_t* resized_hw, Layout* L, bool fill) {
+// u8_out: the vertical pass writes plain uint8 images (zv_resize_u8): any positive output size, row-group work items.
+int build_layout(int32_t n, const int32_t* crop_box, const int32_t* resized_hw, Layout* L, bool fill, bool u8_out = false) {
   L->tmp_off.resize(n); L->ybox0.resize(n); L->nrows.resize(n);
   int64_t coef_ints = 0, tmp_bytes = 0;
   for (int32_t i = 0; i < n; ++i) {
     const int32_t cw = crop_box[4 * i + 2] - crop_box[4 * i], ch = crop_box[4 * i + 3] - crop_box[4 * i + 1];
     const int32_t oh = resized_hw[2 * i], ow = resized_hw[2 * i + 1];
-    if (cw <= 0 || ch <= 0 || oh <= 0 || ow <= 0 || oh % 28 || ow % 28)
-      return zv::fail(ZV_EINVAL, "zv_preprocess: crop %d has extent %dx%d -> %dx%d (need >0 and multiples of 28)",
-                      i, cw, ch, ow, oh);
+    if (cw <= 0 || ch <= 0 || oh <= 0 || ow <= 0 || (!u8_out && (oh % 28 || ow % 28)))
+      return zv::fail(ZV_EINVAL, "%s: crop %d has extent %dx%d -> %dx%d (need >0%s)", u8_out ? "zv_resize_u8" : "zv_preprocess",
+                      i, cw, ch, ow, oh, u8_out ? "" : " and multiples of 28");
     const std::pair<int32_t, int32_t> keys[2] = {{cw, ow}, {ch, oh}};
     for (const auto& key : keys) {
       if (L->axis.count(key)) continue;
@@ -524,6 +586,7 @@ int build_layout(int32_t n, const int32_t* crop_box, const int32_t* resized_hw, 
           t.seg_words = std::max(t.seg_words, w0[o1] + t.nw - w0[o0]);
         }
         for (int32_t o0 = 0; o0 + 27 < key.second; o0 += 28) t.tile_quads = std::max(t.tile_quads, w0[o0 + 27] + t.nw - w0[o0]);
+        if (t.tile_quads == 0) t.tile_quads = 1;            // outputs shorter than 28 (uint8 mode only)
       }
       L->axis[key] = t;
       coef_ints += ints;
@@ -551,7 +614,7 @@ int build_layout(int32_t n, const int32_t* crop_box, const int32_t* resized_hw, 
     const int32_t oh = resized_hw[2 * i], ow = resized_hw[2 * i + 1];
     const int64_t rows = L->nrows[i] + (L->ybox0[i] & 3);
     units_h += ((rows + kHRows - 1) / kHRows) * ((ow + kHCols - 1) / kHCols);
-    units_v += (int64_t)(oh / 28) * ((ow / 28 + 1) / 2);
+    units_v += u8_out ? (oh + 7) / 8 : (int64_t)(oh / 28) * ((ow / 28 + 1) / 2);
   }
   L->strips_per_item = (int32_t)std::min<int64_t>(16, std::max<int64_t>(1, units_h / kItemsTarget));
   L->pairs_per_item = (int32_t)std::min<int64_t>(8, std::max<int64_t>(1, units_v / kItemsTarget));
@@ -560,7 +623,7 @@ int build_layout(int32_t n, const int32_t* crop_box, const int32_t* resized_hw, 
     const int64_t rows = L->nrows[i] + (L->ybox0[i] & 3);
     const int64_t strips = (rows + kHRows - 1) / kHRows, pairs = (ow / 28 + 1) / 2;
     L->item_cap_h += ((ow + kHCols - 1) / kHCols) * ((strips + L->strips_per_item - 1) / L->strips_per_item);
-    L->item_cap_v += (int64_t)(oh / 28) * ((pairs + L->pairs_per_item - 1) / L->pairs_per_item);
+    L->item_cap_v += u8_out ? (oh + 7) / 8 : (int64_t)(oh / 28) * ((pairs + L->pairs_per_item - 1) / L->pairs_per_item);
   }
   if (L->item_cap_h > INT32_MAX / 8 || L->item_cap_v > INT32_MAX / 8) return zv::fail(ZV_EINVAL, "zv_preprocess: batch too large for one launch");
   int64_t off = 0;
@@ -616,41 +679,26 @@ void launch_vpass(int nw, int count, cudaStream_t s, const K1Crop* d, const int3
     case 4: launch_vfast<4, OutT>(count, s, d, items, coef, ws, lut, out, row_order, wsz, tile_quads); break;
     case 5: launch_vfast<5, OutT>(count, s, d, items, coef, ws, lut, out, row_order, wsz, tile_quads); break;
     case 7: launch_vfast<7, OutT>(count, s, d, items, coef, ws, lut, out, row_order, wsz, tile_quads); break;
-    default: launch_vfast<10, OutT>(count, s, d, items, coef, ws, lut, out, row_order, wsz, tile_quads); break;
+    case 10: launch_vfast<10, OutT>(count, s, d, items, coef, ws, lut, out, row_order, wsz, tile_quads); break;
+    default: launch_vfast<12, OutT>(count, s, d, items, coef, ws, lut, out, row_order, wsz, tile_quads); break;
   }
 }
 
-}  // namespace
-
-extern "C" {
-
-int64_t zv_preprocess_workspace_bytes(int32_t n, const int32_t* crop_box, const int32_t* resized_hw) {
-  if (n <= 0 || !crop_box || !resized_hw) return zv::fail(ZV_EINVAL, "zv_preprocess_workspace_bytes: bad argument");
-  Layout L;
-  int rc = build_layout(n, crop_box, resized_hw, &L, false);
-  return rc ? rc : L.bytes;
-}
-
-int zv_preprocess(const zv_cfg* cfg, int32_t n, const uint8_t* const* src_dev, const int32_t* src_hw,
-                  const int64_t* src_pitch, const int32_t* crop_box, const int32_t* resized_hw,
-                  const int64_t* row_off, void* out_dev, int32_t out_dtype, int32_t row_order, void* workspace_dev,
-                  int64_t workspace_bytes, void* stream_) {
-  zv::reset_launch_count();
-  zv::NvtxRange nvtx_k1("zv:K1 crop+resize+normalize+patchify");
-  if (!cfg || n <= 0 || !src_dev || !src_hw || !src_pitch || !crop_box || !resized_hw || !out_dev || !workspace_dev)
-    return zv::fail(ZV_EINVAL, "zv_preprocess: null argument");
-  if (cfg->patch != 14 || cfg->merge != 2 || cfg->temporal != 2)
-    return zv::fail(ZV_EINVAL, "zv_preprocess: only patch=14, merge=2, temporal=2 is built");
-  if (out_dtype != ZV_F32 && out_dtype != ZV_BF16 && out_dtype != ZV_F16) return zv::fail(ZV_EINVAL, "zv_preprocess: bad out_dtype");
-  if (row_order != ZV_ORDER_HF && row_order != ZV_ORDER_WINDOW) return zv::fail(ZV_EINVAL, "zv_preprocess: bad row_order");
+// Both device entry points: the two resample passes over n crops.  u8_dst == nullptr: patches (LUT + patchify) into out_dev;
+// else plain uint8 images into u8_dst[i] (row pitch u8_pitch[i]).
+int k1_run(const char* who, const zv_cfg* cfg, int32_t n, const uint8_t* const* src_dev, const int32_t* src_hw,
+           const int64_t* src_pitch, const int32_t* crop_box, const int32_t* resized_hw, const int64_t* row_off,
+           void* out_dev, int32_t out_dtype, int32_t row_order, uint8_t* const* u8_dst, const int64_t* u8_pitch,
+           void* workspace_dev, int64_t workspace_bytes, void* stream_) {
+  const bool u8_out = u8_dst != nullptr;
   int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return zv::fail(ZV_ENODEV, "zv_preprocess: no CUDA device");
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return zv::fail(ZV_ENODEV, "%s: no CUDA device", who);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   Layout L;
-  int rc = build_layout(n, crop_box, resized_hw, &L, true);
+  int rc = build_layout(n, crop_box, resized_hw, &L, true, u8_out);
   if (rc) return rc;
   if (workspace_bytes < L.bytes)
-    return zv::fail(ZV_ENOMEM, "zv_preprocess: workspace %lld B < required %lld B", (long long)workspace_bytes, (long long)L.bytes);
+    return zv::fail(ZV_ENOMEM, "%s: workspace %lld B < required %lld B", who, (long long)workspace_bytes, (long long)L.bytes);
 
   // host image of [descriptors | LUT | coefficient tables | launch lists]
   std::vector<uint8_t> host((size_t)L.off_tmp, 0);
@@ -669,7 +717,11 @@ int zv_preprocess(const zv_cfg* cfg, int32_t n, const uint8_t* const* src_dev, c
     c.x0 = crop_box[4 * i]; c.y0 = crop_box[4 * i + 1];
     c.cw = crop_box[4 * i + 2] - c.x0; c.ch = crop_box[4 * i + 3] - c.y0;
     c.oh = resized_hw[2 * i]; c.ow = resized_hw[2 * i + 1];
-    if (!c.src || c.pitch < 3 * (int64_t)c.src_w) return zv::fail(ZV_EINVAL, "zv_preprocess: image %d has a null pointer or short pitch", i);
+    if (!c.src || c.pitch < 3 * (int64_t)c.src_w) return zv::fail(ZV_EINVAL, "%s: image %d has a null pointer or short pitch", who, i);
+    if (u8_out) {
+      c.dst = u8_dst[i]; c.dst_pitch = u8_pitch[i];
+      if (!c.dst || c.dst_pitch < 3 * (int64_t)c.ow) return zv::fail(ZV_EINVAL, "%s: output %d has a null pointer or short pitch", who, i);
+    }
     const AxisTables& h = L.axis[{c.cw, c.ow}];
     const AxisTables& v = L.axis[{c.ch, c.oh}];
     c.ksh = h.ksize; c.ksv = v.ksize;
@@ -692,7 +744,7 @@ int zv_preprocess(const zv_cfg* cfg, int32_t n, const uint8_t* const* src_dev, c
     c.out_row0 = row_off ? row_off[i] : row;
     row += (int64_t)(c.oh / 14) * (c.ow / 14);
   }
-  zv::normalize_lut(cfg, reinterpret_cast<float*>(host.data() + L.off_lut));
+  if (!u8_out) zv::normalize_lut(cfg, reinterpret_cast<float*>(host.data() + L.off_lut));
   std::memcpy(host.data() + L.off_coef, L.coef.data(), L.coef.size() * sizeof(int32_t));
 
   // launch lists, crops grouped by kernel class.  Fast classes: a work list of int4 items - hpass (crop, 128-column
@@ -703,13 +755,17 @@ int zv_preprocess(const zv_cfg* cfg, int32_t n, const uint8_t* const* src_dev, c
   int32_t* lists = reinterpret_cast<int32_t*>(host.data() + L.off_lists);
   int64_t cur = 0;                                    // in ints; items are appended first, so they stay 16-byte aligned
   auto build = [&](bool vpass, std::vector<Launch>* outl) -> int {
-    for (int nw : {2, 3, 4, 5, 7, 10}) {
+    for (int nw : {2, 3, 4, 5, 7, 10, 12}) {
       Launch l{};
       l.nw = nw; l.list_off = cur;
       for (int32_t i = 0; i < n; ++i) {
         const K1Crop& c = d[i];
         if ((vpass ? c.nwv : c.nwh) != nw) continue;
-        if (vpass) {
+        if (vpass && u8_out) {
+          for (int y0 = 0; y0 < c.oh; y0 += 8) {
+            lists[cur++] = i; lists[cur++] = y0; lists[cur++] = std::min(8, c.oh - y0); lists[cur++] = 0;
+          }
+        } else if (vpass) {
           const int pairs = (c.lw + 1) / 2;
           for (int my = 0; my < c.lh; ++my)
             for (int p0 = 0; p0 < pairs; p0 += L.pairs_per_item) {
@@ -743,7 +799,7 @@ int zv_preprocess(const zv_cfg* cfg, int32_t n, const uint8_t* const* src_dev, c
     for (int32_t id : ids) {
       const K1Crop& c = d[id];
       lists[cur++] = (int32_t)blocks;
-      blocks += vpass ? (int64_t)c.lh * c.lw : ((int64_t)c.nrows * c.ow + 255) / 256;
+      blocks += !vpass ? ((int64_t)c.nrows * c.ow + 255) / 256 : u8_out ? ((int64_t)c.oh * c.ow * 3 + 255) / 256 : (int64_t)c.lh * c.lw;
       if (blocks > INT32_MAX) return zv::fail(ZV_EINVAL, "zv_preprocess: batch too large for one launch");
     }
     l.count = blocks;
@@ -759,12 +815,12 @@ int zv_preprocess(const zv_cfg* cfg, int32_t n, const uint8_t* const* src_dev, c
 
   uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
   cudaError_t e = cudaMemcpyAsync(ws, host.data(), host.size(), cudaMemcpyHostToDevice, stream);
-  if (e != cudaSuccess) return zv::fail(ZV_ECUDA, "zv_preprocess: table upload: %s", cudaGetErrorString(e));
+  if (e != cudaSuccess) return zv::fail(ZV_ECUDA, "%s: table upload: %s", who, cudaGetErrorString(e));
   const K1Crop* dcrops = reinterpret_cast<const K1Crop*>(ws + L.off_desc);
   const int32_t* dcoef = reinterpret_cast<const int32_t*>(ws + L.off_coef);
   const int32_t* dlists = reinterpret_cast<const int32_t*>(ws + L.off_lists);
   const float* dlut = reinterpret_cast<const float*>(ws + L.off_lut);
-  const int wsz = cfg->window / cfg->merge / cfg->patch;
+  const int wsz = u8_out ? 0 : cfg->window / cfg->merge / cfg->patch;
   {
     zv::KernelTimer timer(zv::KC_K1_HPASS, stream);
     for (const Launch& l : hl) {
@@ -778,7 +834,8 @@ int zv_preprocess(const zv_cfg* cfg, int32_t n, const uint8_t* const* src_dev, c
         case 4: launch_hfast<4>(ni, stream, dcrops, items, dcoef, ws, l.seg_words); break;
         case 5: launch_hfast<5>(ni, stream, dcrops, items, dcoef, ws, l.seg_words); break;
         case 7: launch_hfast<7>(ni, stream, dcrops, items, dcoef, ws, l.seg_words); break;
-        default: launch_hfast<10>(ni, stream, dcrops, items, dcoef, ws, l.seg_words); break;
+        case 10: launch_hfast<10>(ni, stream, dcrops, items, dcoef, ws, l.seg_words); break;
+        default: launch_hfast<12>(ni, stream, dcrops, items, dcoef, ws, l.seg_words); break;
       }
       zv::count_launch();
     }
@@ -789,15 +846,73 @@ int zv_preprocess(const zv_cfg* cfg, int32_t n, const uint8_t* const* src_dev, c
       const int32_t* list = dlists + l.list_off;
       const int32_t* blk0 = dlists + l.blk_off;
       const int cnt = (int)l.count;
-      if (out_dtype == ZV_BF16) launch_vpass<__nv_bfloat16>(l.nw, cnt, stream, dcrops, list, blk0, l.ncls, dcoef, ws, dlut, out_dev, row_order, wsz, l.tile_quads);
+      if (u8_out) {
+        const int4* items = reinterpret_cast<const int4*>(list);
+        const int grid = (int)std::min<int64_t>(cnt, (int64_t)zv::num_sms() * 8);
+        switch (l.nw) {
+          case 0: k1_vpass_u8<<<(unsigned)cnt, 256, 0, stream>>>(dcrops, list, blk0, l.ncls, dcoef, ws); break;
+          case 2: k1_vpass_u8_fast<2><<<grid, 256, 0, stream>>>(dcrops, items, cnt, dcoef, ws); break;
+          case 3: k1_vpass_u8_fast<3><<<grid, 256, 0, stream>>>(dcrops, items, cnt, dcoef, ws); break;
+          case 4: k1_vpass_u8_fast<4><<<grid, 256, 0, stream>>>(dcrops, items, cnt, dcoef, ws); break;
+          case 5: k1_vpass_u8_fast<5><<<grid, 256, 0, stream>>>(dcrops, items, cnt, dcoef, ws); break;
+          case 7: k1_vpass_u8_fast<7><<<grid, 256, 0, stream>>>(dcrops, items, cnt, dcoef, ws); break;
+          case 10: k1_vpass_u8_fast<10><<<grid, 256, 0, stream>>>(dcrops, items, cnt, dcoef, ws); break;
+          default: k1_vpass_u8_fast<12><<<grid, 256, 0, stream>>>(dcrops, items, cnt, dcoef, ws); break;
+        }
+      } else if (out_dtype == ZV_BF16) launch_vpass<__nv_bfloat16>(l.nw, cnt, stream, dcrops, list, blk0, l.ncls, dcoef, ws, dlut, out_dev, row_order, wsz, l.tile_quads);
       else if (out_dtype == ZV_F16) launch_vpass<__half>(l.nw, cnt, stream, dcrops, list, blk0, l.ncls, dcoef, ws, dlut, out_dev, row_order, wsz, l.tile_quads);
       else launch_vpass<float>(l.nw, cnt, stream, dcrops, list, blk0, l.ncls, dcoef, ws, dlut, out_dev, row_order, wsz, l.tile_quads);
       zv::count_launch();
     }
   }
   e = cudaGetLastError();
-  if (e != cudaSuccess) return zv::fail(ZV_ECUDA, "zv_preprocess: launch: %s", cudaGetErrorString(e));
+  if (e != cudaSuccess) return zv::fail(ZV_ECUDA, "%s: launch: %s", who, cudaGetErrorString(e));
   return ZV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t zv_preprocess_workspace_bytes(int32_t n, const int32_t* crop_box, const int32_t* resized_hw) {
+  if (n <= 0 || !crop_box || !resized_hw) return zv::fail(ZV_EINVAL, "zv_preprocess_workspace_bytes: bad argument");
+  Layout L;
+  int rc = build_layout(n, crop_box, resized_hw, &L, false);
+  return rc ? rc : L.bytes;
+}
+
+int zv_preprocess(const zv_cfg* cfg, int32_t n, const uint8_t* const* src_dev, const int32_t* src_hw,
+                  const int64_t* src_pitch, const int32_t* crop_box, const int32_t* resized_hw,
+                  const int64_t* row_off, void* out_dev, int32_t out_dtype, int32_t row_order, void* workspace_dev,
+                  int64_t workspace_bytes, void* stream_) {
+  zv::reset_launch_count();
+  zv::NvtxRange nvtx_k1("zv:K1 crop+resize+normalize+patchify");
+  if (!cfg || n <= 0 || !src_dev || !src_hw || !src_pitch || !crop_box || !resized_hw || !out_dev || !workspace_dev)
+    return zv::fail(ZV_EINVAL, "zv_preprocess: null argument");
+  if (cfg->patch != 14 || cfg->merge != 2 || cfg->temporal != 2)
+    return zv::fail(ZV_EINVAL, "zv_preprocess: only patch=14, merge=2, temporal=2 is built");
+  if (out_dtype != ZV_F32 && out_dtype != ZV_BF16 && out_dtype != ZV_F16) return zv::fail(ZV_EINVAL, "zv_preprocess: bad out_dtype");
+  if (row_order != ZV_ORDER_HF && row_order != ZV_ORDER_WINDOW) return zv::fail(ZV_EINVAL, "zv_preprocess: bad row_order");
+  return k1_run("zv_preprocess", cfg, n, src_dev, src_hw, src_pitch, crop_box, resized_hw, row_off, out_dev, out_dtype, row_order,
+                nullptr, nullptr, workspace_dev, workspace_bytes, stream_);
+}
+
+int64_t zv_resize_u8_workspace_bytes(int32_t n, const int32_t* crop_box, const int32_t* out_hw) {
+  if (n <= 0 || !crop_box || !out_hw) return zv::fail(ZV_EINVAL, "zv_resize_u8_workspace_bytes: bad argument");
+  Layout L;
+  int rc = build_layout(n, crop_box, out_hw, &L, false, true);
+  return rc ? rc : L.bytes;
+}
+
+int zv_resize_u8(int32_t n, const uint8_t* const* src_dev, const int32_t* src_hw, const int64_t* src_pitch,
+                 const int32_t* crop_box, const int32_t* out_hw, uint8_t* const* dst_dev, const int64_t* dst_pitch,
+                 void* workspace_dev, int64_t workspace_bytes, void* stream_) {
+  zv::reset_launch_count();
+  zv::NvtxRange nvtx_k1("zv:K1 crop+resize (uint8)");
+  if (n <= 0 || !src_dev || !src_hw || !src_pitch || !crop_box || !out_hw || !dst_dev || !dst_pitch || !workspace_dev)
+    return zv::fail(ZV_EINVAL, "zv_resize_u8: null argument");
+  return k1_run("zv_resize_u8", nullptr, n, src_dev, src_hw, src_pitch, crop_box, out_hw, nullptr, nullptr, 0, 0, dst_dev, dst_pitch,
+                workspace_dev, workspace_bytes, stream_);
 }
 
 }  // extern "C"
