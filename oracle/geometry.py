@@ -80,3 +80,38 @@ def smart_resize(height, width, factor=28, min_pixels=56 * 56, max_pixels=14 * 1
         h_bar = math.ceil(height * beta / factor) * factor
         w_bar = math.ceil(width * beta / factor) * factor
     return h_bar, w_bar
+
+
+# ---------------------------------------------------------------- the other call sites' variants
+RESIZE_MODE = {"infer": 0, "demo": 0, "sft": 1, "custom": 2}
+
+
+def resize_dims_ex(w, h, max_size, variant="infer"):
+    """(new_w, new_h, 1/scale) of ``resize_image`` at each call site: ``infer`` / ``demo`` infer.py:78-85, demo.py:86-93
+    (resize only when scale < 1); ``sft`` SFT.py:76-81 (always resizes, may upscale); ``custom`` customized_funcs.py:76-85
+    (scale = max(30 / min(w, h), max_size / max(w, h)), resize only when < 1)."""
+    scale = max_size / max(w, h)
+    if variant == "custom":
+        scale = max(30 / min(w, h), scale)
+    if variant == "sft" or scale < 1:
+        return int(w * scale), int(h * scale), 1 / scale
+    return w, h, 1 / scale
+
+
+def cut_ops(img_w, img_h, bbox, min_size=512, variant="infer"):
+    """The Pillow operations ``cut_image`` performs at each call site, as a list of ["crop", box] / ["resize", (w, h)]:
+    ``infer`` infer.py:41-76; ``custom`` customized_funcs.py:37-74 (the image itself when len(bbox) != 4); ``sft``
+    SFT.py:83-125 (boxes with both sides >= min_size: crop, resize to min side = min_size, centre crop)."""
+    if variant == "custom" and len(bbox) != 4:
+        return []
+    box = cut_box(img_w, img_h, bbox, min_size)
+    ops = [["crop", list(box)]]
+    if variant == "sft":
+        x1, y1, x2, y2 = (int(v) for v in bbox)
+        if not (x2 - x1 < min_size or y2 - y1 < min_size):
+            w, h = box[2] - box[0], box[3] - box[1]
+            scale = min_size / min(w, h)
+            nw, nh = int(w * scale), int(h * scale)
+            left, top = (nw - min_size) // 2, (nh - min_size) // 2
+            ops += [["resize", [nw, nh]], ["crop", [left, top, left + min_size, top + min_size]]]
+    return ops

@@ -55,6 +55,41 @@ def resize_dims(w, h, max_size=512):
     return wh[0], wh[1], inv.value
 
 
+RESIZE_MODE = {"infer": 0, "demo": 0, "sft": 1, "custom": 2}
+DEFAULT_MAX_SIZE = {"infer": 512, "demo": 1024, "sft": 1024, "custom": 512}
+
+
+def resize_dims_ex(w, h, max_size=None, variant="infer"):
+    """``resize_image`` at the reference's call sites -> (new_w, new_h, 1/scale).  ``infer`` src/eval/infer.py:78-85 (512),
+    ``demo`` src/demo.py:86-93 (1024), ``sft`` src/train/SFT.py:76-81 (1024, always resizes), ``custom``
+    open_r1/custom/customized_funcs.py:76-85 (512, scale floored at 30 / min side)."""
+    if max_size is None:
+        max_size = DEFAULT_MAX_SIZE[variant]
+    wh = (C.c_int32 * 2)()
+    inv = C.c_double()
+    _lib.check(_lib.lib().zv_resize_dims_ex(int(w), int(h), int(max_size), RESIZE_MODE[variant], wh, C.byref(inv)))
+    return wh[0], wh[1], inv.value
+
+
+def cut_ops(img_w, img_h, bbox, min_size=512, variant="infer"):
+    """The Pillow operations ``cut_image`` performs at a call site, as ``["crop", box]`` / ``["resize", (w, h)]`` steps:
+    ``infer`` / ``demo`` one crop (infer.py:41-76); ``custom`` the same, or nothing at all when ``len(bbox) != 4``
+    (customized_funcs.py:38-39); ``sft`` crop, and for boxes with both sides >= min_size a resize to min side = min_size
+    plus a centre crop (SFT.py:83-125)."""
+    if variant == "custom" and len(bbox) != 4:
+        return []
+    if variant != "sft":
+        return [["crop", list(cut_box(img_w, img_h, bbox, min_size))]]
+    cut_box(img_w, img_h, bbox, min_size)                       # same argument checks / errors as the plain rule
+    b = (C.c_double * 4)(*[float(v) for v in bbox])
+    box, rs, cb = (C.c_int32 * 4)(), (C.c_int32 * 2)(), (C.c_int32 * 4)()
+    _lib.check(_lib.lib().zv_cut_box_sft(int(img_w), int(img_h), b, int(min_size), box, rs, cb))
+    ops = [["crop", list(box)]]
+    if rs[0] > 0:
+        ops += [["resize", [rs[0], rs[1]]], ["crop", list(cb)]]
+    return ops
+
+
 def smart_resize(height, width, factor=28, min_pixels=56 * 56, max_pixels=14 * 14 * 4 * 1280):
     out = (C.c_int32 * 2)()
     rc = _lib.lib().zv_smart_resize(int(height), int(width), int(factor), int(min_pixels), int(max_pixels), out)

@@ -191,6 +191,99 @@ class FusedImageProcessor:
         self.last_launches = lib.zv_last_launch_count()
         return out, torch.from_numpy(grid), crop
 
+    # ---- the reference's cut_image / resize_image on the device (uint8 in, uint8 out, Pillow-exact)
+    def resize_u8(self, images_dev, boxes, out_wh, image_index=None):
+        """``PIL.Image.crop(box).resize((w, h), Image.BICUBIC)`` for n (image, box, size) triples in one call of
+        ``zv_resize_u8``.  images_dev: (H, W, 3) uint8 CUDA tensors (row-pitched views are fine); boxes (n, 4) ints
+        (x0, y0, x1, y1), may reach outside the image (zero fill, like Image.crop); out_wh (n, 2) (w, h).
+        Returns a list of n contiguous (h, w, 3) uint8 CUDA tensors."""
+        n = len(boxes)
+        idx = list(range(n)) if image_index is None else list(image_index)
+        device = images_dev[0].device
+        if device.type != "cuda":
+            raise RuntimeError("resize_u8 takes CUDA tensors; there is no CPU path")
+        crop = np.ascontiguousarray(np.asarray(boxes, np.int64).reshape(n, 4).astype(np.int32))
+        if (crop[:, 2] < crop[:, 0]).any():
+            raise ValueError("Coordinate 'right' is less than 'left'")
+        if (crop[:, 3] < crop[:, 1]).any():
+            raise ValueError("Coordinate 'lower' is less than 'upper'")
+        out_hw = np.ascontiguousarray(np.asarray(out_wh, np.int64).reshape(n, 2)[:, ::-1].astype(np.int32))
+        img_hw = np.array([[images_dev[i].shape[0], images_dev[i].shape[1]] for i in idx], np.int32)
+        for i in idx:
+            t = images_dev[i]
+            if t.dtype != torch.uint8 or t.ndim != 3 or t.shape[2] != 3 or t.stride(2) != 1 or t.stride(1) != 3:
+                raise ValueError("images must be (H, W, 3) uint8 CUDA tensors with packed pixels")
+        lib = _lib.lib()
+        ws_bytes = _lib.check(lib.zv_resize_u8_workspace_bytes(n, crop.ctypes.data, out_hw.ctypes.data))
+        ws = self._workspace(ws_bytes, device)
+        outs = [torch.empty((int(h), int(w), 3), dtype=torch.uint8, device=device) for h, w in out_hw]
+        src = (C.c_void_p * n)(*[images_dev[i].data_ptr() for i in idx])
+        pitch = np.array([images_dev[i].stride(0) for i in idx], np.int64)
+        dst = (C.c_void_p * n)(*[o.data_ptr() for o in outs])
+        dpitch = np.array([o.stride(0) for o in outs], np.int64)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        with torch.cuda.device(device):
+            _lib.check(lib.zv_resize_u8(n, src, img_hw.ctypes.data, pitch.ctypes.data, crop.ctypes.data, out_hw.ctypes.data,
+                                        dst, dpitch.ctypes.data, ws.data_ptr(), ws.numel(), stream))
+        self.last_launches = lib.zv_last_launch_count()
+        return outs
+
+    def cut_resize(self, images_dev, bboxes=None, image_index=None, variant="infer", max_size=None, min_size=512,
+                   apply_cut_image=True):
+        """``resize_image(cut_image(image, bbox))`` of the reference on the device, for a batch: what infer.py:215,239 /
+        demo.py:133,140 / SFT.py:159-169 / grpo_trainer.py:530,606 hand to the processor.  ``bboxes`` None = the global
+        view (``resize_image(image)``).  ``max_size`` 0 = cut_image only.  Returns (list of uint8 CUDA images, list of
+        1/scale) - pixels bit-identical to Pillow's.  Crops that need no resampling at all come back as views.
+        ``apply_cut_image=False``: ``bboxes`` are final crop boxes (``Image.crop`` semantics) instead of model boxes."""
+        n = len(images_dev) if bboxes is None else len(bboxes)
+        idx = list(range(n)) if image_index is None else list(image_index)
+        if max_size is None:
+            max_size = geometry.DEFAULT_MAX_SIZE[variant]
+        cur = [images_dev[i] for i in idx]                    # per item: the image its next step reads
+        plans, inv = [], [1.0] * n
+        for k in range(n):                                    # the whole chain of Pillow calls, sizes known up front
+            w, h = int(cur[k].shape[1]), int(cur[k].shape[0])
+            if bboxes is None:
+                ops = []
+            elif apply_cut_image:
+                ops = geometry.cut_ops(w, h, bboxes[k], min_size, variant)
+            else:                                             # final crop boxes, PIL.Image.crop rounding
+                ops = [["crop", [int(v) for v in np.rint(np.asarray(bboxes[k], np.float64))]]]
+            for kind, arg in ops:
+                w, h = (arg[2] - arg[0], arg[3] - arg[1]) if kind == "crop" else (arg[0], arg[1])
+            if max_size:
+                nw, nh, inv[k] = geometry.resize_dims_ex(w, h, max_size, variant)
+                if (nw, nh) != (w, h) or variant == "sft":
+                    ops = ops + [["resize", [nw, nh]]]
+            plans.append(ops)
+        # a crop followed by a resize is ONE item of a zv_resize_u8 call (infer.py's whole chain); a lone crop is a view,
+        # or a same-size zero-filled copy when it leaves the image; at most three rounds (SFT's crop-resize-crop + resize)
+        while any(plans):
+            todo = []
+            for k in range(n):
+                ops = plans[k]
+                if not ops:
+                    continue
+                h, w = int(cur[k].shape[0]), int(cur[k].shape[1])
+                kind, arg = ops[0]
+                if kind == "resize":
+                    todo.append((k, [0, 0, w, h], arg))
+                    plans[k] = ops[1:]
+                elif len(ops) > 1 and ops[1][0] == "resize":
+                    todo.append((k, arg, ops[1][1]))
+                    plans[k] = ops[2:]
+                elif 0 <= arg[0] <= arg[2] <= w and 0 <= arg[1] <= arg[3] <= h:
+                    cur[k] = cur[k][arg[1]:arg[3], arg[0]:arg[2]]
+                    plans[k] = ops[1:]
+                else:
+                    todo.append((k, arg, [arg[2] - arg[0], arg[3] - arg[1]]))
+                    plans[k] = ops[1:]
+            if todo:
+                outs = self.resize_u8([cur[k] for k, _, _ in todo], [b for _, b, _ in todo], [s for _, _, s in todo])
+                for (k, _, _), o in zip(todo, outs):
+                    cur[k] = o
+        return cur, inv
+
     # ---- HF surface
     def preprocess(self, images, videos=None, return_tensors=None, min_pixels=None, max_pixels=None, size=None,
                    do_resize=None, do_rescale=None, do_normalize=None, **unused):

@@ -10,17 +10,22 @@ rows that ``get_image_features`` would have produced, in the order the reference
 import numpy as np
 import torch
 
-from .geometry import cut_box, resize_dims
+from .geometry import cut_box, resize_dims_ex
 from .zoom import ZoomEncoder
 
 
 class ZoomSession:
-    def __init__(self, encoder: ZoomEncoder, global_max_size=None):
-        """global_max_size: if set (512 in infer.py, 1024 in demo.py), the global view is the image resized so its
-        longer side is that size first (``resize_image``), done by capping the fused resample at the same pixel
-        budget; None keeps the processor's max_pixels as the only cap."""
+    def __init__(self, encoder: ZoomEncoder, global_max_size=None, variant="infer"):
+        """global_max_size: if set (512 in infer.py, 1024 in demo.py), every image the tower sees goes through the
+        reference's ``resize_image`` first - the global view (infer.py:215) AND each zoom crop
+        (``resize_image(cut_image(...))``, infer.py:239) - as a device-side uint8 resample (``zv_resize_u8``), so grids,
+        token counts and pixels are those of the unmodified loop and ``scale()`` is the factor that maps boxes the model
+        draws on the resized view back to source pixels.  None = the fused single-resample fast path, scale 1.
+        ``variant``: which call site's ``resize_image`` / ``cut_image`` ("infer", "demo", "sft", "custom")."""
         self.enc = encoder
         self.global_max_size = global_max_size
+        self.variant = variant
+        self._pre = None if global_max_size is None else (variant, int(global_max_size))
         self._images = {}          # key -> resident uint8 tensor
         self._global = {}          # key -> (embeddings (T, D), grid_thw row)
 
@@ -38,13 +43,13 @@ class ZoomSession:
         t = self._images[key]
         if self.global_max_size is None:
             return 1.0
-        return resize_dims(int(t.shape[1]), int(t.shape[0]), self.global_max_size)[2]
+        return resize_dims_ex(int(t.shape[1]), int(t.shape[0]), self.global_max_size, self.variant)[2]
 
     def stage1(self, keys):
         """Global-view embeddings for ``keys`` (cached).  Returns (list of (T_i, D) tensors, grid_thw (n, 3))."""
         missing = [k for k in keys if k not in self._global]
         if missing:
-            emb, grid, _ = self.enc.encode([self._images[k] for k in missing], None)
+            emb, grid, _ = self.enc.encode([self._images[k] for k in missing], None, pre_resize=self._pre)
             tokens = self.enc.tokens_per_crop(grid.numpy())
             off = 0
             for k, n, g in zip(missing, tokens, grid):
@@ -59,7 +64,8 @@ class ZoomSession:
         g_emb, g_grid = self.stage1(keys)
         uniq = {k: i for i, k in enumerate(dict.fromkeys(keys))}
         imgs = [self._images[k] for k in uniq]
-        emb, grid, crop = self.enc.encode(imgs, np.asarray(bboxes, np.float64), image_index=[uniq[k] for k in keys])
+        emb, grid, crop = self.enc.encode(imgs, np.asarray(bboxes, np.float64), image_index=[uniq[k] for k in keys],
+                                          pre_resize=self._pre)
         tokens = self.enc.tokens_per_crop(grid.numpy())
         out, off = [], 0
         for i, n in enumerate(tokens):

@@ -13,13 +13,66 @@ from .processor import FusedImageProcessor
 from .visual import FusedVisual
 
 
+def proc_min_size(proc):
+    """cut_image()'s min_size (512 at every call site of the reference)."""
+    return getattr(proc, "cut_min_size", 512)
+
+
 class ZoomEncoder:
     def __init__(self, visual: FusedVisual, processor: FusedImageProcessor = None, max_pixels=128 * 128 * 28 * 28,
-                 min_pixels=56 * 56):
+                 min_pixels=56 * 56, pre_resize=None):
+        """``pre_resize``: None = the fused single-resample step (crop -> smart_resize straight from the source pixels);
+        a call-site name - "infer" (512), "demo" (1024), "sft" (1024), "custom" (512) - or a (name, max_size) pair = the
+        reference-faithful TWO-resample flow: ``resize_image(cut_image(image, bbox))`` as uint8 on the device
+        (``zv_resize_u8``, infer.py:215,239 / demo.py:133,140), then the processor's smart_resize on that image
+        (``zv_preprocess``) - bit-identical to what the unmodified scripts feed the tower, with no host trip."""
         self.visual = visual
         self.processor = processor or FusedImageProcessor(min_pixels=min_pixels, max_pixels=max_pixels,
                                                           device=visual.device)
+        self.pre_resize = self._norm_pre_resize(pre_resize)
         self.last_launches = 0
+        self.last_inv_scales = None
+
+    @staticmethod
+    def _norm_pre_resize(pre_resize):
+        from . import geometry
+        if pre_resize is None:
+            return None
+        if isinstance(pre_resize, str):
+            pre_resize = (pre_resize, geometry.DEFAULT_MAX_SIZE[pre_resize])
+        variant, max_size = pre_resize
+        if variant not in geometry.RESIZE_MODE:
+            raise ValueError(f"pre_resize variant must be one of {sorted(geometry.RESIZE_MODE)}")
+        return variant, int(max_size)
+
+    def _patches(self, images_dev, boxes, image_index, apply_cut_image, pre_resize):
+        """-> (patches in window order, image_grid_thw, crop boxes in source pixels, K1 launches)."""
+        proc = self.processor
+        if pre_resize is None:
+            pv, grid, crop = proc.preprocess_crops(
+                images_dev, boxes, out_dtype=self.visual.operand_dtype, window_order=True, image_index=image_index,
+                apply_cut_image=apply_cut_image and boxes is not None)
+            self.last_inv_scales = None
+            return pv, grid, crop, proc.last_launches
+        variant, max_size = pre_resize
+        n = len(images_dev) if boxes is None else len(boxes)
+        idx = list(range(n)) if image_index is None else list(image_index)
+        imgs, inv = proc.cut_resize(images_dev, boxes, image_index, variant, max_size, proc_min_size(proc), apply_cut_image)
+        launches = proc.last_launches if any(i is not images_dev[j] for i, j in zip(imgs, idx)) else 0
+        pv, grid, _ = proc.preprocess_crops(imgs, None, out_dtype=self.visual.operand_dtype, window_order=True)
+        self.last_inv_scales = inv
+        from . import geometry
+        crop = np.zeros((n, 4), np.int32)
+        for k in range(n):
+            t = images_dev[idx[k]]
+            if boxes is None:
+                crop[k] = (0, 0, t.shape[1], t.shape[0])
+            elif apply_cut_image:
+                ops = geometry.cut_ops(int(t.shape[1]), int(t.shape[0]), boxes[k], proc_min_size(proc), variant)
+                crop[k] = ops[0][1] if ops else (0, 0, t.shape[1], t.shape[0])
+            else:
+                crop[k] = np.rint(np.asarray(boxes[k], np.float64)).astype(np.int32)
+        return pv, grid, crop, launches + proc.last_launches
 
     def upload(self, image):
         """PIL / (H, W, 3) uint8 array or tensor -> resident uint8 CUDA tensor (one H2D copy per image)."""
@@ -31,13 +84,12 @@ class ZoomEncoder:
 
     @torch.no_grad()
     def encode(self, images_dev, boxes=None, image_index=None, apply_cut_image=True, return_patches=False,
-               gather=None, gather_row=0, use_graph=False):
+               gather=None, gather_row=0, use_graph=False, pre_resize="default"):
         """images_dev: resident images; boxes (n, 4) in image pixels (None = global view of every image).
-        Returns (embeddings (T, out_hidden), image_grid_thw (n, 3), crop boxes (n, 4))."""
-        pv, grid, crop = self.processor.preprocess_crops(
-            images_dev, boxes, out_dtype=self.visual.operand_dtype, window_order=True, image_index=image_index,
-            apply_cut_image=apply_cut_image and boxes is not None)
-        k1 = self.processor.last_launches
+        Returns (embeddings (T, out_hidden), image_grid_thw (n, 3), crop boxes (n, 4)).  ``pre_resize`` overrides the
+        encoder's setting for this call (see ``__init__``)."""
+        pr = self.pre_resize if isinstance(pre_resize, str) and pre_resize == "default" else self._norm_pre_resize(pre_resize)
+        pv, grid, crop, k1 = self._patches(images_dev, boxes, image_index, apply_cut_image, pr)
         emb = self.visual(pv, grid, window_order=True, gather=gather, gather_row=gather_row, use_graph=use_graph)
         self.last_launches = k1 + self.visual.last_launches
         if return_patches:
