@@ -37,7 +37,7 @@ def read(path):
 
 
 def short(kernel):
-    k = kernel.replace("void ", "").replace("zv::", "").replace("(anonymous namespace)::", "").replace("unnamed>::", "")
+    k = kernel.replace("void ", "").replace("zv::", "").replace("(anonymous namespace)::", "").replace("<unnamed>::", "").replace("unnamed>::", "")
     return k.split("(")[0].strip()
 
 
