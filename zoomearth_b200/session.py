@@ -15,14 +15,16 @@ from .zoom import ZoomEncoder
 
 
 class ZoomSession:
-    def __init__(self, encoder: ZoomEncoder, global_max_size=None, variant="infer"):
+    def __init__(self, encoder: ZoomEncoder, global_max_size=None, variant="infer", store=None):
         """global_max_size: if set (512 in infer.py, 1024 in demo.py), every image the tower sees goes through the
         reference's ``resize_image`` first - the global view (infer.py:215) AND each zoom crop
         (``resize_image(cut_image(...))``, infer.py:239) - as a device-side uint8 resample (``zv_resize_u8``), so grids,
         token counts and pixels are those of the unmodified loop and ``scale()`` is the factor that maps boxes the model
         draws on the resized view back to source pixels.  None = the fused single-resample fast path, scale 1.
-        ``variant``: which call site's ``resize_image`` / ``cut_image`` ("infer", "demo", "sft", "custom")."""
+        ``variant``: which call site's ``resize_image`` / ``cut_image`` ("infer", "demo", "sft", "custom").
+        ``store``: an ``ingest.ImageStore`` for ``add_image(key, path)`` (created on first use otherwise)."""
         self.enc = encoder
+        self.store = store             # optional ingest.ImageStore: add_image(key, path) decodes each file once
         self.global_max_size = global_max_size
         self.variant = variant
         self._pre = None if global_max_size is None else (variant, int(global_max_size))
@@ -30,8 +32,15 @@ class ZoomSession:
         self._global = {}          # key -> (embeddings (T, D), grid_thw row)
 
     def add_image(self, key, image):
+        """image: PIL / uint8 array / tensor, or a file path (decoded once through ``store``, infer.py:215,237)."""
         if key not in self._images:
-            self._images[key] = self.enc.upload(image)
+            if isinstance(image, (str, bytes)) or hasattr(image, "__fspath__"):
+                if self.store is None:
+                    from .ingest import ImageStore
+                    self.store = ImageStore(device=self.enc.visual.device)
+                self._images[key] = self.store.get(image)
+            else:
+                self._images[key] = self.enc.upload(image)
         return self._images[key]
 
     def drop(self, key):
