@@ -191,6 +191,74 @@ def zoom_step_latency(visual, dev, reps=30):
     return out
 
 
+def config3_sharded(enc, visual, dev, rank, world, op_dtype, n_crops):
+    """BASELINE configs[3] as a sub-record of the line: `n_crops` mixed-size crops (256-2048 px per side, cut_image rule)
+    of 16 replicated source images, STRONG scaling - sharded over the ranks by LPT partition, every rank's merger GEMM
+    scattering its embedding rows to their global rows of every rank's gather buffer (ragged fused gather).  One warm-up
+    pass, one timed pass (CUDA events, max over ranks).  At N=1 the same crops run through the same micro-batched path."""
+    import torch.distributed as dist
+    from zoomearth_b200 import FusedImageProcessor, ZoomEncoder, sharding, synthetic
+    enc3 = ZoomEncoder(visual, FusedImageProcessor(min_pixels=MIN_PIXELS, max_pixels=16384 * 28 * 28, device=dev))
+    g = torch.Generator(device=dev).manual_seed(7)                  # same pool on every rank (images are replicated)
+    pool = [torch.randint(0, 256, (IMG, IMG, 3), generator=g, dtype=torch.uint8, device=dev) for _ in range(16)]
+    boxes, index = synthetic.mixed_crop_boxes(n_crops, 16)
+    pg3, total, check = None, None, None
+    if world > 1:
+        from zoomearth_b200 import geometry
+        cfg = enc3.processor._cfg()
+        _, _, grid = geometry.geometry(cfg, np.array([[IMG, IMG]] * n_crops, np.int32), boxes.astype(np.float64))
+        total = int(((grid[:, 1] * grid[:, 2]) // 4).sum())
+        pg3 = sharding.PeerGather(total, 2048, op_dtype, dev)
+
+    def one_pass():
+        if pg3 is None:
+            emb, _, _ = enc3.encode_batched(pool, boxes, index)
+            return emb
+        out, _, _ = sharding.encode_sharded(enc3, pool, boxes, index, pg3)
+        pg3.barrier()
+        return out
+
+    out = one_pass()
+    torch.cuda.synchronize()
+    if world > 1:
+        # correctness of the ragged fused gather, once: every crop's rows equal what its owner computes on its own
+        parts = sharding.partition(sharding.crop_cost(np.asarray(grid)), world)
+        mine = parts[rank][:3]
+        starts = np.concatenate([[0], np.cumsum((grid[:, 1] * grid[:, 2]) // 4)])
+        ok = 1
+        for i in mine:
+            e, _, _ = enc3.encode([pool[int(index[i])]], [boxes[i]], image_index=[0])
+            got = out[int(starts[i]):int(starts[i + 1])].float()
+            # not bitwise: a segment's K/V tile split in the full-attention layers depends on its row offset in the batch
+            ok &= int(got.shape == e.shape and ((got - e.float()).abs().max() / e.float().abs().max()).item() <= 5e-3)
+        t = torch.tensor([ok], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        # ... and every rank holds the same bytes
+        h = torch.stack([out.view(torch.int16).to(torch.int64).sum()])
+        hs = [torch.zeros_like(h) for _ in range(world)]
+        dist.all_gather(hs, h)
+        check = bool(t.item()) and all(int(x) == int(hs[0]) for x in hs)
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    out = one_pass()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    tokens = int(out.shape[0])
+    del pool
+    return {"workload": f"BASELINE configs[3]: {n_crops} mixed-size crops (256-2048 px) of 16 source images, cut_image rule, "
+                        f"max_pixels=12845056, sharded by crop (LPT) over {world} GPU(s)", "scaling": "strong",
+            "tokens": tokens, "ms": ms, "value": tokens / (ms / 1e3), "unit": "tokens/s",
+            "gather": "ragged fused gather (zv_visual_forward_gather_rows): per-row peer stores from the merger GEMM epilogue"
+                      if world > 1 else "none (single GPU)", "gather_check": check}
+
+
 # ------------------------------------------------------------------------------------------- our arm (CUDA)
 def run_ours(args):
     import torch.distributed as dist
@@ -232,8 +300,9 @@ def run_ours(args):
         if not args.nccl_gather:
             try:
                 from zoomearth_b200.sharding import PeerGather
-                pg = PeerGather(world * tokens_step, 2048, op_dtype, dev)
-                gather_kind = "fused: merger GEMM epilogue stores into every rank's buffer over NVLink (symmetric memory)"
+                pg = PeerGather(world * tokens_step, 2048, op_dtype, dev, double_buffer=True)
+                gather_kind = ("fused: merger GEMM epilogue stores into every rank's buffer over NVLink (symmetric memory); "
+                               "two buffers, the barrier of step i is waited on at the start of step i+1")
             except Exception as e:          # symmetric memory unavailable on this box: the NCCL collective still gathers
                 pg = None
                 if rank == 0:
@@ -245,9 +314,10 @@ def run_ours(args):
 
     def step():
         if pg is not None:
+            pg.begin_step()                                # waits for the PREVIOUS step's cross-rank barrier, flips buffers
             enc.encode(images, None, gather=pg, gather_row=rank * tokens_step)
-            pg.barrier()                                   # every rank's rows have landed in every buffer
-            return pg.buffer
+            pg.end_step()                                  # this step's barrier runs on a side stream behind the kernels
+            return None
         emb, grid, _ = enc.encode(images, None)
         if world > 1:
             out = torch.empty((world * emb.shape[0], emb.shape[1]), dtype=emb.dtype, device=dev)
@@ -256,6 +326,8 @@ def run_ours(args):
         return emb
 
     def barrier():
+        if pg is not None:
+            pg.finish()                                    # the last step's gather is complete on every rank
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -267,7 +339,8 @@ def run_ours(args):
     if world > 1:
         # correctness of the data path being timed: what step() leaves on every rank must be, bit for bit, NCCL's
         # all_gather_into_tensor of the per-rank embeddings (checked once, outside the timed region)
-        got = step().clone()
+        got = step()
+        got = (pg.finish() if pg is not None else got).clone()
         barrier()
         emb, _, _ = enc.encode(images, None)
         want = torch.empty((world * emb.shape[0], emb.shape[1]), dtype=emb.dtype, device=dev)
@@ -288,6 +361,8 @@ def run_ours(args):
     for _ in range(args.steps):
         step()
         launches += enc.last_launches
+    if pg is not None:
+        pg.finish()                                        # inside the timed region: every step's gather has landed
     e1.record()
     barrier()
     lib.zv_timing_enable(0)
@@ -355,6 +430,10 @@ def run_ours(args):
                     "sample": f"{args.ref_images} of the {n_img} images of one step ({tokens} tokens, {dt:.1f} s): PIL crop + "
                               f"HF Qwen2VLImageProcessorPil + HF vision tower fp32 sdpa on {cores} threads"}
 
+    sharded = None
+    if not args.no_sharded:
+        sharded = config3_sharded(enc, visual, dev, rank, world, op_dtype, args.sharded_crops)
+
     latency = None
     if rank == 0 and world == 1 and not args.no_latency:
         latency = zoom_step_latency(visual, dev)
@@ -392,6 +471,7 @@ def run_ours(args):
             "kernel_ms": {k: round(v[0] / args.steps, 3) for k, v in cls.items()},
             "cpu_baseline": cpu_base,
             "latency": latency,
+            "sharded": sharded,
         }
         if gather_check is not None:
             line["gather_check"] = gather_check
@@ -417,6 +497,8 @@ def main():
     ap.add_argument("--operand-dtype", default="fp16", choices=["fp16", "bf16"],
                     help="16-bit type of the GEMM / attention operands (fp16 = the shipped default; same tensor-core rate)")
     ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the configs[3] sub-record")
+    ap.add_argument("--sharded-crops", type=int, default=1024, help="crops of the configs[3] sub-record (SURVEY: 1024)")
     ap.add_argument("--nccl-gather", action="store_true", help="gather embeddings with NCCL instead of the fused peer stores")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -179,6 +179,14 @@ ZV_API int zv_visual_forward_gather(const zv_cfg* cfg, const void* weights_dev, 
                                     const void* patches_dev, int32_t in_dtype, int32_t in_order, void* merged_out_dev,
                                     int32_t out_dtype, void* workspace_dev, int64_t workspace_bytes,
                                     void* const* peer_out_dev, int32_t n_peers, int64_t peer_row_off, void* stream);
+/* Ragged form of the fused gather (crop-sharded batches whose crops interleave in the global order): embedding k of this
+ * rank's batch (HF order) is written to row dest_rows_dev[k] of this rank's own gather buffer gather_local_dev
+ * ((gather_rows, out_hidden) of out_dtype) AND to the same row of every peer buffer.  dest_rows_dev: int64 [T] on the device. */
+ZV_API int zv_visual_forward_gather_rows(const zv_cfg* cfg, const void* weights_dev, const zv_plan* p, const void* plan_dev,
+                                         const void* patches_dev, int32_t in_dtype, int32_t in_order, void* gather_local_dev,
+                                         int64_t gather_rows, int32_t out_dtype, const int64_t* dest_rows_dev,
+                                         void* workspace_dev, int64_t workspace_bytes, void* const* peer_out_dev,
+                                         int32_t n_peers, void* stream);
 /* Same forward with the LM hand-off fused into the last GEMM's epilogue: embedding k (HF order) is written to row
  * dest_rows_dev[k] of embeds_dev, the flattened (embeds_rows, out_hidden) inputs_embeds of the language model
  * (element type embeds_dtype) - torch's inputs_embeds.masked_scatter(image_mask, image_embeds) without the

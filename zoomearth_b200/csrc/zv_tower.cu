@@ -412,6 +412,18 @@ int zv_visual_forward_gather(const zv_cfg* cfg, const void* weights_dev, const z
                              nullptr, workspace_dev, workspace_bytes, peer_out_dev, n_peers, peer_row_off, nullptr, 0, stream);
 }
 
+int zv_visual_forward_gather_rows(const zv_cfg* cfg, const void* weights_dev, const zv_plan* p, const void* plan_dev,
+                                  const void* patches_dev, int32_t in_dtype, int32_t in_order, void* gather_local_dev,
+                                  int64_t gather_rows, int32_t out_dtype, const int64_t* dest_rows_dev, void* workspace_dev,
+                                  int64_t workspace_bytes, void* const* peer_out_dev, int32_t n_peers, void* stream) {
+  if (!dest_rows_dev || !gather_local_dev) return fail(ZV_EINVAL, "zv_visual_forward_gather_rows: null argument");
+  if (gather_rows <= 0 || gather_rows > INT32_MAX) return fail(ZV_EINVAL, "zv_visual_forward_gather_rows: gather buffer has %lld rows (1 .. 2^31-1 supported)", (long long)gather_rows);
+  if (n_peers < 0 || n_peers > 8 || (n_peers > 0 && !peer_out_dev)) return fail(ZV_EINVAL, "zv_visual_forward_gather_rows: bad peer list");
+  if (out_dtype == ZV_F32) return fail(ZV_EINVAL, "zv_visual_forward_gather_rows: the fused gather writes 16-bit embeddings");
+  return visual_forward_impl(cfg, weights_dev, p, plan_dev, patches_dev, in_dtype, in_order, gather_local_dev, out_dtype,
+                             nullptr, workspace_dev, workspace_bytes, peer_out_dev, n_peers, 0, dest_rows_dev, gather_rows, stream);
+}
+
 namespace {
 int visual_forward_impl(const zv_cfg* cfg, const void* weights_dev, const zv_plan* p, const void* plan_dev,
                         const void* patches_dev, int32_t in_dtype, int32_t in_order, void* merged_out_dev,

@@ -64,6 +64,19 @@ def gather_embeddings(local_emb, local_tokens, parts, group=None):
     return out, counts
 
 
+def sharded_rows(parts, tokens):
+    """Row bookkeeping of a crop-sharded batch whose embeddings are gathered in GLOBAL crop order.  tokens: tokens of every
+    crop (global order); parts: per rank, the crop indices it owns.  Returns (starts (n + 1,) int64 - first gather row of
+    every crop - and, per rank, the int64 array of gather rows of that rank's local embeddings, crops in parts[rank] order)."""
+    tokens = np.asarray(tokens, dtype=np.int64)
+    starts = np.concatenate([[0], np.cumsum(tokens)]).astype(np.int64)
+    rows = []
+    for p in parts:
+        rows.append(np.concatenate([np.arange(starts[i], starts[i + 1], dtype=np.int64) for i in p]) if len(p)
+                    else np.zeros(0, np.int64))
+    return starts, rows
+
+
 class PeerGather:
     """Gather buffer in symmetric memory for the fused GEMM -> gather path (C1 without a collective).
 
@@ -72,20 +85,107 @@ class PeerGather:
     (merger.mlp.2 + un-reorder) then stores each embedding row into its own buffer and, over NVLink, into every
     peer's buffer at the same global row, so after one cross-rank barrier each rank holds all embeddings - the
     transfer overlaps the GEMM tile by tile and no NCCL collective runs on the data path.
+
+    ``double_buffer=True``: two buffers alternate per step and the barrier of step i runs on a side stream; the main
+    stream only waits for it at the start of step i + 1 (``begin_step``), i.e. a rank that finishes early starts its next
+    step instead of idling until the slowest (power-capped) GPU arrives.  Contract: the buffer ``begin_step`` returns as
+    ``ready`` holds the previous step's gather; read it on the current stream before the next ``begin_step``.
     """
 
-    def __init__(self, rows_total, dim, dtype, device, group=None):
+    def __init__(self, rows_total, dim, dtype, device, group=None, double_buffer=False):
         import torch.distributed._symmetric_memory as symm_mem
         self.group = group if group is not None else dist.group.WORLD
         self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
-        self.buffer = symm_mem.empty((rows_total, dim), dtype=dtype, device=device)
-        self.handle = symm_mem.rendezvous(self.buffer, self.group)
-        ptrs = [int(p) for p in self.handle.buffer_ptrs]
-        self.local_ptr = ptrs[self.rank]
-        self.peer_ptrs = [p for r, p in enumerate(ptrs) if r != self.rank]
-        if len(self.peer_ptrs) > 8:
+        self.rows_total, self.dim, self.n_buf = int(rows_total), int(dim), 2 if double_buffer else 1
+        self._all = symm_mem.empty((self.n_buf * self.rows_total, dim), dtype=dtype, device=device)
+        self.handle = symm_mem.rendezvous(self._all, self.group)
+        self._base_ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        if len(self._base_ptrs) - 1 > 8:
             raise ValueError("the fused gather supports at most 9 ranks per node")
+        self._stride = self.rows_total * dim * self._all.element_size()
+        self.cur = 0
+        self._side = torch.cuda.Stream(device) if double_buffer else None
+        self._pending = None                       # event: the async barrier of the last finished step
+        self._select(0)
+
+    def _select(self, b):
+        self.cur = b
+        self.buffer = self._all[b * self.rows_total:(b + 1) * self.rows_total]
+        self.local_ptr = self._base_ptrs[self.rank] + b * self._stride
+        self.peer_ptrs = [p + b * self._stride for r, p in enumerate(self._base_ptrs) if r != self.rank]
 
     def barrier(self):
         """All ranks' stores are visible after this (device-side barrier over the signal pads, on the current stream)."""
-        self.handle.barrier()
+        self.handle.barrier(channel=self.cur)
+
+    # ---- pipelined form (double_buffer=True)
+    def begin_step(self):
+        """Waits (on the current stream) for the previous step's barrier, then switches to the other buffer.  Returns the
+        buffer that is now complete on every rank (None before the first step)."""
+        ready = None
+        if self._pending is not None:
+            torch.cuda.current_stream(self._all.device).wait_event(self._pending)
+            self._pending = None
+            ready = self.buffer
+        if self.n_buf == 2:
+            self._select(self.cur ^ 1)
+        return ready
+
+    def end_step(self):
+        """Call after the step's kernels are enqueued: the cross-rank barrier runs on a side stream behind them."""
+        if self._side is None:
+            self.barrier()
+            return
+        dev = self._all.device
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(ev)
+            self.handle.barrier(channel=self.cur)
+            done = torch.cuda.Event()
+            done.record(self._side)
+        self._pending = done
+
+    def finish(self):
+        """Waits for the last step's barrier on the current stream; returns that step's buffer."""
+        if self._pending is not None:
+            torch.cuda.current_stream(self._all.device).wait_event(self._pending)
+            self._pending = None
+        return self.buffer
+
+
+def encode_sharded(enc, images_dev, boxes, image_index, gather, max_patches=400_000, apply_cut_image=True):
+    """configs[3] / [4]: a ragged crop list sharded over the ranks by LPT partition, every rank encoding its crops in
+    bounded micro-batches whose last GEMM scatters each embedding row straight to its GLOBAL row of every rank's gather
+    buffer (``zv_visual_forward_gather_rows``) - no padded all-gather, no per-crop copy loop.  Source images are
+    replicated.  Returns (gather buffer rows [0, T_total) in global crop order - complete after ``gather.barrier()`` /
+    ``end_step()`` -, per-crop token counts, parts)."""
+    from . import geometry
+    rank, world = gather.rank, gather.world
+    n = len(boxes)
+    idx = list(range(n)) if image_index is None else [int(i) for i in image_index]
+    cfg = enc.processor._cfg()
+    if not apply_cut_image:
+        cfg.min_size = -1
+    img_hw = np.array([[images_dev[i].shape[0], images_dev[i].shape[1]] for i in idx], np.int32)
+    _, _, grid = geometry.geometry(cfg, img_hw, np.asarray(boxes, np.float64).reshape(n, 4))
+    tokens = (grid[:, 0] * grid[:, 1] * grid[:, 2]) // enc.visual.spatial_merge_unit
+    parts = partition(crop_cost(grid), world)
+    starts, rows = sharded_rows(parts, tokens)
+    if starts[-1] > gather.rows_total:
+        raise ValueError(f"gather buffer holds {gather.rows_total} rows, the batch needs {int(starts[-1])}")
+    mine = parts[rank]
+    launches = 0
+    if mine:
+        lb = [boxes[i] for i in mine]
+        li = [idx[i] for i in mine]
+        dev = images_dev[0].device
+        for g in enc.micro_batches(images_dev, lb, li, max_patches, apply_cut_image):
+            used = sorted({li[i] for i in g})
+            local = {k: j for j, k in enumerate(used)}
+            r = torch.from_numpy(np.concatenate([np.arange(starts[mine[i]], starts[mine[i] + 1], dtype=np.int64) for i in g])).to(dev)
+            enc.encode([images_dev[k] for k in used], [lb[i] for i in g], image_index=[local[li[i]] for i in g],
+                       apply_cut_image=apply_cut_image, gather=gather, gather_rows=r)
+            launches += enc.last_launches
+    enc.last_launches = launches
+    return gather.buffer[: int(starts[-1])], tokens, parts

@@ -159,7 +159,7 @@ class FusedVisual(nn.Module):
 
     @torch.no_grad()
     def forward(self, hidden_states, grid_thw, window_order=False, return_hidden=False, gather=None, gather_row=0,
-                use_graph=False, **kwargs):
+                use_graph=False, gather_rows=None, **kwargs):
         if use_graph and gather is None and not return_hidden and not self.return_pooling_output:
             x = hidden_states
             if x.dtype not in _DT or (x.dtype != torch.float32 and x.dtype != self.operand_dtype):
@@ -173,7 +173,7 @@ class FusedVisual(nn.Module):
             # (0.3 MB for a 512-px crop) unless the caller asked for the buffer itself
             return out if kwargs.get("graph_static_output") else out.clone()
         plan = self.plan_for(grid_thw)
-        return self._forward_impl(hidden_states, plan, window_order, return_hidden, gather, gather_row)
+        return self._forward_impl(hidden_states, plan, window_order, return_hidden, gather, gather_row, gather_rows=gather_rows)
 
     @torch.no_grad()
     def forward_into(self, inputs_embeds, dest_rows, hidden_states, grid_thw, window_order=False, validate_rows=True):
@@ -219,7 +219,7 @@ class FusedVisual(nn.Module):
             raise ValueError(f"pixel_values has shape {tuple(x.shape)}, grid_thw implies ({plan.num_patches}, 1176)")
         return x
 
-    def _forward_impl(self, hidden_states, plan, window_order, return_hidden, gather, gather_row, out=None):
+    def _forward_impl(self, hidden_states, plan, window_order, return_hidden, gather, gather_row, out=None, gather_rows=None):
         """hidden_states: (S, 1176) patches, float32/bfloat16, HF row order (or the window-ordered bf16 output of
         the fused preprocess when ``window_order=True``).  ``gather`` (a ``sharding.PeerGather``) fuses the multi-GPU
         embedding gather into the last GEMM: this rank's rows land at ``gather_row`` of every rank's gather buffer."""
@@ -237,7 +237,18 @@ class FusedVisual(nn.Module):
                 out = torch.empty((plan.num_tokens, self.cfg.out_hidden), dtype=self._dtype, device=self._device)
             hidden = (torch.empty((plan.num_patches, self.cfg.hidden), dtype=torch.float32, device=self._device)
                       if (return_hidden or self.return_pooling_output) else None)
-            if gather is not None:
+            if gather is not None and gather_rows is not None:
+                # ragged form: embedding k of this batch lands at row gather_rows[k] of every rank's gather buffer
+                if gather_rows.dtype != torch.int64 or gather_rows.device != self._device or gather_rows.numel() != plan.num_tokens:
+                    raise ValueError(f"gather_rows must be {plan.num_tokens} int64 row indices on {self._device}")
+                peers = (C.c_void_p * max(1, len(gather.peer_ptrs)))(*gather.peer_ptrs)
+                _lib.check(lib.zv_visual_forward_gather_rows(
+                    C.byref(self.cfg), self.packed_weights.data_ptr(), plan.handle, tables.data_ptr(), x.data_ptr(),
+                    _DT[x.dtype], _lib.ORDER_WINDOW if window_order else _lib.ORDER_HF, gather.buffer.data_ptr(),
+                    gather.buffer.shape[0], _DT[self._dtype], gather_rows.contiguous().data_ptr(), ws.data_ptr(), ws.numel(),
+                    peers, len(gather.peer_ptrs), stream))
+                out = gather.buffer
+            elif gather is not None:
                 peers = (C.c_void_p * len(gather.peer_ptrs))(*gather.peer_ptrs)
                 _lib.check(lib.zv_visual_forward_gather(
                     C.byref(self.cfg), self.packed_weights.data_ptr(), plan.handle, tables.data_ptr(), x.data_ptr(),

@@ -84,13 +84,14 @@ class ZoomEncoder:
 
     @torch.no_grad()
     def encode(self, images_dev, boxes=None, image_index=None, apply_cut_image=True, return_patches=False,
-               gather=None, gather_row=0, use_graph=False, pre_resize="default"):
+               gather=None, gather_row=0, use_graph=False, pre_resize="default", gather_rows=None):
         """images_dev: resident images; boxes (n, 4) in image pixels (None = global view of every image).
         Returns (embeddings (T, out_hidden), image_grid_thw (n, 3), crop boxes (n, 4)).  ``pre_resize`` overrides the
         encoder's setting for this call (see ``__init__``)."""
         pr = self.pre_resize if isinstance(pre_resize, str) and pre_resize == "default" else self._norm_pre_resize(pre_resize)
         pv, grid, crop, k1 = self._patches(images_dev, boxes, image_index, apply_cut_image, pr)
-        emb = self.visual(pv, grid, window_order=True, gather=gather, gather_row=gather_row, use_graph=use_graph)
+        emb = self.visual(pv, grid, window_order=True, gather=gather, gather_row=gather_row, use_graph=use_graph,
+                          gather_rows=gather_rows)
         self.last_launches = k1 + self.visual.last_launches
         if return_patches:
             return emb, grid, crop, pv
