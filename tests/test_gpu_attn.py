@@ -6,7 +6,11 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-@pytest.mark.parametrize("segs", [[64], [64, 64, 32, 16, 4], [100], [4900 // 4 * 4], [1, 7, 129, 64, 200], [2048, 36]])
+@pytest.mark.parametrize("segs", [[64], [64, 64, 32, 16, 4], [100], [4900 // 4 * 4], [1, 7, 129, 64, 200], [2048, 36],
+                                  # window layers (every segment <= 64 rows: the tcgen05 window kernel): the bench shape's window
+                                  # sizes, every multiple of 4, blocks that end with tiny windows, odd sizes, hundreds of windows
+                                  [64] * 8 + [48] + [64] * 8 + [48] + [48] * 8 + [36], list(range(4, 68, 4)), [64, 60, 4, 4, 4, 64, 12],
+                                  [4], [1, 7, 33, 64, 5, 63, 2], [64] * 300 + [16] * 7 + [48] * 41])
 def test_attention_vs_sdpa(cuda, lib, segs, dtype):
     import numpy as np
     from zoomearth_b200 import _lib

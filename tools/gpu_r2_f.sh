@@ -1,0 +1,17 @@
+#!/bin/bash
+# Round-2 run F: tcgen05 window attention - parity, bench, ncu; latency breakdown of one zoom step
+mkdir -p gpurun_out
+rc=0
+for f in tests/test_gpu_attn.py tests/test_gpu_tower.py tests/test_gpu_configs.py; do
+  n=$(basename $f .py)
+  timeout 900 python -m pytest $f -q -s -m gpu --timeout 600 -p no:cacheprovider -x > gpurun_out/$n.log 2>&1
+  r=$?; echo "== $f exit $r: $(grep -E 'passed|failed' gpurun_out/$n.log | tail -n 1)"; [ $r -ne 0 ] && { rc=1; grep -E "^(FAILED|ERROR)|^E |zoomvit:" gpurun_out/$n.log | head -30; }
+done
+grep -h PARITY gpurun_out/test_gpu_*.log | head -20
+if [ $rc -eq 0 ]; then
+timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu --no-sharded > gpurun_out/bench_f.json 2> gpurun_out/bench_f.err; python -c "
+import json; d=json.load(open('gpurun_out/bench_f.json')); print(round(d['value']), round(d['ms_per_step'],1), 'e2e', round(d['e2e']['value']), d['clocks'], d['kernel_ms'], d['latency'], d['roofline_attn'])"
+python tools/latency_breakdown.py > gpurun_out/latency_breakdown.json 2> gpurun_out/latency_breakdown.err; cat gpurun_out/latency_breakdown.json | tr -d '\n '; echo
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"attn_win_tc" -s 30 -c 1 -o gpurun_out/prof_attn_win_tc -f python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --no-latency --no-sharded --images 8 > gpurun_out/ncu_win.log 2>&1; echo "ncu exit $?"
+fi
+exit $rc

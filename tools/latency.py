@@ -2,6 +2,10 @@
 import sys, time, json
 import numpy as np, torch
 sys.path.insert(0, ".")
+from zoomearth_b200 import _lib
+if len(sys.argv) > 2 and sys.argv[1] == "--lib":            # build variants (experiments only)
+    import os
+    _lib.LIB_PATH = os.path.abspath(sys.argv[2])
 from zoomearth_b200 import FusedImageProcessor, FusedVisual, ZoomEncoder
 from zoomearth_b200.synthetic import random_vision_state_dict
 dev = torch.device("cuda", 0)

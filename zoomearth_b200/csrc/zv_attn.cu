@@ -233,6 +233,7 @@ __global__ void __launch_bounds__(128, 3) attn_window_kernel(const __nv_bfloat16
 
   int item = blockIdx.x;
   if (item >= n_items) return;
+  ptx::pdl_wait();                                  // qkv (the QKV GEMM's output) is complete from here on
   int4 tl = __ldg(tiles + item / heads);
   int4 tl_next = item + (int)gridDim.x < n_items ? __ldg(tiles + (item + gridDim.x) / heads) : tl;
   issue_loads(tl, item, 0);
@@ -323,6 +324,7 @@ __global__ void __launch_bounds__(128, 3) attn_window_kernel(const __nv_bfloat16
     tl = tl_next;
     tl_next = tl_after;
   }
+  ptx::pdl_trigger();
 }
 
 template <bool F16>
@@ -340,9 +342,9 @@ int launch_window(const void* qkv, void* out, int heads, const int32_t* tiles_de
   const int grid = n_items < 3 * n_sm ? n_items : 3 * n_sm;
   NvtxRange nvtx("zv:K3 window attention");
   KernelTimer timer(KC_ATTN_WINDOW, stream_);
-  attn_window_kernel<F16><<<grid, 128, kSmem, static_cast<cudaStream_t>(stream_)>>>(
-      static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), reinterpret_cast<const int4*>(tiles_dev),
-      n_items, heads, scale_log2);
+  launch_pdl(attn_window_kernel<F16>, dim3((unsigned)grid), dim3(128), kSmem, static_cast<cudaStream_t>(stream_), 1,
+             static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), reinterpret_cast<const int4*>(tiles_dev),
+             n_items, heads, scale_log2);
   return ZV_OK;
 }
 

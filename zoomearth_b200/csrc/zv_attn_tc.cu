@@ -42,14 +42,23 @@ namespace {
 constexpr int HD = 80, BQ = 128, BKV = 64, STAGES = 4, kCtasPerSm = 2;
 constexpr int kK64 = BKV * 64 * 2, kK16 = BKV * 16 * 2;                   // 8192, 2048: [rows][64] and [rows][16] blocks
 constexpr int kStage = 2 * (kK64 + kK16);                                // 20480: K and V tiles have the same shape
-constexpr int kOffBar = STAGES * kStage;
+constexpr int kOffOnes = STAGES * kStage;                                // [16][64] 16-bit ones: B operand of the row-sum MMA
+constexpr int kOnesBytes = 16 * 64 * 2;
+constexpr int kOffBar = kOffOnes + kOnesBytes;
 constexpr int kSmem = kOffBar + 256 + 1024;
-// TMEM columns: S [0,64)  O [64,144)  P [144,176) 16-bit pairs  Q [176,216) 16-bit pairs
-constexpr int kTmemCols = 256, kOCol = BKV, kPCol = kOCol + HD, kQCol = kPCol + BKV / 2;
+// TMEM columns: S [0,64)  O [64,144)  P [144,176) 16-bit pairs  Q [176,216) 16-bit pairs  L [216,232) row sums of P
+constexpr int kTmemCols = 256, kOCol = BKV, kPCol = kOCol + HD, kQCol = kPCol + BKV / 2, kLCol = kQCol + HD / 2;
+// every kPolyEvery-th pair of exponentials is evaluated on the FMA pipe (Cody-Waite + a cubic) instead of MUFU.EX2: the
+// softmax warps are bound by the 16 ex2 / clk / SM of the SFU (512 clk per 128 x 64 tile against 320 clk of MMA)
+#ifndef ZV_ATTN_POLY_EVERY
+#define ZV_ATTN_POLY_EVERY 4
+#endif
+constexpr int kPolyEvery = ZV_ATTN_POLY_EVERY;                           // 0 = all on the SFU
 constexpr int kThreads = 192;
 constexpr uint32_t kSw128 = 2, kSw32 = 6;                                // UMMA descriptor layout types
 static_assert(kStage % 1024 == 0 && (kK64 + kK16) % 1024 == 0 && kK64 % 1024 == 0, "swizzle atom alignment");
-static_assert(kQCol + HD / 2 <= kTmemCols, "TMEM budget");
+static_assert(kLCol + 16 <= kTmemCols, "TMEM budget");
+static_assert(kOffOnes % 1024 == 0, "swizzle atom alignment of the ones tile");
 static_assert(STAGES <= 4, "mbarrier slots");
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout) {
@@ -112,6 +121,22 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
       : "memory");
 }
 
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+// 2^x for x in [-125, 125] on the FMA / ALU pipes: n = round(x) by the magic-number add, 2^f on [-0.5, 0.5] by a cubic
+// (max rel err 7.5e-5, a sixth of the 16-bit rounding P gets anyway), exponent patched in with an integer add.
+__device__ __forceinline__ float exp2_poly(float x) {
+  const float t = x + 12582912.f;                           // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float f = x - (t - 12582912.f);
+  float p = fmaf(f, 0.05517084f, 0.24260935f);              // minimax cubic of 2^f on [-0.5, 0.5] (relative error)
+  p = fmaf(p, f, 0.69326097f);
+  p = fmaf(p, f, 0.99992818f);
+  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));
+}
+
 struct AttnArgs {
   void* out;
   const void* qkv;           // (S, 3 * hidden) 16-bit: the q rows are read directly, K goes through TMA
@@ -170,10 +195,17 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) attn_tc_kernel(const __g
     fence_mbar_init();
   }
   if (warp == 0) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
+  {
+    // B operand of the row-sum MMA: 16 x 64 ones (every element equal, so the swizzle pattern is irrelevant)
+    uint32_t* ones = reinterpret_cast<uint32_t*>(smem + kOffOnes);
+    for (int i = threadIdx.x; i < kOnesBytes / 4; i += kThreads) ones[i] = F16 ? 0x3C003C00u : 0x3F803F80u;
+    fence_proxy_async();                           // generic-proxy stores -> visible to the tensor core (async proxy)
+  }
   tc_fence_before();
   cluster_sync_all();                             // both CTAs' barriers exist before either multicasts into the other
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();                                     // qkv (the previous kernel's output) is complete from here on
 
   if (warp == 0) {
     if (elect_one()) {
@@ -222,6 +254,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) attn_tc_kernel(const __g
       // ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units = rows of one kv, 8-row groups SBO apart (CUTLASS make_umma_desc)
       const uint32_t idesc_pv64 = umma_idesc_16bit(BQ, 64, F16) | (1u << 16);
       const uint32_t idesc_pv16 = umma_idesc_16bit(BQ, 16, F16) | (1u << 16);
+      // row sums l = P 1: the same P the P V product consumes, summed exactly in fp32 by the tensor core (K-major B of ones)
+      const uint32_t idesc_l = umma_idesc_16bit(BQ, 16, F16);
+      const uint64_t desc_ones = umma_desc(smem_u32(smem + kOffOnes), 1024, kSw128);
       auto issue_qk = [&](int t) {
         const int st = t % STAGES;
         const uint32_t sk = smem_u32(smem + st * kStage);
@@ -249,6 +284,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) attn_tc_kernel(const __g
           // 16 kv rows per step: 2048 B of the [64][64] block, 512 B of the [64][16] block
           umma_ts(tmem + kOCol, tmem + kPCol + 8 * ks, umma_desc(sv, 1024, kSw128) + 128 * ks, idesc_pv64, (j | ks) != 0);
           umma_ts(tmem + kOCol + 64, tmem + kPCol + 8 * ks, umma_desc(sv + kK64, 256, kSw32) + 32 * ks, idesc_pv16, (j | ks) != 0);
+          umma_ts(tmem + kLCol, tmem + kPCol + 8 * ks, desc_ones + 2 * ks, idesc_l, (j | ks) != 0);
         }
         if (shared_kv) umma_commit_mc(v_empty + st, 3); else umma_commit(v_empty + st);
         umma_commit(pv_done);
@@ -263,8 +299,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) attn_tc_kernel(const __g
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const float sl2 = a.scale_log2;
-    float m_used = -INFINITY;               // scale in use (raw score units)
-    float l_run = 0.f;                      // running sum of the row's probabilities, in that scale
+    float m_used = -INFINITY;               // scale in use (raw score units); the row sum lives in TMEM next to O
 
     // Q row -> TMEM (A operand of every Q K^T): 80 16-bit values = 40 columns.  Rows past the end of the tensor read as 0.
     {
@@ -302,6 +337,14 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) attn_tc_kernel(const __g
         for (int i = 0; i < 16; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * factor);
         tmem_st_x16(tmem + lane_addr + kOCol + c, t);
       }
+      {                                      // ... and the row sum (16 identical columns; one chunk)
+        uint32_t t[16];
+        tmem_ld_x16(tmem + lane_addr + kLCol, t);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * factor);
+        tmem_st_x16(tmem + lane_addr + kLCol, t);
+      }
       tmem_st_wait();
       tc_fence_before();
     };
@@ -328,11 +371,12 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) attn_tc_kernel(const __g
 #pragma unroll
         for (int i = 0; i < BKV; ++i) if (i < lo || i >= hi) s[i] = -INFINITY;
       }
-      float mx4[4] = {s[0], s[1], s[2], s[3]};          // four independent chains, not one deep dependency
+      // row max with three-input FMNMX3: four independent chains of 2 values per instruction (32 instead of 64)
+      float mx4[4] = {fmaxf(s[0], s[1]), fmaxf(s[2], s[3]), fmaxf(s[4], s[5]), fmaxf(s[6], s[7])};
 #pragma unroll
-      for (int i = 4; i < BKV; i += 4) {
-        mx4[0] = fmaxf(mx4[0], s[i]); mx4[1] = fmaxf(mx4[1], s[i + 1]);
-        mx4[2] = fmaxf(mx4[2], s[i + 2]); mx4[3] = fmaxf(mx4[3], s[i + 3]);
+      for (int i = 8; i < BKV; i += 8) {
+        mx4[0] = fmax3(mx4[0], s[i], s[i + 1]); mx4[1] = fmax3(mx4[1], s[i + 2], s[i + 3]);
+        mx4[2] = fmax3(mx4[2], s[i + 4], s[i + 5]); mx4[3] = fmax3(mx4[3], s[i + 6], s[i + 7]);
       }
       const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       // the first tile of a segment always holds a valid column, so m_used is finite from then on; a later tile that
@@ -343,15 +387,18 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) attn_tc_kernel(const __g
       // the exponentials only need registers: they run while the tensor core is still busy with P_{j-1} V_{j-1}
       const float ms = m_used * sl2;
       uint32_t pk[BKV / 2];
-      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int i = 0; i < BKV / 2; ++i) {
-        const float p0 = ex2_approx(s[2 * i] * sl2 - ms), p1 = ex2_approx(s[2 * i + 1] * sl2 - ms);
-        sum4[(2 * i) & 3] += p0;
-        sum4[(2 * i + 1) & 3] += p1;
+        const float x0 = fmaf(s[2 * i], sl2, -ms), x1 = fmaf(s[2 * i + 1], sl2, -ms);
+        float p0, p1;
+        // interior tiles only: a masked column is -inf, which the SFU maps to 0 and the polynomial cannot
+        if (!MASK && kPolyEvery > 0 && (i % (kPolyEvery > 0 ? kPolyEvery : 1)) == kPolyEvery - 1) {
+          p0 = exp2_poly(fmaxf(x0, -120.f)); p1 = exp2_poly(fmaxf(x1, -120.f));
+        } else {
+          p0 = ex2_approx(x0); p1 = ex2_approx(x1);
+        }
         pk[i] = pack2<F16>(p0, p1);
       }
-      l_run = l_run * factor + ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
       if (j > 0) {
         mbar_wait(pv_done, (j - 1) & 1);                     // the tensor core is done with P_{j-1}; O_{j-1} accumulated
         if (__any_sync(0xffffffffu, grow)) rescale_o(factor);
@@ -370,7 +417,13 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) attn_tc_kernel(const __g
     }
     mbar_wait(pv_done, (n_kv - 1) & 1);
     tc_fence_after();
-    const float inv = 1.f / l_run;
+    float inv;
+    {
+      uint32_t t[16];
+      tmem_ld_x16(tmem + lane_addr + kLCol, t);
+      tmem_ld_wait();
+      inv = 1.f / __uint_as_float(t[0]);
+    }
     uint16_t* dst = static_cast<uint16_t*>(a.out) + (int64_t)(q0 + row) * a.hidden + head * HD;
 #pragma unroll
     for (int c = 0; c < 80; c += 16) {
@@ -389,6 +442,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) attn_tc_kernel(const __g
     }
     tc_fence_before();
   }
+  pdl_trigger();
   tc_fence_before();
   cluster_sync_all();                             // the partner's last multicast arrivals have landed before this CTA exits
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, kTmemCols); }
@@ -417,22 +471,14 @@ int attention_tc(const void* qkv, void* out, int64_t S, int heads, int head_dim,
   AttnArgs a{};
   a.out = out; a.qkv = qkv; a.S = S; a.tiles = reinterpret_cast<const int4*>(tiles_dev); a.n_tiles = n_tiles; a.heads = heads; a.hidden = hidden; a.f16 = f16;
   a.scale_log2 = (float)(1.4426950408889634 / std::sqrt((double)head_dim));
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)((n_tiles + 1) & ~1), (unsigned)heads);      // clusters of two neighbouring q tiles
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = kSmem;
-  cfg.stream = static_cast<cudaStream_t>(stream_);
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  const dim3 grid((unsigned)((n_tiles + 1) & ~1), (unsigned)heads);      // clusters of two neighbouring q tiles
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   cudaError_t le;
   {
     NvtxRange nvtx("zv:K4 full attention (tcgen05)");
     KernelTimer timer(KC_ATTN_FULL, stream_);
-    le = f16 ? cudaLaunchKernelEx(&cfg, attn_tc_kernel<true>, t64, t16, a)
-             : cudaLaunchKernelEx(&cfg, attn_tc_kernel<false>, t64, t16, a);
+    le = f16 ? launch_pdl(attn_tc_kernel<true>, grid, dim3(kThreads), kSmem, stream, 2, t64, t16, a)
+             : launch_pdl(attn_tc_kernel<false>, grid, dim3(kThreads), kSmem, stream, 2, t64, t16, a);
   }
   if (le != cudaSuccess) return fail(ZV_ECUDA, "attention_tc: launch: %s", cudaGetErrorString(le));
   count_launch();

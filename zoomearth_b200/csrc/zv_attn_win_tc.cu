@@ -1,0 +1,344 @@
+// K3: tcgen05 window attention for the 28 windowed layers (HF modeling_qwen2_5_vl.py:207-287 with cu_window_seqlens:
+// segments = windows of <= 64 patches, :498-502).
+//
+// The layer is bandwidth-bound (10.2 KB per patch: q, k, v in, attention out) but the mma.sync kernel it replaces was
+// bound by instruction issue at the power-capped clock of the bench (1 600 warp instructions per (window, head): ldmatrix,
+// mma.sync, shuffles).  Here the tensor core does both products from TMA-staged shared memory and a thread only runs the
+// softmax of one row:
+//   item       (row block, head): a row block = up to 128 CONSECUTIVE rows holding whole windows (the plan packs windows
+//              greedily; in window order the windows of an image are contiguous), so one TMA box per operand fetches it
+//   loads      warp 0: Q, K, V tiles [128 rows][80] as a 128B-swizzled [128][64] block + a 32B-swizzled [128][16] block
+//              each (TMA out-of-bounds rows read as zero), 3-stage ring, one mbarrier per stage
+//   S = Q K^T  warp 1: tcgen05.mma M=128 N=128, A and B from shared memory, 4 + 1 K steps, fp32 S in TMEM.  S covers the
+//              whole block: entries that pair rows of different windows are masked by the softmax (block-diagonal)
+//   softmax    warps 2-5, thread = row: the row's window is columns [cb, ce) of the block (per-row bounds table of the
+//              plan); two passes over the 32-column chunks that intersect it (max, then exp2 / sum); P is rounded to 16 bit
+//              and written over the consumed S columns (S and P share a TMEM buffer), zeros outside the window
+//   O = P V    warp 1: A = P from TMEM, B = V as it lies in qkv (MN-major), 8 K steps of one N=64 + one N=16 MMA
+//   epilogue   warps 2-5: O row * 1/l -> 16 bit -> global
+// S/P and O are double-buffered in TMEM (2 x 128 + 2 x 80 columns), so the products of item i+1 run under the softmax of
+// item i and the epilogue of item i runs after the softmax of item i+1.  Persistent: one CTA per SM walks the items.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+
+#include "zv_common.h"
+#include "zv_gemm.h"
+#include "zv_ptx.cuh"
+
+namespace zv {
+using namespace ptx;
+namespace {
+
+constexpr int HD = 80, BR = 128, STAGES = 3, kThreads = 192;
+constexpr int kB64 = BR * 64 * 2, kB16 = BR * 16 * 2;                      // 16384, 4096
+constexpr int kTile = kB64 + kB16;                                        // 20480: one of Q, K, V
+constexpr int kStage = 3 * kTile;                                         // 61440
+constexpr int kOffBar = STAGES * kStage;
+constexpr int kSmem = kOffBar + 256 + 1024;
+constexpr int kTmemCols = 512, kOCol = 256;                               // S/P buffer b at [128 b, 128 b + 128), O buffer b at [256 + 80 b, ..)
+constexpr uint32_t kSw128 = 2, kSw32 = 6;                                 // UMMA descriptor layout types
+static_assert(kTile % 1024 == 0 && kB64 % 1024 == 0 && kStage % 1024 == 0, "swizzle atom alignment");
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+template <bool F16>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  if constexpr (F16) { __half2 v = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&v); }
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+struct WinArgs {
+  void* out;
+  const int4* tiles;          // (row0, n_rows, -, -): row blocks of whole windows
+  const int2* bounds;         // [S]: (first row, end row) of the window each patch row belongs to
+  int n_tiles, heads, hidden;
+  float scale_log2;
+};
+
+template <bool F16>
+__global__ void __launch_bounds__(kThreads, 1) attn_win_tc_kernel(const __grid_constant__ CUtensorMap tm64,
+                                                                  const __grid_constant__ CUtensorMap tm16, const WinArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* load_full = bars;            // STAGES
+  uint64_t* load_empty = bars + 3;       // STAGES
+  uint64_t* s_full = bars + 6;           // 2
+  uint64_t* p_full = bars + 8;           // 2
+  uint64_t* o_full = bars + 10;          // 2
+  uint64_t* o_empty = bars + 12;         // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tm64); prefetch_tensormap(&tm16);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(load_full + s, 1); mbar_init(load_empty + s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(s_full + b, 1); mbar_init(p_full + b, 4); mbar_init(o_full + b, 1); mbar_init(o_empty + b, 4); }
+    fence_mbar_init();
+  }
+  if (warp == 0) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  pdl_wait();                                     // qkv (the QKV GEMM's output) is complete from here on
+
+  const int n_items = a.n_tiles * a.heads;
+  const int first = blockIdx.x, step = gridDim.x;
+  const int n_mine = first < n_items ? (n_items - first + step - 1) / step : 0;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // ---- TMA producer
+      for (int k = 0; k < n_mine; ++k) {
+        const int item = first + k * step;
+        const int st = k % STAGES;
+        const uint32_t ph = (k / STAGES) & 1;
+        const int row0 = __ldg(&a.tiles[item / a.heads]).x;
+        const int head = item % a.heads;
+        uint8_t* s = smem + st * kStage;
+        mbar_wait(load_empty + st, ph ^ 1);
+        mbar_arrive_expect_tx(load_full + st, kStage);
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {               // q, k, v column groups of qkv
+          const int col = t * a.hidden + head * HD;
+          tma_load_2d(s + t * kTile, &tm64, load_full + st, col, row0);
+          tma_load_2d(s + t * kTile + kB64, &tm16, load_full + st, col + 64, row0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // ---- MMA issuer
+      const uint32_t idesc_qk = umma_idesc_16bit(BR, BR, F16);
+      const uint32_t idesc_pv64 = umma_idesc_16bit(BR, 64, F16) | (1u << 16);    // B = V is MN-major (transpose-B bit)
+      const uint32_t idesc_pv16 = umma_idesc_16bit(BR, 16, F16) | (1u << 16);
+      auto issue_qk = [&](int k) {
+        const int st = k % STAGES, b = k & 1;
+        // S/P buffer b was last read by P V of item k - 2 (its A operand): that product must have retired
+        if (k >= 2) mbar_wait(o_full + b, ((k - 2) >> 1) & 1);
+        mbar_wait(load_full + st, (k / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t sq = smem_u32(smem + st * kStage), sk = sq + kTile;
+        const uint32_t d = tmem + b * BR;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_bf16(d, umma_desc(sq, 1024, kSw128) + 2 * ks, umma_desc(sk, 1024, kSw128) + 2 * ks, idesc_qk, ks != 0);
+        umma_bf16(d, umma_desc(sq + kB64, 256, kSw32), umma_desc(sk + kB64, 256, kSw32), idesc_qk, 1);
+        umma_commit(s_full + b);
+      };
+      if (n_mine > 0) issue_qk(0);
+      for (int k = 0; k < n_mine; ++k) {
+        if (k + 1 < n_mine) issue_qk(k + 1);
+        const int st = k % STAGES, b = k & 1;
+        const uint32_t sv = smem_u32(smem + st * kStage + 2 * kTile);
+        mbar_wait(p_full + b, (k >> 1) & 1);
+        mbar_wait(o_empty + b, ((k >> 1) & 1) ^ 1);          // the epilogue of item k - 2 has the old O in registers
+        tc_fence_after();
+        const uint32_t o = tmem + kOCol + b * HD, pa = tmem + b * BR;
+#pragma unroll
+        for (int ks = 0; ks < BR / 16; ++ks) {
+          // 16 kv rows per step: 2048 B of the [128][64] block, 512 B of the [128][16] block
+          umma_ts(o, pa + 8 * ks, umma_desc(sv, 1024, kSw128) + 128 * ks, idesc_pv64, ks != 0);
+          umma_ts(o + 64, pa + 8 * ks, umma_desc(sv + kB64, 256, kSw32) + 32 * ks, idesc_pv16, ks != 0);
+        }
+        umma_commit(load_empty + st);
+        umma_commit(o_full + b);
+      }
+    }
+  } else {
+    // ---- softmax + epilogue warps: thread = row of the block
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const float sl2 = a.scale_log2;
+
+    // softmax of item k; returns the row sum (0 for rows outside the block)
+    auto softmax_item = [&](int k) -> float {
+      const int item = first + k * step;
+      const int b = k & 1;
+      const int4 tl = __ldg(&a.tiles[item / a.heads]);
+      const bool valid = row < tl.y;
+      int cb = 0, ce = 0;
+      if (valid) { const int2 w = __ldg(&a.bounds[tl.x + row]); cb = w.x - tl.x; ce = w.y - tl.x; }
+      const uint32_t sbuf = tmem + lane_addr + b * BR;
+      mbar_wait(s_full + b, (k >> 1) & 1);
+      tc_fence_after();
+      // pass 1: row maximum over the row's window
+      float m = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const bool need = cb < 32 * (c + 1) && ce > 32 * c;
+        if (!__any_sync(0xffffffffu, need)) continue;
+        uint32_t r[32];
+        tmem_ld_x32(sbuf + 32 * c, r);
+        tmem_ld_wait();
+        const bool full = __all_sync(0xffffffffu, cb <= 32 * c && ce >= 32 * (c + 1));
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        if (full) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(r[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int col = 32 * c + i;
+            m4[i & 3] = fmaxf(m4[i & 3], (col >= cb && col < ce) ? __uint_as_float(r[i]) : -INFINITY);
+          }
+        }
+        m = fmaxf(m, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+      }
+      const float ms = valid ? m * sl2 : 0.f;
+      // pass 2: exponentials, row sum, P over the consumed S columns (P chunk c lives in columns [16 c, 16 c + 16), which
+      // only overlap S chunks <= c / 2: already consumed when it is written)
+      float l4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const bool need = cb < 32 * (c + 1) && ce > 32 * c;
+        uint32_t pk[16];
+        if (__any_sync(0xffffffffu, need)) {
+          uint32_t r[32];
+          tmem_ld_x32(sbuf + 32 * c, r);
+          tmem_ld_wait();
+          const bool full = __all_sync(0xffffffffu, cb <= 32 * c && ce >= 32 * (c + 1));
+          if (full) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * i]), sl2, -ms));
+              const float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), sl2, -ms));
+              l4[i & 3] += p0 + p1;
+              pk[i] = pack2<F16>(p0, p1);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int col = 32 * c + 2 * i;
+              const float p0 = (col >= cb && col < ce) ? ex2_approx(fmaf(__uint_as_float(r[2 * i]), sl2, -ms)) : 0.f;
+              const float p1 = (col + 1 >= cb && col + 1 < ce) ? ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), sl2, -ms)) : 0.f;
+              l4[i & 3] += p0 + p1;
+              pk[i] = pack2<F16>(p0, p1);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = 0u;
+        }
+        tmem_st_x16(sbuf + 16 * c, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full + b);
+      return (l4[0] + l4[1]) + (l4[2] + l4[3]);
+    };
+
+    auto epilogue_item = [&](int k, float l) {
+      const int item = first + k * step;
+      const int b = k & 1;
+      const int4 tl = __ldg(&a.tiles[item / a.heads]);
+      const int head = item % a.heads;
+      const bool valid = row < tl.y;
+      mbar_wait(o_full + b, (k >> 1) & 1);
+      tc_fence_after();
+      uint32_t o[HD];
+#pragma unroll
+      for (int c = 0; c < HD; c += 16) tmem_ld_x16(tmem + lane_addr + kOCol + b * HD + c, *reinterpret_cast<uint32_t(*)[16]>(o + c));
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty + b);
+      if (valid) {
+        const float inv = 1.f / l;
+        uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(a.out) + (int64_t)(tl.x + row) * a.hidden + head * HD);
+#pragma unroll
+        for (int j = 0; j < HD / 8; ++j)
+          dst[j] = make_uint4(pack2<F16>(__uint_as_float(o[8 * j]) * inv, __uint_as_float(o[8 * j + 1]) * inv),
+                              pack2<F16>(__uint_as_float(o[8 * j + 2]) * inv, __uint_as_float(o[8 * j + 3]) * inv),
+                              pack2<F16>(__uint_as_float(o[8 * j + 4]) * inv, __uint_as_float(o[8 * j + 5]) * inv),
+                              pack2<F16>(__uint_as_float(o[8 * j + 6]) * inv, __uint_as_float(o[8 * j + 7]) * inv));
+      }
+    };
+
+    float l_cur = n_mine > 0 ? softmax_item(0) : 0.f;
+    for (int k = 0; k < n_mine; ++k) {
+      float l_next = 0.f;
+      if (k + 1 < n_mine) l_next = softmax_item(k + 1);     // the products of item k + 1 ran under the softmax of item k
+      epilogue_item(k, l_cur);
+      l_cur = l_next;
+    }
+  }
+  pdl_trigger();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, kTmemCols); }
+}
+
+}  // namespace
+
+// tiles_dev: (row0, n_rows, -, -) row blocks of whole windows (<= 128 rows); bounds_dev: int32 [S][2] per-row window bounds.
+int attention_win_tc(const void* qkv, void* out, int64_t S, int heads, int head_dim, const int32_t* tiles_dev, int n_tiles,
+                     const int32_t* bounds_dev, void* stream_, bool f16) {
+  if (head_dim != HD) return fail(ZV_EINVAL, "attention_win_tc: only head_dim=80 is built (got %d)", head_dim);
+  if (n_tiles <= 0) return ZV_OK;
+  const int hidden = heads * head_dim;
+  CUtensorMap t64, t16;
+  int rc = make_tmap_2d(&t64, qkv, S, 3 * hidden, 3 * hidden, 64, BR, 128, f16);
+  if (rc) return rc;
+  rc = make_tmap_2d(&t16, qkv, S, 3 * hidden, 3 * hidden, 16, BR, 32, f16);
+  if (rc) return rc;
+  static std::atomic<uint64_t> attr_set{0};
+  const int dev = current_device();
+  if (device_needs_setup(attr_set, dev)) {
+    cudaError_t e = cudaFuncSetAttribute(attn_win_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_win_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (e != cudaSuccess) return fail(ZV_ECUDA, "attention_win_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    mark_device(attr_set, dev);
+  }
+  WinArgs a{};
+  a.out = out; a.tiles = reinterpret_cast<const int4*>(tiles_dev); a.bounds = reinterpret_cast<const int2*>(bounds_dev);
+  a.n_tiles = n_tiles; a.heads = heads; a.hidden = hidden;
+  a.scale_log2 = (float)(1.4426950408889634 / std::sqrt((double)head_dim));
+  const int64_t n_items = (int64_t)n_tiles * heads;
+  const int grid = (int)std::min<int64_t>(n_items, num_sms());
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  cudaError_t le;
+  {
+    NvtxRange nvtx("zv:K3 window attention (tcgen05)");
+    KernelTimer timer(KC_ATTN_WINDOW, stream_);
+    le = f16 ? launch_pdl(attn_win_tc_kernel<true>, dim3((unsigned)grid), dim3(kThreads), kSmem, stream, 1, t64, t16, a)
+             : launch_pdl(attn_win_tc_kernel<false>, dim3((unsigned)grid), dim3(kThreads), kSmem, stream, 1, t64, t16, a);
+  }
+  if (le != cudaSuccess) return fail(ZV_ECUDA, "attention_win_tc: launch: %s", cudaGetErrorString(le));
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(ZV_ECUDA, "attention_win_tc: launch: %s", cudaGetErrorString(e));
+  return ZV_OK;
+}
+
+}  // namespace zv

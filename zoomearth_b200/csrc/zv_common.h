@@ -56,6 +56,8 @@ int32_t resample_ksize(int32_t in_size, int32_t out_size);
 void resample_coeffs(int32_t in_size, int32_t out_size, AxisCoeffs* out);
 void normalize_lut(const zv_cfg* cfg, float* lut768);
 void plan_device_image(const zv_plan* p, std::vector<uint8_t>* image);
+void build_window_blocks(const std::vector<int32_t>& cu, int32_t max_rows, std::vector<int32_t>* blocks);
+void fill_window_bounds(const std::vector<int32_t>& cu, int32_t* bounds);
 
 // ---- plan (host tables; device image produced by zv_plan_upload)
 struct PlanDeviceLayout {
@@ -63,6 +65,8 @@ struct PlanDeviceLayout {
   int64_t off_rope = 0;                    // float [max_pos][20][2]: (cos, sin) of pos * inv_freq[j]
   int64_t off_widx = 0;                    // int32 [T]: window position i <-> HF merge-group index
   int64_t off_win_tiles = 0, off_full_tiles = 0;  // int4 work items (q0, q_len, seg_begin, seg_end)
+  int64_t off_win_blocks = 0;              // int4 (row0, n_rows, 0, 0): row blocks of whole windows, <= 128 rows (window layers)
+  int64_t off_win_bounds = 0;              // int32 [S][2]: (first row, end row) of the window of every patch row
   int32_t max_pos = 0;
   int64_t bytes = 0;
 };
@@ -78,6 +82,7 @@ struct zv_plan {
   std::vector<int32_t> cu_window_raw, cu_window, cu_full;
   std::vector<int32_t> pos_ids;            // [S][2], HF order
   std::vector<int32_t> win_tiles, full_tiles;   // 4 ints per q tile
-  int32_t n_win_tiles = 0, n_full_tiles = 0;
+  std::vector<int32_t> win_blocks;              // 4 ints per row block of the tcgen05 window kernel
+  int32_t n_win_tiles = 0, n_full_tiles = 0, n_win_blocks = 0;
   zv::PlanDeviceLayout dev;
 };

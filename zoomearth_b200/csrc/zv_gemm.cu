@@ -445,6 +445,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc(const __grid_constant__ C
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                             // everything above overlapped the previous kernel's tail; its outputs are complete now
 
   if (warp == 0) {
     if (elect_one()) {
@@ -467,6 +468,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc(const __grid_constant__ C
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
       }
+      pdl_trigger();                      // this CTA has requested its last operands: the next kernel may be scheduled
     }
   } else if (warp == 1) {
     if (leader && elect_one()) {
@@ -570,23 +572,13 @@ int launch(const GemmArgs& g, const void* a, int64_t lda, const void* b, int64_t
   const int tiles = ((g.M + BM * CG - 1) / (BM * CG)) * (g.N / BN);
   const int slots = num_sms() / CG;
   const int grid = (tiles < slots ? tiles : slots) * CG;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = C::kSmemBytes;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
   cudaError_t e;
   {
     static const char* const kNames[] = {"zv:K2 gemm store", "zv:K2 gemm qkv+rope", "zv:K2 gemm residual", "zv:K2 gemm swiglu",
                                          "zv:K2 gemm gelu", "zv:K2 gemm scatter"};
     NvtxRange nvtx(kNames[EPI]);
     KernelTimer timer(KC_GEMM_STORE + EPI, stream);
-    e = cudaLaunchKernelEx(&cfg, gemm_tc<BN, EPI, CG>, ta, tb, g);
+    e = launch_pdl(gemm_tc<BN, EPI, CG>, dim3((unsigned)grid), dim3(kThreads), C::kSmemBytes, stream, CG, ta, tb, g);
   }
   count_launch();
   if (e == cudaSuccess) e = cudaGetLastError();

@@ -3,7 +3,36 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include <utility>
+
 namespace zv {
+
+// Launch with the programmatic-dependent-launch attribute (see zv_ptx.cuh pdl_wait / pdl_trigger); `cluster` > 1 adds a
+// cluster dimension.  Kernels launched this way MUST call pdl_wait() before touching predecessor-written global memory.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+#ifndef ZV_NO_PDL
+  attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[n].val.programmaticStreamSerializationAllowed = 1;
+  ++n;
+#endif
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = (unsigned)cluster; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = (unsigned)n;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 enum GemmEpilogue { EPI_STORE = 0, EPI_QKV_ROPE = 1, EPI_RESID = 2, EPI_SWIGLU = 3, EPI_GELU = 4, EPI_SCATTER = 5 };
 
@@ -46,6 +75,11 @@ int make_tmap_2d(void* tm, const void* base, int64_t rows, int64_t cols, int64_t
 // (q0, q_len, seg_begin, seg_end) with q_len <= 128.
 int attention_tc(const void* qkv, void* out, int64_t S, int heads, int head_dim, const int32_t* tiles_dev, int n_tiles,
                  void* stream, bool f16);
+
+// tcgen05 window attention (zv_attn_win_tc.cu): row blocks (row0, n_rows, -, -) of whole windows (<= 128 rows) and the
+// per-row window bounds table int32 [S][2]
+int attention_win_tc(const void* qkv, void* out, int64_t S, int heads, int head_dim, const int32_t* blocks_dev, int n_blocks,
+                     const int32_t* bounds_dev, void* stream, bool f16);
 
 // fp32 (S, H) -> 16-bit copy (S, H) + per-row sum of squares in ss[row][0] (ss[row][1..kSsParts) = 0): the producer side
 // of the folded RMSNorm for rows that no residual GEMM has written yet (the patch-embed output)

@@ -97,6 +97,27 @@ void resample_coeffs(int32_t in_size, int32_t out_size, AxisCoeffs* c) {
   }
 }
 
+// Row blocks of the tcgen05 window-attention kernel: windows (segments of cu, each <= max_rows) in order, as many whole
+// consecutive ones per block as fit in max_rows rows.  4 ints per block: (row0, n_rows, 0, 0).
+void build_window_blocks(const std::vector<int32_t>& cu, int32_t max_rows, std::vector<int32_t>* blocks) {
+  blocks->clear();
+  int32_t row0 = cu.empty() ? 0 : cu[0], rows = 0;
+  for (size_t s = 0; s + 1 < cu.size(); ++s) {
+    const int32_t len = cu[s + 1] - cu[s];
+    if (rows > 0 && rows + len > max_rows) {
+      blocks->insert(blocks->end(), {row0, rows, 0, 0});
+      row0 = cu[s]; rows = 0;
+    }
+    rows += len;
+  }
+  if (rows > 0) blocks->insert(blocks->end(), {row0, rows, 0, 0});
+}
+// bounds[row] = (first row, end row) of the segment that holds `row`
+void fill_window_bounds(const std::vector<int32_t>& cu, int32_t* bounds) {
+  for (size_t s = 0; s + 1 < cu.size(); ++s)
+    for (int32_t r = cu[s]; r < cu[s + 1]; ++r) { bounds[2 * r] = cu[s]; bounds[2 * r + 1] = cu[s + 1]; }
+}
+
 void normalize_lut(const zv_cfg* cfg, float* lut) {
   for (int c = 0; c < 3; ++c)
     for (int v = 0; v < 256; ++v) {
@@ -355,6 +376,9 @@ int zv_plan_create(const zv_cfg* cfg, int32_t n, const int64_t* grid, zv_plan** 
   };
   tiles(p->cu_window, 64, &p->win_tiles);      // windows hold <= 64 patches: one 64-row q tile each
   tiles(p->cu_full, 128, &p->full_tiles);      // whole-image segments: 128-row q tiles (zv_attn.cu, 8 warps)
+  // window layers (tcgen05 kernel): consecutive whole windows packed greedily into row blocks of <= 128 rows
+  build_window_blocks(p->cu_window, 128, &p->win_blocks);
+  p->n_win_blocks = (int32_t)(p->win_blocks.size() / 4);
   p->n_win_tiles = (int32_t)(p->win_tiles.size() / 4);
   p->n_full_tiles = (int32_t)(p->full_tiles.size() / 4);
 
@@ -370,6 +394,8 @@ int zv_plan_create(const zv_cfg* cfg, int32_t n, const int64_t* grid, zv_plan** 
   d.off_widx = off; off = align_up(off + p->T * (int64_t)sizeof(int32_t), 256);
   d.off_win_tiles = off; off = align_up(off + (int64_t)p->win_tiles.size() * sizeof(int32_t), 256);
   d.off_full_tiles = off; off = align_up(off + (int64_t)p->full_tiles.size() * sizeof(int32_t), 256);
+  d.off_win_blocks = off; off = align_up(off + (int64_t)p->win_blocks.size() * sizeof(int32_t), 256);
+  d.off_win_bounds = off; off = align_up(off + (int64_t)S * 2 * sizeof(int32_t), 256);
   d.bytes = off;
   *out = p;
   return ZV_OK;
@@ -404,6 +430,8 @@ void zv::plan_device_image(const zv_plan* p, std::vector<uint8_t>* image) {
     }
   std::memcpy(base + d.off_win_tiles, p->win_tiles.data(), p->win_tiles.size() * sizeof(int32_t));
   std::memcpy(base + d.off_full_tiles, p->full_tiles.data(), p->full_tiles.size() * sizeof(int32_t));
+  std::memcpy(base + d.off_win_blocks, p->win_blocks.data(), p->win_blocks.size() * sizeof(int32_t));
+  fill_window_bounds(p->cu_window, reinterpret_cast<int32_t*>(base + d.off_win_bounds));
 }
 
 extern "C" {

@@ -36,6 +36,8 @@
 #include <vector>
 
 #include "zv_common.h"
+#include "zv_gemm.h"
+#include "zv_ptx.cuh"
 
 namespace {
 
@@ -120,6 +122,7 @@ template <typename OutT> __device__ __forceinline__ OutT to_out(float v) {
 __global__ void __launch_bounds__(256) k1_hpass(const K1Crop* __restrict__ crops, const int32_t* __restrict__ ids,
                                                 const int32_t* __restrict__ blk0, int n_cls,
                                                 const int32_t* __restrict__ coef, uint8_t* __restrict__ ws) {
+  zv::ptx::pdl_wait();
   const int slot = find_slot(blk0, n_cls, blockIdx.x);
   const K1Crop c = crops[ids[slot]];
   const int64_t item = (int64_t)(blockIdx.x - blk0[slot]) * blockDim.x + threadIdx.x;
@@ -157,6 +160,7 @@ __global__ void __launch_bounds__(256) k1_vpass(const K1Crop* __restrict__ crops
                                                 int wsz) {
   __shared__ __align__(16) OutT stage[4 * kPatchElems];
   __shared__ float s_lut[768];
+  zv::ptx::pdl_wait();
   const int slot = find_slot(blk0, n_cls, blockIdx.x);
   const K1Crop c = crops[ids[slot]];
   const int g = blockIdx.x - blk0[slot];        // merge group, raster order inside the crop
@@ -209,6 +213,7 @@ __global__ void __launch_bounds__(256, NW <= 2 ? 4 : 3) k1_hpass_fast(const K1Cr
   uint8_t* raw = reinterpret_cast<uint8_t*>(planes + kHRows * 3 * seg_words_max);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kStride = 1 + 3 * NW;
+  zv::ptx::pdl_wait();                // the source may be the previous kernel's output (zv_resize_u8 -> zv_preprocess)
 
   for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
     const int4 item = __ldg(items + it);
@@ -342,6 +347,7 @@ __global__ void __launch_bounds__(256, NW <= 2 ? 4 : 3) k1_hpass_fast(const K1Cr
     }
     __syncthreads();                // the next item's first copy may land in raw[0] / its planes pass follows a barrier
   }
+  zv::ptx::pdl_trigger();
 }
 
 // Vertical pass on dp4a + LUT + patchify.  Item = (crop, merge-group row, first pair, pairs): the 28 output rows' limb
@@ -359,6 +365,7 @@ __global__ void __launch_bounds__(256) k1_vpass_fast(const K1Crop* __restrict__ 
   OutT* stage = reinterpret_cast<OutT*>(vsm + (size_t)2 * tile_quads_max * 168 * 4);   // [2][4][1176]
   float* s_lut = reinterpret_cast<float*>(stage + 2 * 4 * kPatchElems);                // [768]
   int32_t* s_coef = reinterpret_cast<int32_t*>(s_lut + 768);                           // [28][kStride]
+  zv::ptx::pdl_wait();                // the intermediate is the horizontal pass's output
   for (int i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i] = lut[i];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // per-lane column decomposition, hoisted out of every loop: stage offset and LUT base of columns lane + 32 i
@@ -449,6 +456,7 @@ __global__ void __launch_bounds__(256) k1_vpass_fast(const K1Crop* __restrict__ 
       }
     }
   }
+  zv::ptx::pdl_trigger();
 }
 
 // ------------------------------------------------------------------------------------------------ uint8 output
@@ -463,6 +471,7 @@ __global__ void __launch_bounds__(256) k1_vpass_u8_fast(const K1Crop* __restrict
                                                         const uint8_t* __restrict__ ws) {
   constexpr int kStride = 1 + 3 * NW;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  zv::ptx::pdl_wait();
   for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
     const int4 item = __ldg(items + it);
     if (warp >= item.z) continue;
@@ -496,6 +505,7 @@ __global__ void __launch_bounds__(256) k1_vpass_u8_fast(const K1Crop* __restrict
 __global__ void __launch_bounds__(256) k1_vpass_u8(const K1Crop* __restrict__ crops, const int32_t* __restrict__ ids,
                                                    const int32_t* __restrict__ blk0, int n_cls,
                                                    const int32_t* __restrict__ coef, const uint8_t* __restrict__ ws) {
+  zv::ptx::pdl_wait();
   const int slot = find_slot(blk0, n_cls, blockIdx.x);
   const K1Crop c = crops[ids[slot]];
   const int64_t tpitch = (int64_t)c.ow * 3;
@@ -652,7 +662,8 @@ void launch_hfast(int n_items, cudaStream_t s, const K1Crop* d, const int4* item
   static std::atomic<uint64_t> attr{0};
   const int dev = zv::current_device();
   if (zv::device_needs_setup(attr, dev)) { cudaFuncSetAttribute(k1_hpass_fast<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); zv::mark_device(attr, dev); }
-  k1_hpass_fast<NW><<<persistent_grid(k1_hpass_fast<NW>, smem, n_items), 256, smem, s>>>(d, items, n_items, coef, ws, seg_words);
+  zv::launch_pdl(k1_hpass_fast<NW>, dim3((unsigned)persistent_grid(k1_hpass_fast<NW>, smem, n_items)), dim3(256), smem, s, 1,
+                 d, items, n_items, coef, ws, seg_words);
 }
 inline int vfast_smem(int nw, int tile_quads, int out_bytes) {
   return 2 * tile_quads * 168 * 4 + 2 * 4 * kPatchElems * out_bytes + 768 * 4 + 28 * (1 + 3 * nw) * 4;
@@ -664,8 +675,8 @@ void launch_vfast(int n_items, cudaStream_t s, const K1Crop* d, const int4* item
   static std::atomic<uint64_t> attr{0};
   const int dev = zv::current_device();
   if (zv::device_needs_setup(attr, dev)) { cudaFuncSetAttribute(k1_vpass_fast<NW, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); zv::mark_device(attr, dev); }
-  k1_vpass_fast<NW, OutT><<<persistent_grid(k1_vpass_fast<NW, OutT>, smem, n_items), 256, smem, s>>>(
-      d, items, n_items, coef, ws, lut, out, row_order, wsz, tile_quads);
+  zv::launch_pdl(k1_vpass_fast<NW, OutT>, dim3((unsigned)persistent_grid(k1_vpass_fast<NW, OutT>, smem, n_items)), dim3(256), smem, s, 1,
+                 d, items, n_items, coef, ws, lut, out, row_order, wsz, tile_quads);
 }
 template <typename OutT>
 void launch_vpass(int nw, int count, cudaStream_t s, const K1Crop* d, const int32_t* list, const int32_t* blk0, int ncls,
@@ -673,7 +684,7 @@ void launch_vpass(int nw, int count, cudaStream_t s, const K1Crop* d, const int3
   OutT* out = static_cast<OutT*>(out_);
   const int4* items = reinterpret_cast<const int4*>(list);
   switch (nw) {
-    case 0: k1_vpass<OutT><<<(unsigned)count, 256, 0, s>>>(d, list, blk0, ncls, coef, ws, lut, out, row_order, wsz); break;
+    case 0: zv::launch_pdl(k1_vpass<OutT>, dim3((unsigned)count), dim3(256), 0, s, 1, d, list, blk0, ncls, coef, ws, lut, out, row_order, wsz); break;
     case 2: launch_vfast<2, OutT>(count, s, d, items, coef, ws, lut, out, row_order, wsz, tile_quads); break;
     case 3: launch_vfast<3, OutT>(count, s, d, items, coef, ws, lut, out, row_order, wsz, tile_quads); break;
     case 4: launch_vfast<4, OutT>(count, s, d, items, coef, ws, lut, out, row_order, wsz, tile_quads); break;
@@ -828,7 +839,7 @@ int k1_run(const char* who, const zv_cfg* cfg, int32_t n, const uint8_t* const* 
       const int4* items = reinterpret_cast<const int4*>(list);
       const int ni = (int)l.count;
       switch (l.nw) {
-        case 0: k1_hpass<<<(unsigned)l.count, 256, 0, stream>>>(dcrops, list, dlists + l.blk_off, l.ncls, dcoef, ws); break;
+        case 0: zv::launch_pdl(k1_hpass, dim3((unsigned)l.count), dim3(256), 0, stream, 1, dcrops, list, dlists + l.blk_off, l.ncls, dcoef, ws); break;
         case 2: launch_hfast<2>(ni, stream, dcrops, items, dcoef, ws, l.seg_words); break;
         case 3: launch_hfast<3>(ni, stream, dcrops, items, dcoef, ws, l.seg_words); break;
         case 4: launch_hfast<4>(ni, stream, dcrops, items, dcoef, ws, l.seg_words); break;
@@ -850,14 +861,14 @@ int k1_run(const char* who, const zv_cfg* cfg, int32_t n, const uint8_t* const* 
         const int4* items = reinterpret_cast<const int4*>(list);
         const int grid = (int)std::min<int64_t>(cnt, (int64_t)zv::num_sms() * 8);
         switch (l.nw) {
-          case 0: k1_vpass_u8<<<(unsigned)cnt, 256, 0, stream>>>(dcrops, list, blk0, l.ncls, dcoef, ws); break;
-          case 2: k1_vpass_u8_fast<2><<<grid, 256, 0, stream>>>(dcrops, items, cnt, dcoef, ws); break;
-          case 3: k1_vpass_u8_fast<3><<<grid, 256, 0, stream>>>(dcrops, items, cnt, dcoef, ws); break;
-          case 4: k1_vpass_u8_fast<4><<<grid, 256, 0, stream>>>(dcrops, items, cnt, dcoef, ws); break;
-          case 5: k1_vpass_u8_fast<5><<<grid, 256, 0, stream>>>(dcrops, items, cnt, dcoef, ws); break;
-          case 7: k1_vpass_u8_fast<7><<<grid, 256, 0, stream>>>(dcrops, items, cnt, dcoef, ws); break;
-          case 10: k1_vpass_u8_fast<10><<<grid, 256, 0, stream>>>(dcrops, items, cnt, dcoef, ws); break;
-          default: k1_vpass_u8_fast<12><<<grid, 256, 0, stream>>>(dcrops, items, cnt, dcoef, ws); break;
+          case 0: zv::launch_pdl(k1_vpass_u8, dim3((unsigned)cnt), dim3(256), 0, stream, 1, dcrops, list, blk0, l.ncls, dcoef, (const uint8_t*)ws); break;
+          case 2: zv::launch_pdl(k1_vpass_u8_fast<2>, dim3((unsigned)grid), dim3(256), 0, stream, 1, dcrops, items, cnt, dcoef, (const uint8_t*)ws); break;
+          case 3: zv::launch_pdl(k1_vpass_u8_fast<3>, dim3((unsigned)grid), dim3(256), 0, stream, 1, dcrops, items, cnt, dcoef, (const uint8_t*)ws); break;
+          case 4: zv::launch_pdl(k1_vpass_u8_fast<4>, dim3((unsigned)grid), dim3(256), 0, stream, 1, dcrops, items, cnt, dcoef, (const uint8_t*)ws); break;
+          case 5: zv::launch_pdl(k1_vpass_u8_fast<5>, dim3((unsigned)grid), dim3(256), 0, stream, 1, dcrops, items, cnt, dcoef, (const uint8_t*)ws); break;
+          case 7: zv::launch_pdl(k1_vpass_u8_fast<7>, dim3((unsigned)grid), dim3(256), 0, stream, 1, dcrops, items, cnt, dcoef, (const uint8_t*)ws); break;
+          case 10: zv::launch_pdl(k1_vpass_u8_fast<10>, dim3((unsigned)grid), dim3(256), 0, stream, 1, dcrops, items, cnt, dcoef, (const uint8_t*)ws); break;
+          default: zv::launch_pdl(k1_vpass_u8_fast<12>, dim3((unsigned)grid), dim3(256), 0, stream, 1, dcrops, items, cnt, dcoef, (const uint8_t*)ws); break;
         }
       } else if (out_dtype == ZV_BF16) launch_vpass<__nv_bfloat16>(l.nw, cnt, stream, dcrops, list, blk0, l.ncls, dcoef, ws, dlut, out_dev, row_order, wsz, l.tile_quads);
       else if (out_dtype == ZV_F16) launch_vpass<__half>(l.nw, cnt, stream, dcrops, list, blk0, l.ncls, dcoef, ws, dlut, out_dev, row_order, wsz, l.tile_quads);

@@ -17,6 +17,20 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the path is launched with programmaticStreamSerializationAllowed (zv::launch_pdl): it may be scheduled
+// while its predecessor in the stream is still draining, so that launch latency and the prologue (barrier init, TMEM
+// allocation, descriptor prefetch) overlap the predecessor's tail.  pdl_wait() blocks until every prerequisite grid has
+// COMPLETED and its memory is visible: it must precede the first access to global memory a predecessor may have written
+// (or may still read).  pdl_trigger() lets the dependent grid be scheduled once every CTA has issued it or exited.
+#ifdef ZV_NO_PDL
+__device__ __forceinline__ void pdl_wait() {}
+__device__ __forceinline__ void pdl_trigger() {}
+#else
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -27,6 +27,7 @@
 
 #include "zv_common.h"
 #include "zv_gemm.h"
+#include "zv_ptx.cuh"
 
 namespace zv {
 namespace {
@@ -48,6 +49,7 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ 
                                                       uint16_t* __restrict__ y, bool f16, int64_t rows, int hidden, float eps) {
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
+  ptx::pdl_wait();
   const int lane = threadIdx.x & 31;
   const float4* xr = reinterpret_cast<const float4*>(x + row * hidden);
   const int nv = hidden / 4;
@@ -82,6 +84,7 @@ __global__ void __launch_bounds__(256) cast_rows_ss_kernel(const float* __restri
                                                            float* __restrict__ ss, int64_t rows, int hidden) {
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
+  ptx::pdl_wait();
   const int lane = threadIdx.x & 31;
   const float4* xr = reinterpret_cast<const float4*>(x + row * hidden);
   uint2* yr = reinterpret_cast<uint2*>(y + row * hidden);
@@ -102,6 +105,7 @@ template <typename SrcT>
 __global__ void __launch_bounds__(256) gather_kernel(const SrcT* __restrict__ src, uint16_t* __restrict__ dst, bool f16,
                                                      const int32_t* __restrict__ widx, int group_elems) {
   const int64_t gi = blockIdx.x;
+  ptx::pdl_wait();
   const SrcT* s = src + (int64_t)widx[gi] * group_elems;
   uint16_t* d = dst + gi * group_elems;
   for (int i = threadIdx.x * 4; i < group_elems; i += blockDim.x * 4) {
@@ -122,6 +126,7 @@ __global__ void __launch_bounds__(256) gather_kernel(const SrcT* __restrict__ sr
 __global__ void __launch_bounds__(256) compose_rows_kernel(const int64_t* __restrict__ dest, const int32_t* __restrict__ widx,
                                                            int32_t* __restrict__ comp, int64_t n, int64_t rows) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  ptx::pdl_wait();
   if (i < n) {
     const int64_t d = dest[widx[i]];
     comp[i] = (d >= 0 && d < rows) ? (int32_t)d : -1;
@@ -224,8 +229,8 @@ int rmsnorm(const float* x, const float* w, void* y, int y_f16, int64_t rows, in
   if (hidden % 4 || hidden > 1280) return fail(ZV_EINVAL, "rmsnorm: hidden=%d unsupported", hidden);
   {
     KernelTimer timer(KC_RMSNORM, stream);
-    rmsnorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, w, static_cast<uint16_t*>(y), y_f16 != 0, rows, hidden, eps);
+    launch_pdl(rmsnorm_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), 1,
+               x, w, static_cast<uint16_t*>(y), y_f16 != 0, rows, hidden, eps);
   }
   count_launch();
   return ZV_OK;
@@ -235,8 +240,8 @@ int cast_rows_ss(const float* x, void* x16, int x16_f16, float* ss, int64_t rows
   if (hidden % 4) return fail(ZV_EINVAL, "cast_rows_ss: hidden=%d unsupported", hidden);
   {
     KernelTimer timer(KC_RMSNORM, stream);
-    cast_rows_ss_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, static_cast<uint16_t*>(x16), x16_f16 != 0, ss, rows, hidden);
+    launch_pdl(cast_rows_ss_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), 1,
+               x, static_cast<uint16_t*>(x16), x16_f16 != 0, ss, rows, hidden);
   }
   count_launch();
   return ZV_OK;
@@ -249,9 +254,11 @@ int gather_rows(const void* src, int src_dtype, void* dst, int dst_f16, const in
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   KernelTimer timer(KC_GATHER, stream);
   if (src_dtype == ZV_F32)
-    gather_kernel<float><<<(unsigned)n_groups, 256, 0, s>>>(static_cast<const float*>(src), static_cast<uint16_t*>(dst), dst_f16 != 0, widx, ge);
+    launch_pdl(gather_kernel<float>, dim3((unsigned)n_groups), dim3(256), 0, s, 1, static_cast<const float*>(src),
+               static_cast<uint16_t*>(dst), dst_f16 != 0, widx, ge);
   else   // already the 16-bit operand type: plain row move
-    gather_kernel<uint16_t><<<(unsigned)n_groups, 256, 0, s>>>(static_cast<const uint16_t*>(src), static_cast<uint16_t*>(dst), dst_f16 != 0, widx, ge);
+    launch_pdl(gather_kernel<uint16_t>, dim3((unsigned)n_groups), dim3(256), 0, s, 1, static_cast<const uint16_t*>(src),
+               static_cast<uint16_t*>(dst), dst_f16 != 0, widx, ge);
   count_launch();
   return ZV_OK;
 }
@@ -455,6 +462,8 @@ int visual_forward_impl(const zv_cfg* cfg, const void* weights_dev, const zv_pla
   const int32_t* d_widx = reinterpret_cast<const int32_t*>(pd + p->dev.off_widx);
   const int32_t* d_win = reinterpret_cast<const int32_t*>(pd + p->dev.off_win_tiles);
   const int32_t* d_full = reinterpret_cast<const int32_t*>(pd + p->dev.off_full_tiles);
+  const int32_t* d_wblk = reinterpret_cast<const int32_t*>(pd + p->dev.off_win_blocks);
+  const int32_t* d_wbnd = reinterpret_cast<const int32_t*>(pd + p->dev.off_win_bounds);
   float* X = reinterpret_cast<float*>(ws + W.x);
   void* Y = ws + W.y;
   void* BIG = ws + W.big;
@@ -493,6 +502,8 @@ int visual_forward_impl(const zv_cfg* cfg, const void* weights_dev, const zv_pla
     ZV_TRY(gemm(EPI_QKV_ROPE, g, X16, H, wb + o.wqkv, H, stream));
     if (full && !legacy_full) {
       ZV_TRY(attention_tc(BIG, Y, S, cfg->heads, (int)(H / cfg->heads), d_full, p->n_full_tiles, stream, f16 != 0));
+    } else if (!full && !legacy_full) {
+      ZV_TRY(attention_win_tc(BIG, Y, S, cfg->heads, (int)(H / cfg->heads), d_wblk, p->n_win_blocks, d_wbnd, stream, f16 != 0));
     } else {
       ZV_TRY(attention(BIG, Y, cfg->heads, (int)(H / cfg->heads), full ? d_full : d_win, full ? p->n_full_tiles : p->n_win_tiles, stream, full, f16 != 0));
     }
@@ -533,7 +544,8 @@ int visual_forward_impl(const zv_cfg* cfg, const void* weights_dev, const zv_pla
   if (dest_rows_dev) {
     // LM hand-off (HF :1301-1307 masked_scatter): the un-reorder and the scatter into inputs_embeds are one index map
     int32_t* comp = reinterpret_cast<int32_t*>(ws + W.comp);
-    compose_rows_kernel<<<(unsigned)((T + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dest_rows_dev, d_widx, comp, T, dest_rows_limit);
+    launch_pdl(compose_rows_kernel, dim3((unsigned)((T + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 1,
+               dest_rows_dev, d_widx, comp, T, dest_rows_limit);
     count_launch();
     g.scatter = comp;
   }
@@ -557,6 +569,25 @@ int zv_attention(const void* qkv_dev, void* out_dev, int32_t heads, int32_t head
   int32_t longest = 0;
   for (int32_t s = 0; s < n_seg; ++s) longest = std::max(longest, cu_host[s + 1] - cu_host[s]);
   const bool full = longest > 64;                 // same choice the tower makes: 128-row q tiles for long segments
+#ifndef ZV_DEBUG_ATTN_LEGACY
+  if (!full) {
+    // window layers: row blocks + per-row bounds, uploaded into the work buffer, then the tcgen05 window kernel
+    std::vector<int32_t> cu(cu_host, cu_host + n_seg + 1), blocks;
+    build_window_blocks(cu, 128, &blocks);
+    const int64_t S_ = cu_host[n_seg];
+    const int64_t off_bounds = ((int64_t)blocks.size() * 4 + 255) / 256 * 256;
+    const int64_t need_w = off_bounds + S_ * 8;
+    if (work_bytes < need_w) return fail(ZV_ENOMEM, "zv_attention: work buffer %lld B < required %lld B", (long long)work_bytes, (long long)need_w);
+    std::vector<int32_t> bounds((size_t)S_ * 2);
+    fill_window_bounds(cu, bounds.data());
+    uint8_t* w = static_cast<uint8_t*>(work_dev);
+    cudaError_t e1 = cudaMemcpyAsync(w, blocks.data(), blocks.size() * 4, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream));
+    if (e1 == cudaSuccess) e1 = cudaMemcpyAsync(w + off_bounds, bounds.data(), bounds.size() * 4, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream));
+    if (e1 != cudaSuccess) return fail(ZV_ECUDA, "zv_attention: %s", cudaGetErrorString(e1));
+    return attention_win_tc(qkv_dev, out_dev, S_, heads, head_dim, reinterpret_cast<const int32_t*>(w), (int)(blocks.size() / 4),
+                            reinterpret_cast<const int32_t*>(w + off_bounds), stream, dtype == ZV_F16);
+  }
+#endif
   const int32_t bq = full ? 128 : 64;
   for (int32_t s = 0; s < n_seg; ++s)
     for (int32_t q0 = cu_host[s]; q0 < cu_host[s + 1]; q0 += bq) {
