@@ -461,7 +461,7 @@ def run_ours(args):
                             "traffic": (traffic.get("k1_bytes_per_image") * n_img) if traffic.get("k1_bytes_per_image") else None,
                             "traffic_note": traffic.get("k1_note", "no ncu capture of this tree under profiles/ncu_traffic.json"),
                             "algorithmic_bytes": k1_bytes},
-            "roofline_attn": {"bound": "tensor", "kernel": "attn_tc_kernel (tcgen05, full layers) + attn_window_kernel (mma.sync, window layers)", "achieved": attn_tf,
+            "roofline_attn": {"bound": "tensor", "kernel": "attn_tc_kernel (tcgen05, full layers) + attn_win_tc_kernel (tcgen05, window layers)", "achieved": attn_tf,
                               "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": attn_tf / pk["tf_sust"],
                               "ms_total": attn_ms, "share_of_step": attn_ms / ms,
                               "full_layers_tflops": (f_full * args.steps / (cls["attn_full"][0] / 1e3) / 1e12) if cls["attn_full"][0] else 0.0,

@@ -16,6 +16,10 @@
 //              and written over the consumed S columns (S and P share a TMEM buffer), zeros outside the window
 //   O = P V    warp 1: A = P from TMEM, B = V as it lies in qkv (MN-major), 8 K steps of one N=64 + one N=16 MMA
 //   epilogue   warps 2-5: O row * 1/l -> 16 bit -> global
+// Measured (B200): 0.73 ms per layer at the bench shape alone (4.4 TB/s = 0.68 of the copy peak), 1.02 ms inside the
+// power-capped bench step (the mma.sync kernel: 0.72 / 1.15-1.25 ms).  Not bound by the TMA row-request rate (dropping the
+// 32-byte-row boxes changes nothing), nor by bytes in flight (an L2 prefetch of the next blocks made it 1.8x slower), and a
+// cp.async producer variant writing the swizzled layouts by hand was slower (1.07 ms): see profiles/README.md.
 // S/P and O are double-buffered in TMEM (2 x 128 + 2 x 80 columns), so the products of item i+1 run under the softmax of
 // item i and the epilogue of item i runs after the softmax of item i+1.  Persistent: one CTA per SM walks the items.
 #include <cuda.h>
@@ -37,12 +41,16 @@ namespace {
 constexpr int HD = 80, BR = 128, STAGES = 3, kThreads = 192;
 constexpr int kB64 = BR * 64 * 2, kB16 = BR * 16 * 2;                      // 16384, 4096
 constexpr int kTile = kB64 + kB16;                                        // 20480: one of Q, K, V
-constexpr int kStage = 3 * kTile;                                         // 61440
+constexpr int kMetaRows = BR + 2;                                         // per-row window bounds of a block (+ alignment slack)
+constexpr int kMetaBytes = 2048;                                          // [tile record 16 B | pad | bounds at +32: kMetaRows x 8 B]
+constexpr int kBoundsBytes = kMetaRows * 8;                               // 1040: a multiple of 16 (bulk-copy granularity)
+constexpr int kStage = 3 * kTile + kMetaBytes;                            // 63488
 constexpr int kOffBar = STAGES * kStage;
 constexpr int kSmem = kOffBar + 256 + 1024;
 constexpr int kTmemCols = 512, kOCol = 256;                               // S/P buffer b at [128 b, 128 b + 128), O buffer b at [256 + 80 b, ..)
 constexpr uint32_t kSw128 = 2, kSw32 = 6;                                 // UMMA descriptor layout types
 static_assert(kTile % 1024 == 0 && kB64 % 1024 == 0 && kStage % 1024 == 0, "swizzle atom alignment");
+static_assert(kBoundsBytes % 16 == 0 && 32 + kBoundsBytes <= kMetaBytes, "meta block");
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = 0;
@@ -74,10 +82,16 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// 1-D bulk copy global -> shared, completing on an mbarrier (src, dst 16-byte aligned; bytes a multiple of 16)
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 struct WinArgs {
   void* out;
   const int4* tiles;          // (row0, n_rows, -, -): row blocks of whole windows
-  const int2* bounds;         // [S]: (first row, end row) of the window each patch row belongs to
+  const int2* bounds;         // [S + kMetaRows]: (first row, end row) of the window each patch row belongs to (zero padded)
   int n_tiles, heads, hidden;
   float scale_log2;
 };
@@ -121,16 +135,28 @@ __global__ void __launch_bounds__(kThreads, 1) attn_win_tc_kernel(const __grid_c
         const int item = first + k * step;
         const int st = k % STAGES;
         const uint32_t ph = (k / STAGES) & 1;
-        const int row0 = __ldg(&a.tiles[item / a.heads]).x;
+        const int4 tl = __ldg(&a.tiles[item / a.heads]);
+        const int row0 = tl.x;
         const int head = item % a.heads;
         uint8_t* s = smem + st * kStage;
         mbar_wait(load_empty + st, ph ^ 1);
-        mbar_arrive_expect_tx(load_full + st, kStage);
+        // the block's record and per-row window bounds travel with the stage: a dependent L2 round trip per item in the
+        // softmax warps would otherwise sit on the critical path (two of them: record, then bounds)
+        uint8_t* meta = s + 3 * kTile;
+        *reinterpret_cast<int4*>(meta) = tl;                                  // released by the arrive below
+#ifdef ZV_WIN_SKIP16                     // timing experiment only (wrong results): no 32-byte-row boxes
+        mbar_arrive_expect_tx(load_full + st, 3 * kB64 + kBoundsBytes);
+#else
+        mbar_arrive_expect_tx(load_full + st, 3 * kTile + kBoundsBytes);
+#endif
+        bulk_load_1d(meta + 32, a.bounds + (row0 & ~1), kBoundsBytes, load_full + st);
 #pragma unroll
         for (int t = 0; t < 3; ++t) {               // q, k, v column groups of qkv
           const int col = t * a.hidden + head * HD;
           tma_load_2d(s + t * kTile, &tm64, load_full + st, col, row0);
+#ifndef ZV_WIN_SKIP16
           tma_load_2d(s + t * kTile + kB64, &tm16, load_full + st, col + 64, row0);
+#endif
         }
       }
     }
@@ -181,16 +207,17 @@ __global__ void __launch_bounds__(kThreads, 1) attn_win_tc_kernel(const __grid_c
     const float sl2 = a.scale_log2;
 
     // softmax of item k; returns the row sum (0 for rows outside the block)
-    auto softmax_item = [&](int k) -> float {
-      const int item = first + k * step;
+    auto softmax_item = [&](int k, int& row0_out, int& n_rows_out) -> float {
       const int b = k & 1;
-      const int4 tl = __ldg(&a.tiles[item / a.heads]);
+      const uint32_t sbuf = tmem + lane_addr + b * BR;
+      mbar_wait(s_full + b, (k >> 1) & 1);                       // S is complete, so the stage (and its meta block) has landed
+      tc_fence_after();
+      const uint8_t* meta = smem + (k % STAGES) * kStage + 3 * kTile;
+      const int4 tl = *reinterpret_cast<const int4*>(meta);
+      row0_out = tl.x; n_rows_out = tl.y;
       const bool valid = row < tl.y;
       int cb = 0, ce = 0;
-      if (valid) { const int2 w = __ldg(&a.bounds[tl.x + row]); cb = w.x - tl.x; ce = w.y - tl.x; }
-      const uint32_t sbuf = tmem + lane_addr + b * BR;
-      mbar_wait(s_full + b, (k >> 1) & 1);
-      tc_fence_after();
+      if (valid) { const int2 w = reinterpret_cast<const int2*>(meta + 32)[(tl.x & 1) + row]; cb = w.x - tl.x; ce = w.y - tl.x; }
       // pass 1: row maximum over the row's window
       float m = -INFINITY;
 #pragma unroll
@@ -258,12 +285,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn_win_tc_kernel(const __grid_c
       return (l4[0] + l4[1]) + (l4[2] + l4[3]);
     };
 
-    auto epilogue_item = [&](int k, float l) {
+    auto epilogue_item = [&](int k, float l, int row0, int n_rows) {
       const int item = first + k * step;
       const int b = k & 1;
-      const int4 tl = __ldg(&a.tiles[item / a.heads]);
       const int head = item % a.heads;
-      const bool valid = row < tl.y;
+      const bool valid = row < n_rows;
       mbar_wait(o_full + b, (k >> 1) & 1);
       tc_fence_after();
       uint32_t o[HD];
@@ -275,7 +301,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_win_tc_kernel(const __grid_c
       if (lane == 0) mbar_arrive(o_empty + b);
       if (valid) {
         const float inv = 1.f / l;
-        uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(a.out) + (int64_t)(tl.x + row) * a.hidden + head * HD);
+        uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(a.out) + (int64_t)(row0 + row) * a.hidden + head * HD);
 #pragma unroll
         for (int j = 0; j < HD / 8; ++j)
           dst[j] = make_uint4(pack2<F16>(__uint_as_float(o[8 * j]) * inv, __uint_as_float(o[8 * j + 1]) * inv),
@@ -285,12 +311,13 @@ __global__ void __launch_bounds__(kThreads, 1) attn_win_tc_kernel(const __grid_c
       }
     };
 
-    float l_cur = n_mine > 0 ? softmax_item(0) : 0.f;
+    int r0_cur = 0, nr_cur = 0, r0_next = 0, nr_next = 0;
+    float l_cur = n_mine > 0 ? softmax_item(0, r0_cur, nr_cur) : 0.f;
     for (int k = 0; k < n_mine; ++k) {
       float l_next = 0.f;
-      if (k + 1 < n_mine) l_next = softmax_item(k + 1);     // the products of item k + 1 ran under the softmax of item k
-      epilogue_item(k, l_cur);
-      l_cur = l_next;
+      if (k + 1 < n_mine) l_next = softmax_item(k + 1, r0_next, nr_next);     // the products of item k + 1 ran under the softmax of item k
+      epilogue_item(k, l_cur, r0_cur, nr_cur);
+      l_cur = l_next; r0_cur = r0_next; nr_cur = nr_next;
     }
   }
   pdl_trigger();

@@ -395,7 +395,7 @@ int zv_plan_create(const zv_cfg* cfg, int32_t n, const int64_t* grid, zv_plan** 
   d.off_win_tiles = off; off = align_up(off + (int64_t)p->win_tiles.size() * sizeof(int32_t), 256);
   d.off_full_tiles = off; off = align_up(off + (int64_t)p->full_tiles.size() * sizeof(int32_t), 256);
   d.off_win_blocks = off; off = align_up(off + (int64_t)p->win_blocks.size() * sizeof(int32_t), 256);
-  d.off_win_bounds = off; off = align_up(off + (int64_t)S * 2 * sizeof(int32_t), 256);
+  d.off_win_bounds = off; off = align_up(off + (int64_t)(S + 136) * 2 * sizeof(int32_t), 256);   // + a block of zero padding: the kernel bulk-copies 130 rows from any block start
   d.bytes = off;
   *out = p;
   return ZV_OK;

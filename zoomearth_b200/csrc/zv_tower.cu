@@ -576,9 +576,9 @@ int zv_attention(const void* qkv_dev, void* out_dev, int32_t heads, int32_t head
     build_window_blocks(cu, 128, &blocks);
     const int64_t S_ = cu_host[n_seg];
     const int64_t off_bounds = ((int64_t)blocks.size() * 4 + 255) / 256 * 256;
-    const int64_t need_w = off_bounds + S_ * 8;
+    const int64_t need_w = off_bounds + (S_ + 136) * 8;       // zero padding behind the table (130-row bulk copies)
     if (work_bytes < need_w) return fail(ZV_ENOMEM, "zv_attention: work buffer %lld B < required %lld B", (long long)work_bytes, (long long)need_w);
-    std::vector<int32_t> bounds((size_t)S_ * 2);
+    std::vector<int32_t> bounds((size_t)(S_ + 136) * 2, 0);
     fill_window_bounds(cu, bounds.data());
     uint8_t* w = static_cast<uint8_t*>(work_dev);
     cudaError_t e1 = cudaMemcpyAsync(w, blocks.data(), blocks.size() * 4, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream));
