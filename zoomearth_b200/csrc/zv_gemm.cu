@@ -445,28 +445,50 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc(const __grid_constant__ C
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();                             // everything above overlapped the previous kernel's tail; its outputs are complete now
+  // Programmatic dependent launch: everything above overlapped the previous kernel's tail.  The producer goes one step
+  // further: B is the weight matrix, which no predecessor writes, so the weight tiles of the first ring pass are
+  // requested BEFORE the dependency wait (small batches leave SMs idle in the predecessor: the cold weight fetch from
+  // HBM then runs under its tail); A (activations) and every other role wait first.
+  if (warp != 0) pdl_wait();
 
   if (warp == 0) {
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
+      bool first_pass = first_tile < num_tiles;
+      if (first_pass) {
+        const int n_row = (first_tile % n_blocks) * BN + (int)rank * C::kBRows;
+        const int pre = k_blocks < C::kStages ? k_blocks : C::kStages;
+        for (int kb = 0; kb < pre; ++kb) {                    // the ring is empty: no wait on `empty`
+          uint8_t* sa = smem + kb * C::kStageBytes;
+          if constexpr (CG == 2) {
+            if (leader) mbar_arrive_expect_tx(full + kb, 2 * C::kStageBytes);
+            tma_load_2d_pair(sa + C::kABytes, &tma_b, full + kb, kb * BK, n_row);
+          } else {
+            mbar_arrive_expect_tx(full + kb, C::kStageBytes);
+            tma_load_2d(sa + C::kABytes, &tma_b, full + kb, kb * BK, n_row);
+          }
+        }
+      }
+      pdl_wait();                          // the predecessor's outputs (A, and what the epilogue reads) are complete now
       for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         const int m_row = (tile / n_blocks) * BM * CG + (int)rank * BM;
         const int n_row = (tile % n_blocks) * BN + (int)rank * C::kBRows;
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(empty + stage, phase ^ 1);
           uint8_t* sa = smem + stage * C::kStageBytes;
+          const bool b_requested = first_pass && kb < C::kStages;           // first tile, first ring pass: B is already on its way
+          if (!b_requested) mbar_wait(empty + stage, phase ^ 1);
           if constexpr (CG == 2) {
-            if (leader) mbar_arrive_expect_tx(full + stage, 2 * C::kStageBytes);     // both CTAs' bytes land on the leader
+            if (!b_requested && leader) mbar_arrive_expect_tx(full + stage, 2 * C::kStageBytes);     // both CTAs' bytes land on the leader
             tma_load_2d_pair(sa, &tma_a, full + stage, kb * BK, m_row);
-            tma_load_2d_pair(sa + C::kABytes, &tma_b, full + stage, kb * BK, n_row);
+            if (!b_requested) tma_load_2d_pair(sa + C::kABytes, &tma_b, full + stage, kb * BK, n_row);
           } else {
-            mbar_arrive_expect_tx(full + stage, C::kStageBytes);
+            if (!b_requested) mbar_arrive_expect_tx(full + stage, C::kStageBytes);
             tma_load_2d(sa, &tma_a, full + stage, kb * BK, m_row);
-            tma_load_2d(sa + C::kABytes, &tma_b, full + stage, kb * BK, n_row);
+            if (!b_requested) tma_load_2d(sa + C::kABytes, &tma_b, full + stage, kb * BK, n_row);
           }
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
+        first_pass = false;
       }
       pdl_trigger();                      // this CTA has requested its last operands: the next kernel may be scheduled
     }
