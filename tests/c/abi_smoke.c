@@ -50,6 +50,20 @@ int main(void) {
   double inv;
   CHECK(zv_resize_dims(1300, 900, 512, wh, &inv) == ZV_OK && wh[0] == 512 && wh[1] == 354, "resize_dims %d %d", wh[0], wh[1]);
 
+  /* resize_image variants (demo.py:86-93, SFT.py:76-81 always resizes, customized_funcs.py:76-85) and SFT.py's cut_image
+   * (crop -> resize to min side 512 -> centre crop); known answers from tests/golden/flows.json (the reference's own code) */
+  CHECK(zv_resize_dims_ex(5000, 5000, 1024, 1, wh, &inv) == ZV_OK && wh[0] == 1024 && wh[1] == 1024, "resize_dims_ex sft %d %d", wh[0], wh[1]);
+  CHECK(zv_resize_dims_ex(300, 200, 1024, 1, wh, NULL) == ZV_OK && wh[0] == 1024 && wh[1] == 682, "sft upscales: %d %d", wh[0], wh[1]);
+  CHECK(zv_resize_dims_ex(300, 200, 1024, 0, wh, NULL) == ZV_OK && wh[0] == 300 && wh[1] == 200, "infer keeps small images");
+  CHECK(zv_resize_dims_ex(4000, 40, 512, 2, wh, NULL) == ZV_OK && wh[0] == 3000 && wh[1] == 30, "custom min_scale: %d %d", wh[0], wh[1]);
+  {
+    const double bb[4] = {1000, 1200, 2300, 2100};
+    int32_t box[4], rs[2], cb[4];
+    CHECK(zv_cut_box_sft(5000, 5000, bb, 512, box, rs, cb) == ZV_OK, "zv_cut_box_sft rc");
+    CHECK(box[0] == 1000 && box[3] == 2100 && rs[0] == 739 && rs[1] == 512 && cb[0] == 113 && cb[1] == 0 && cb[2] == 625 && cb[3] == 512,
+          "cut_box_sft: resize %d x %d, centre box %d %d %d %d", rs[0], rs[1], cb[0], cb[1], cb[2], cb[3]);
+  }
+
   /* plan: window index of grid (1, 26, 36) */
   const int64_t grid[3] = {1, 26, 36};
   zv_plan* plan = NULL;

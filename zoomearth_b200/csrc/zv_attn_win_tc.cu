@@ -45,7 +45,9 @@ constexpr int kMetaRows = BR + 2;                                         // per
 constexpr int kMetaBytes = 2048;                                          // [tile record 16 B | pad | bounds at +32: kMetaRows x 8 B]
 constexpr int kBoundsBytes = kMetaRows * 8;                               // 1040: a multiple of 16 (bulk-copy granularity)
 constexpr int kStage = 3 * kTile + kMetaBytes;                            // 63488
-constexpr int kOffBar = STAGES * kStage;
+constexpr int kOffOut = STAGES * kStage;                                  // [4 warps][32 rows][80] 16-bit: output staging for the TMA store
+constexpr int kOutBytes = 4 * 32 * HD * 2;                                // 20480
+constexpr int kOffBar = kOffOut + kOutBytes;
 constexpr int kSmem = kOffBar + 256 + 1024;
 constexpr int kTmemCols = 512, kOCol = 256;                               // S/P buffer b at [128 b, 128 b + 128), O buffer b at [256 + 80 b, ..)
 constexpr uint32_t kSw128 = 2, kSw32 = 6;                                 // UMMA descriptor layout types
@@ -88,6 +90,29 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
                ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// TMA store of a [box rows][box cols] tile from shared memory (dense, no swizzle) to a 2-D tensor; bulk async-group completion
+__device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(tmap), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+#ifdef ZV_WIN_TRACE      // debug build only: per-item clock stamps of CTA 0 (tools/win_trace.py)
+__device__ long long g_win_trace[16 * 64];
+#define ZV_TRACE(slot, k) do { if (blockIdx.x == 0 && (k) < 64) g_win_trace[(slot) * 64 + (k)] = clock64(); } while (0)
+#else
+#define ZV_TRACE(slot, k) do { } while (0)
+#endif
+
 struct WinArgs {
   void* out;
   const int4* tiles;          // (row0, n_rows, -, -): row blocks of whole windows
@@ -98,7 +123,8 @@ struct WinArgs {
 
 template <bool F16>
 __global__ void __launch_bounds__(kThreads, 1) attn_win_tc_kernel(const __grid_constant__ CUtensorMap tm64,
-                                                                  const __grid_constant__ CUtensorMap tm16, const WinArgs a) {
+                                                                  const __grid_constant__ CUtensorMap tm16,
+                                                                  const __grid_constant__ CUtensorMap tm_out, const WinArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
@@ -112,7 +138,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_win_tc_kernel(const __grid_c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    prefetch_tensormap(&tm64); prefetch_tensormap(&tm16);
+    prefetch_tensormap(&tm64); prefetch_tensormap(&tm16); prefetch_tensormap(&tm_out);
     for (int s = 0; s < STAGES; ++s) { mbar_init(load_full + s, 1); mbar_init(load_empty + s, 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(s_full + b, 1); mbar_init(p_full + b, 4); mbar_init(o_full + b, 1); mbar_init(o_empty + b, 4); }
     fence_mbar_init();
@@ -153,6 +179,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_win_tc_kernel(const __grid_c
 #pragma unroll
         for (int t = 0; t < 3; ++t) {               // q, k, v column groups of qkv
           const int col = t * a.hidden + head * HD;
+          if (t == 0) ZV_TRACE(0, k);                       // stage free, loads go out
           tma_load_2d(s + t * kTile, &tm64, load_full + st, col, row0);
 #ifndef ZV_WIN_SKIP16
           tma_load_2d(s + t * kTile + kB64, &tm16, load_full + st, col + 64, row0);
@@ -170,7 +197,9 @@ __global__ void __launch_bounds__(kThreads, 1) attn_win_tc_kernel(const __grid_c
         const int st = k % STAGES, b = k & 1;
         // S/P buffer b was last read by P V of item k - 2 (its A operand): that product must have retired
         if (k >= 2) mbar_wait(o_full + b, ((k - 2) >> 1) & 1);
+        ZV_TRACE(1, k);                                        // issuer reaches Q K^T of item k
         mbar_wait(load_full + st, (k / STAGES) & 1);
+        ZV_TRACE(2, k);                                        // ... its tiles have landed
         tc_fence_after();
         const uint32_t sq = smem_u32(smem + st * kStage), sk = sq + kTile;
         const uint32_t d = tmem + b * BR;
@@ -185,8 +214,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn_win_tc_kernel(const __grid_c
         if (k + 1 < n_mine) issue_qk(k + 1);
         const int st = k % STAGES, b = k & 1;
         const uint32_t sv = smem_u32(smem + st * kStage + 2 * kTile);
+        ZV_TRACE(3, k);                                        // issuer waits for P of item k
         mbar_wait(p_full + b, (k >> 1) & 1);
+        ZV_TRACE(4, k);
         mbar_wait(o_empty + b, ((k >> 1) & 1) ^ 1);          // the epilogue of item k - 2 has the old O in registers
+        ZV_TRACE(5, k);
         tc_fence_after();
         const uint32_t o = tmem + kOCol + b * HD, pa = tmem + b * BR;
 #pragma unroll
@@ -206,119 +238,201 @@ __global__ void __launch_bounds__(kThreads, 1) attn_win_tc_kernel(const __grid_c
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const float sl2 = a.scale_log2;
 
-    // softmax of item k; returns the row sum (0 for rows outside the block)
-    auto softmax_item = [&](int k, int& row0_out, int& n_rows_out) -> float {
-      const int b = k & 1;
-      const uint32_t sbuf = tmem + lane_addr + b * BR;
-      mbar_wait(s_full + b, (k >> 1) & 1);                       // S is complete, so the stage (and its meta block) has landed
-      tc_fence_after();
-      const uint8_t* meta = smem + (k % STAGES) * kStage + 3 * kTile;
-      const int4 tl = *reinterpret_cast<const int4*>(meta);
-      row0_out = tl.x; n_rows_out = tl.y;
-      const bool valid = row < tl.y;
-      int cb = 0, ce = 0;
-      if (valid) { const int2 w = reinterpret_cast<const int2*>(meta + 32)[(tl.x & 1) + row]; cb = w.x - tl.x; ce = w.y - tl.x; }
-      // pass 1: row maximum over the row's window
-      float m = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const bool need = cb < 32 * (c + 1) && ce > 32 * c;
-        if (!__any_sync(0xffffffffu, need)) continue;
-        uint32_t r[32];
-        tmem_ld_x32(sbuf + 32 * c, r);
-        tmem_ld_wait();
-        const bool full = __all_sync(0xffffffffu, cb <= 32 * c && ce >= 32 * (c + 1));
-        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        if (full) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(r[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int col = 32 * c + i;
-            m4[i & 3] = fmaxf(m4[i & 3], (col >= cb && col < ce) ? __uint_as_float(r[i]) : -INFINITY);
-          }
+    // One loop step = softmax of item kn (if any) + epilogue of item kc (if any).  A tcgen05.ld round trip costs ~400 clk
+    // here (measured with clock stamps: the two-pass softmax spent 2 000 clk per item, four of them in a row, and the
+    // epilogue 1 600), so every TMEM read of the step - the S chunks of item kn AND the O row of item kc - is issued up front
+    // and waited for once; S stays in registers for the max and the exp pass.
+    float l_cur = 0.f, l_next = 0.f;
+    int r0_cur = 0, nr_cur = 0, r0_next = 0, nr_next = 0;
+    auto step_items = [&](const int kn, const int kc) {
+      uint32_t sr0[32], sr1[32], o[HD];
+      int cb = 0, ce = 0, c_lo = 0;
+      bool valid_n = false, two_chunk = true;
+      uint32_t sbuf = 0;
+      if (kn >= 0) {
+        const int b = kn & 1;
+        sbuf = tmem + lane_addr + b * BR;
+        if (warp == 2 && lane == 0) ZV_TRACE(6, kn);
+        mbar_wait(s_full + b, (kn >> 1) & 1);                    // S is complete, so the stage (and its meta block) has landed
+        if (warp == 2 && lane == 0) ZV_TRACE(7, kn);
+        tc_fence_after();
+        const uint8_t* meta = smem + (kn % STAGES) * kStage + 3 * kTile;
+        const int4 tl = *reinterpret_cast<const int4*>(meta);
+        r0_next = tl.x; nr_next = tl.y;
+        valid_n = row < tl.y;
+        if (valid_n) { const int2 w = reinterpret_cast<const int2*>(meta + 32)[(tl.x & 1) + row]; cb = w.x - tl.x; ce = w.y - tl.x; }
+        // 32-column chunks of S this warp needs: [c_lo, c_hi]; at most two for windows aligned to 32 rows (the usual case)
+        const int my_lo = valid_n ? cb >> 5 : 3, my_hi = valid_n ? (ce - 1) >> 5 : 0;
+        c_lo = __reduce_min_sync(0xffffffffu, my_lo);
+        const int c_hi = __reduce_max_sync(0xffffffffu, my_hi);
+        two_chunk = c_hi <= c_lo + 1;
+        if (two_chunk && c_lo <= c_hi) {
+          tmem_ld_x32(sbuf + 32 * c_lo, sr0);
+          if (c_lo < 3) tmem_ld_x32(sbuf + 32 * (c_lo + 1), sr1);
         }
-        m = fmaxf(m, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
       }
-      const float ms = valid ? m * sl2 : 0.f;
-      // pass 2: exponentials, row sum, P over the consumed S columns (P chunk c lives in columns [16 c, 16 c + 16), which
-      // only overlap S chunks <= c / 2: already consumed when it is written)
-      float l4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (kc >= 0) {
+        const int b = kc & 1;
+        if (warp == 2 && lane == 0) ZV_TRACE(10, kc);
+        mbar_wait(o_full + b, (kc >> 1) & 1);
+        if (warp == 2 && lane == 0) ZV_TRACE(11, kc);
+        tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const bool need = cb < 32 * (c + 1) && ce > 32 * c;
-        uint32_t pk[16];
-        if (__any_sync(0xffffffffu, need)) {
-          uint32_t r[32];
-          tmem_ld_x32(sbuf + 32 * c, r);
-          tmem_ld_wait();
-          const bool full = __all_sync(0xffffffffu, cb <= 32 * c && ce >= 32 * (c + 1));
+        for (int c = 0; c < HD; c += 16) tmem_ld_x16(tmem + lane_addr + kOCol + b * HD + c, *reinterpret_cast<uint32_t(*)[16]>(o + c));
+      }
+      tmem_ld_wait();
+      if (kc >= 0) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(o_empty + (kc & 1));
+      }
+      if (warp == 2 && lane == 0 && kn >= 0) ZV_TRACE(8, kn);
+
+      // ---- softmax of item kn
+      if (kn >= 0) {
+        const int b = kn & 1;
+        float l4[4] = {0.f, 0.f, 0.f, 0.f};
+        if (two_chunk) {
+          const int col0 = 32 * c_lo;
+          const bool full = __all_sync(0xffffffffu, cb <= col0 && ce >= col0 + 64);
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+          if (full) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              m4[(i >> 1) & 3] = fmax3(m4[(i >> 1) & 3], __uint_as_float(sr0[i]), __uint_as_float(sr0[i + 1]));
+              m4[(i >> 1) & 3] = fmax3(m4[(i >> 1) & 3], __uint_as_float(sr1[i]), __uint_as_float(sr1[i + 1]));
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int c0 = col0 + i, c1 = col0 + 32 + i;
+              m4[i & 3] = fmaxf(m4[i & 3], (c0 >= cb && c0 < ce) ? __uint_as_float(sr0[i]) : -INFINITY);
+              m4[i & 3] = fmaxf(m4[i & 3], (c1 >= cb && c1 < ce) ? __uint_as_float(sr1[i]) : -INFINITY);
+            }
+          }
+          const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+          const float ms = valid_n ? m * sl2 : 0.f;
+          if (warp == 2 && lane == 0) ZV_TRACE(13, kn);           // row max done
+          uint32_t pk0[16], pk1[16];
           if (full) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * i]), sl2, -ms));
-              const float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), sl2, -ms));
-              l4[i & 3] += p0 + p1;
-              pk[i] = pack2<F16>(p0, p1);
+              const float p0 = ex2_approx(fmaf(__uint_as_float(sr0[2 * i]), sl2, -ms)), p1 = ex2_approx(fmaf(__uint_as_float(sr0[2 * i + 1]), sl2, -ms));
+              const float p2 = ex2_approx(fmaf(__uint_as_float(sr1[2 * i]), sl2, -ms)), p3 = ex2_approx(fmaf(__uint_as_float(sr1[2 * i + 1]), sl2, -ms));
+              l4[i & 3] += (p0 + p1) + (p2 + p3);
+              pk0[i] = pack2<F16>(p0, p1);
+              pk1[i] = pack2<F16>(p2, p3);
             }
           } else {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const int col = 32 * c + 2 * i;
-              const float p0 = (col >= cb && col < ce) ? ex2_approx(fmaf(__uint_as_float(r[2 * i]), sl2, -ms)) : 0.f;
-              const float p1 = (col + 1 >= cb && col + 1 < ce) ? ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), sl2, -ms)) : 0.f;
-              l4[i & 3] += p0 + p1;
-              pk[i] = pack2<F16>(p0, p1);
+              const int c0 = col0 + 2 * i, c1 = col0 + 32 + 2 * i;
+              const float p0 = (c0 >= cb && c0 < ce) ? ex2_approx(fmaf(__uint_as_float(sr0[2 * i]), sl2, -ms)) : 0.f;
+              const float p1 = (c0 + 1 >= cb && c0 + 1 < ce) ? ex2_approx(fmaf(__uint_as_float(sr0[2 * i + 1]), sl2, -ms)) : 0.f;
+              const float p2 = (c1 >= cb && c1 < ce) ? ex2_approx(fmaf(__uint_as_float(sr1[2 * i]), sl2, -ms)) : 0.f;
+              const float p3 = (c1 + 1 >= cb && c1 + 1 < ce) ? ex2_approx(fmaf(__uint_as_float(sr1[2 * i + 1]), sl2, -ms)) : 0.f;
+              l4[i & 3] += (p0 + p1) + (p2 + p3);
+              pk0[i] = pack2<F16>(p0, p1);
+              pk1[i] = pack2<F16>(p2, p3);
             }
           }
+          if (warp == 2 && lane == 0) ZV_TRACE(14, kn);           // exponentials done
+          // P over the S columns (all of this warp's S is in registers by now); zeros for the chunks of other windows
+          uint32_t zero[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) zero[i] = 0u;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (c == c_lo) tmem_st_x16(sbuf + 16 * c, pk0);
+            else if (c == c_lo + 1) tmem_st_x16(sbuf + 16 * c, pk1);
+            else tmem_st_x16(sbuf + 16 * c, zero);
+          }
         } else {
+          // general case (a warp's rows span three or four chunks: windows not aligned to 32 rows): two passes over TMEM
+          float m = -INFINITY;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) pk[i] = 0u;
+          for (int c = 0; c < 4; ++c) {
+            const bool need = cb < 32 * (c + 1) && ce > 32 * c;
+            if (!__any_sync(0xffffffffu, need)) continue;
+            uint32_t r[32];
+            tmem_ld_x32(sbuf + 32 * c, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int col = 32 * c + i;
+              m = fmaxf(m, (col >= cb && col < ce) ? __uint_as_float(r[i]) : -INFINITY);
+            }
+          }
+          const float ms = valid_n ? m * sl2 : 0.f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const bool need = cb < 32 * (c + 1) && ce > 32 * c;
+            uint32_t pk[16];
+            if (__any_sync(0xffffffffu, need)) {
+              uint32_t r[32];
+              tmem_ld_x32(sbuf + 32 * c, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int col = 32 * c + 2 * i;
+                const float p0 = (col >= cb && col < ce) ? ex2_approx(fmaf(__uint_as_float(r[2 * i]), sl2, -ms)) : 0.f;
+                const float p1 = (col + 1 >= cb && col + 1 < ce) ? ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), sl2, -ms)) : 0.f;
+                l4[i & 3] += p0 + p1;
+                pk[i] = pack2<F16>(p0, p1);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) pk[i] = 0u;
+            }
+            tmem_st_x16(sbuf + 16 * c, pk);       // P chunk c only overlaps S chunks <= c / 2: already consumed
+          }
         }
-        tmem_st_x16(sbuf + 16 * c, pk);
+        if (warp == 2 && lane == 0) ZV_TRACE(15, kn);             // P stores issued
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full + b);
+        if (warp == 2 && lane == 0) ZV_TRACE(9, kn);
+        l_next = (l4[0] + l4[1]) + (l4[2] + l4[3]);
       }
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full + b);
-      return (l4[0] + l4[1]) + (l4[2] + l4[3]);
-    };
 
-    auto epilogue_item = [&](int k, float l, int row0, int n_rows) {
-      const int item = first + k * step;
-      const int b = k & 1;
-      const int head = item % a.heads;
-      const bool valid = row < n_rows;
-      mbar_wait(o_full + b, (k >> 1) & 1);
-      tc_fence_after();
-      uint32_t o[HD];
-#pragma unroll
-      for (int c = 0; c < HD; c += 16) tmem_ld_x16(tmem + lane_addr + kOCol + b * HD + c, *reinterpret_cast<uint32_t(*)[16]>(o + c));
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(o_empty + b);
-      if (valid) {
-        const float inv = 1.f / l;
-        uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(a.out) + (int64_t)(row0 + row) * a.hidden + head * HD);
+      // ---- epilogue of item kc: O row * 1/l -> 16 bit -> global
+      if (kc >= 0) {
+        const int item = first + kc * step;
+        const int head = item % a.heads;
+        // A thread's row is 160 contiguous bytes, but 32 lanes x 16 bytes of 32 different rows per store instruction cost
+        // the LSU ~300 clk each under load (measured: 3 100 clk per item for the ten of them).  A warp whose 32 rows are all
+        // inside the block stages them in shared memory and hands them to the TMA unit as one [32][80] box; warps at the
+        // ragged end of a block keep the per-thread stores.
+        const bool row_ok = row < nr_cur;
+        const float inv = row_ok ? 1.f / l_cur : 0.f;
+        uint4 ov[HD / 8];
 #pragma unroll
         for (int j = 0; j < HD / 8; ++j)
-          dst[j] = make_uint4(pack2<F16>(__uint_as_float(o[8 * j]) * inv, __uint_as_float(o[8 * j + 1]) * inv),
-                              pack2<F16>(__uint_as_float(o[8 * j + 2]) * inv, __uint_as_float(o[8 * j + 3]) * inv),
-                              pack2<F16>(__uint_as_float(o[8 * j + 4]) * inv, __uint_as_float(o[8 * j + 5]) * inv),
-                              pack2<F16>(__uint_as_float(o[8 * j + 6]) * inv, __uint_as_float(o[8 * j + 7]) * inv));
+          ov[j] = make_uint4(pack2<F16>(__uint_as_float(o[8 * j]) * inv, __uint_as_float(o[8 * j + 1]) * inv),
+                             pack2<F16>(__uint_as_float(o[8 * j + 2]) * inv, __uint_as_float(o[8 * j + 3]) * inv),
+                             pack2<F16>(__uint_as_float(o[8 * j + 4]) * inv, __uint_as_float(o[8 * j + 5]) * inv),
+                             pack2<F16>(__uint_as_float(o[8 * j + 6]) * inv, __uint_as_float(o[8 * j + 7]) * inv));
+        if (__all_sync(0xffffffffu, row_ok)) {
+          uint4* stg = reinterpret_cast<uint4*>(smem + kOffOut + quarter * (32 * HD * 2) + lane * (HD * 2));
+          if (lane == 0) bulk_store_wait_read();               // the previous box has left this staging area
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < HD / 8; ++j) stg[j] = ov[j];
+          fence_proxy_async_smem();                            // generic-proxy writes -> visible to the TMA unit
+          __syncwarp();
+          if (lane == 0) tma_store_2d(&tm_out, smem + kOffOut + quarter * (32 * HD * 2), head * HD, r0_cur + quarter * 32);
+        } else if (row_ok) {
+          uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(a.out) + (int64_t)(r0_cur + row) * a.hidden + head * HD);
+#pragma unroll
+          for (int j = 0; j < HD / 8; ++j) dst[j] = ov[j];
+        }
+        if (warp == 2 && lane == 0) ZV_TRACE(12, kc);
       }
-    };
-
-    int r0_cur = 0, nr_cur = 0, r0_next = 0, nr_next = 0;
-    float l_cur = n_mine > 0 ? softmax_item(0, r0_cur, nr_cur) : 0.f;
-    for (int k = 0; k < n_mine; ++k) {
-      float l_next = 0.f;
-      if (k + 1 < n_mine) l_next = softmax_item(k + 1, r0_next, nr_next);     // the products of item k + 1 ran under the softmax of item k
-      epilogue_item(k, l_cur, r0_cur, nr_cur);
       l_cur = l_next; r0_cur = r0_next; nr_cur = nr_next;
-    }
+    };
+    for (int k = -1; k < n_mine; ++k) step_items(k + 1 < n_mine ? k + 1 : -1, k);      // the products of item k + 1 run under the softmax of item k
+    if (lane == 0) bulk_store_wait_all();           // this warp's TMA stores have been written before the CTA exits
   }
   pdl_trigger();
   tc_fence_before();
@@ -339,6 +453,9 @@ int attention_win_tc(const void* qkv, void* out, int64_t S, int heads, int head_
   if (rc) return rc;
   rc = make_tmap_2d(&t16, qkv, S, 3 * hidden, 3 * hidden, 16, BR, 32, f16);
   if (rc) return rc;
+  CUtensorMap tout;                                   // output (S, hidden): [32 rows][80] boxes, dense in shared memory
+  rc = make_tmap_2d(&tout, out, S, hidden, hidden, HD, 32, 0, f16);
+  if (rc) return rc;
   static std::atomic<uint64_t> attr_set{0};
   const int dev = current_device();
   if (device_needs_setup(attr_set, dev)) {
@@ -358,8 +475,8 @@ int attention_win_tc(const void* qkv, void* out, int64_t S, int heads, int head_
   {
     NvtxRange nvtx("zv:K3 window attention (tcgen05)");
     KernelTimer timer(KC_ATTN_WINDOW, stream_);
-    le = f16 ? launch_pdl(attn_win_tc_kernel<true>, dim3((unsigned)grid), dim3(kThreads), kSmem, stream, 1, t64, t16, a)
-             : launch_pdl(attn_win_tc_kernel<false>, dim3((unsigned)grid), dim3(kThreads), kSmem, stream, 1, t64, t16, a);
+    le = f16 ? launch_pdl(attn_win_tc_kernel<true>, dim3((unsigned)grid), dim3(kThreads), kSmem, stream, 1, t64, t16, tout, a)
+             : launch_pdl(attn_win_tc_kernel<false>, dim3((unsigned)grid), dim3(kThreads), kSmem, stream, 1, t64, t16, tout, a);
   }
   if (le != cudaSuccess) return fail(ZV_ECUDA, "attention_win_tc: launch: %s", cudaGetErrorString(le));
   count_launch();
@@ -369,3 +486,9 @@ int attention_win_tc(const void* qkv, void* out, int64_t S, int heads, int head_
 }
 
 }  // namespace zv
+
+#ifdef ZV_WIN_TRACE
+extern "C" __attribute__((visibility("default"))) int zv_debug_win_trace(long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, zv::g_win_trace, sizeof(long long) * 16 * 64);
+}
+#endif
