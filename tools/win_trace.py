@@ -22,7 +22,7 @@ buf = np.zeros(16 * 64, np.int64)
 h.zv_debug_win_trace(buf.ctypes.data_as(C.c_void_p))
 t = buf.reshape(16, 64)
 t0 = t[0, 0]
-names = ["load issue", "qk reach", "qk tiles landed", "pv reach", "pv P ready", "pv O free", "sm reach", "sm S ready", "sm pass1", "sm P out", "ep reach", "ep O ready", "ep stored", "sm max", "sm exps", "sm P issued"]
+names = ["load issue", "O loaded", "ep pre-wait", "ep post-wait", "ep fenced", "-", "sm reach", "sm S ready", "sm S loaded", "sm P out", "ep reach", "ep O ready", "ep stored", "sm max", "sm exps", "sm P issued"]
 print("item " + " ".join(f"{n:>15s}" for n in names))
 for k in range(3, 16):
     print(f"{k:4d} " + " ".join(f"{int(t[i, k] - t0):15d}" for i in range(16)))

@@ -11,11 +11,11 @@
 //              each (TMA out-of-bounds rows read as zero), 3-stage ring, one mbarrier per stage
 //   S = Q K^T  warp 1: tcgen05.mma M=128 N=128, A and B from shared memory, 4 + 1 K steps, fp32 S in TMEM.  S covers the
 //              whole block: entries that pair rows of different windows are masked by the softmax (block-diagonal)
-//   softmax    warps 2-5, thread = row: the row's window is columns [cb, ce) of the block (per-row bounds table of the
+//   softmax    warps 2-5 (even items) and 6-9 (odd items), thread = row: the row's window is columns [cb, ce) of the block (per-row bounds table of the
 //              plan); two passes over the 32-column chunks that intersect it (max, then exp2 / sum); P is rounded to 16 bit
 //              and written over the consumed S columns (S and P share a TMEM buffer), zeros outside the window
 //   O = P V    warp 1: A = P from TMEM, B = V as it lies in qkv (MN-major), 8 K steps of one N=64 + one N=16 MMA
-//   epilogue   warps 2-5: O row * 1/l -> 16 bit -> global
+//   epilogue   the same warps: O row * 1/l -> 16 bit -> shared-memory staging -> one TMA store per warp ([32 rows][80])
 // Measured (B200): 0.73 ms per layer at the bench shape alone (4.4 TB/s = 0.68 of the copy peak), 1.02 ms inside the
 // power-capped bench step (the mma.sync kernel: 0.72 / 1.15-1.25 ms).  Not bound by the TMA row-request rate (dropping the
 // 32-byte-row boxes changes nothing), nor by bytes in flight (an L2 prefetch of the next blocks made it 1.8x slower), and a
@@ -38,21 +38,23 @@ namespace zv {
 using namespace ptx;
 namespace {
 
-constexpr int HD = 80, BR = 128, STAGES = 3, kThreads = 192;
+constexpr int HD = 80, BR = 128, STAGES = 3, kThreads = 320;      // warps: 0 loads, 1 MMA issue, 2-5 and 6-9 softmax + epilogue (two sets)
 constexpr int kB64 = BR * 64 * 2, kB16 = BR * 16 * 2;                      // 16384, 4096
 constexpr int kTile = kB64 + kB16;                                        // 20480: one of Q, K, V
 constexpr int kMetaRows = BR + 2;                                         // per-row window bounds of a block (+ alignment slack)
-constexpr int kMetaBytes = 2048;                                          // [tile record 16 B | pad | bounds at +32: kMetaRows x 8 B]
+constexpr int kMetaBytes = 1152;                                          // [tile record 16 B | pad | bounds at +32: kMetaRows x 8 B]
 constexpr int kBoundsBytes = kMetaRows * 8;                               // 1040: a multiple of 16 (bulk-copy granularity)
-constexpr int kStage = 3 * kTile + kMetaBytes;                            // 63488
-constexpr int kOffOut = STAGES * kStage;                                  // [4 warps][32 rows][80] 16-bit: output staging for the TMA store
-constexpr int kOutBytes = 4 * 32 * HD * 2;                                // 20480
+constexpr int kStage = 3 * kTile;                                         // 61440
+constexpr int kOffMeta = STAGES * kStage;                                 // [STAGES][kMetaBytes]
+constexpr int kOffOut = kOffMeta + STAGES * kMetaBytes;                   // [8 warps][32 rows][80] 16-bit: output staging for the TMA stores
+constexpr int kOutBytes = 8 * 32 * HD * 2;                                // 40960
 constexpr int kOffBar = kOffOut + kOutBytes;
 constexpr int kSmem = kOffBar + 256 + 1024;
 constexpr int kTmemCols = 512, kOCol = 256;                               // S/P buffer b at [128 b, 128 b + 128), O buffer b at [256 + 80 b, ..)
 constexpr uint32_t kSw128 = 2, kSw32 = 6;                                 // UMMA descriptor layout types
 static_assert(kTile % 1024 == 0 && kB64 % 1024 == 0 && kStage % 1024 == 0, "swizzle atom alignment");
-static_assert(kBoundsBytes % 16 == 0 && 32 + kBoundsBytes <= kMetaBytes, "meta block");
+static_assert(kBoundsBytes % 16 == 0 && 32 + kBoundsBytes <= kMetaBytes && kMetaBytes % 128 == 0, "meta block");
+static_assert(kSmem <= 227 * 1024, "shared memory budget");
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = 0;
@@ -168,7 +170,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_win_tc_kernel(const __grid_c
         mbar_wait(load_empty + st, ph ^ 1);
         // the block's record and per-row window bounds travel with the stage: a dependent L2 round trip per item in the
         // softmax warps would otherwise sit on the critical path (two of them: record, then bounds)
-        uint8_t* meta = s + 3 * kTile;
+        uint8_t* meta = smem + kOffMeta + st * kMetaBytes;
         *reinterpret_cast<int4*>(meta) = tl;                                  // released by the arrive below
 #ifdef ZV_WIN_SKIP16                     // timing experiment only (wrong results): no 32-byte-row boxes
         mbar_arrive_expect_tx(load_full + st, 3 * kB64 + kBoundsBytes);
@@ -197,9 +199,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_win_tc_kernel(const __grid_c
         const int st = k % STAGES, b = k & 1;
         // S/P buffer b was last read by P V of item k - 2 (its A operand): that product must have retired
         if (k >= 2) mbar_wait(o_full + b, ((k - 2) >> 1) & 1);
-        ZV_TRACE(1, k);                                        // issuer reaches Q K^T of item k
         mbar_wait(load_full + st, (k / STAGES) & 1);
-        ZV_TRACE(2, k);                                        // ... its tiles have landed
         tc_fence_after();
         const uint32_t sq = smem_u32(smem + st * kStage), sk = sq + kTile;
         const uint32_t d = tmem + b * BR;
@@ -214,11 +214,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_win_tc_kernel(const __grid_c
         if (k + 1 < n_mine) issue_qk(k + 1);
         const int st = k % STAGES, b = k & 1;
         const uint32_t sv = smem_u32(smem + st * kStage + 2 * kTile);
-        ZV_TRACE(3, k);                                        // issuer waits for P of item k
         mbar_wait(p_full + b, (k >> 1) & 1);
-        ZV_TRACE(4, k);
         mbar_wait(o_empty + b, ((k >> 1) & 1) ^ 1);          // the epilogue of item k - 2 has the old O in registers
-        ZV_TRACE(5, k);
         tc_fence_after();
         const uint32_t o = tmem + kOCol + b * HD, pa = tmem + b * BR;
 #pragma unroll
@@ -231,208 +228,193 @@ __global__ void __launch_bounds__(kThreads, 1) attn_win_tc_kernel(const __grid_c
         umma_commit(o_full + b);
       }
     }
-  } else {
-    // ---- softmax + epilogue warps: thread = row of the block
+  } else if (warp >= 2) {
+    // ---- softmax + epilogue warps: two sets of four (warps 2-5: even items, S/P/O buffer 0; warps 6-9: odd items, buffer 1;
+    // a warp reads the TMEM lane quarter warp % 4), thread = row of the block.  A tcgen05.ld round trip is ~400 clk plus
+    // the bytes over a 64 B/clk port (72 KB of S and O per item: measured 1 200 clk), then 600 clk of exponentials, the P
+    // store and the output staging - 4 000 clk per item when one set did everything in a row (clock stamps, tools/win_trace.py).
+    // With two sets the TMEM transfers of one item run under the arithmetic of the other.
+    const int set = (warp - 2) >> 2;
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const float sl2 = a.scale_log2;
-
-    // One loop step = softmax of item kn (if any) + epilogue of item kc (if any).  A tcgen05.ld round trip costs ~400 clk
-    // here (measured with clock stamps: the two-pass softmax spent 2 000 clk per item, four of them in a row, and the
-    // epilogue 1 600), so every TMEM read of the step - the S chunks of item kn AND the O row of item kc - is issued up front
-    // and waited for once; S stays in registers for the max and the exp pass.
-    float l_cur = 0.f, l_next = 0.f;
-    int r0_cur = 0, nr_cur = 0, r0_next = 0, nr_next = 0;
-    auto step_items = [&](const int kn, const int kc) {
-      uint32_t sr0[32], sr1[32], o[HD];
-      int cb = 0, ce = 0, c_lo = 0;
-      bool valid_n = false, two_chunk = true;
-      uint32_t sbuf = 0;
-      if (kn >= 0) {
-        const int b = kn & 1;
-        sbuf = tmem + lane_addr + b * BR;
-        if (warp == 2 && lane == 0) ZV_TRACE(6, kn);
-        mbar_wait(s_full + b, (kn >> 1) & 1);                    // S is complete, so the stage (and its meta block) has landed
-        if (warp == 2 && lane == 0) ZV_TRACE(7, kn);
-        tc_fence_after();
-        const uint8_t* meta = smem + (kn % STAGES) * kStage + 3 * kTile;
-        const int4 tl = *reinterpret_cast<const int4*>(meta);
-        r0_next = tl.x; nr_next = tl.y;
-        valid_n = row < tl.y;
-        if (valid_n) { const int2 w = reinterpret_cast<const int2*>(meta + 32)[(tl.x & 1) + row]; cb = w.x - tl.x; ce = w.y - tl.x; }
-        // 32-column chunks of S this warp needs: [c_lo, c_hi]; at most two for windows aligned to 32 rows (the usual case)
-        const int my_lo = valid_n ? cb >> 5 : 3, my_hi = valid_n ? (ce - 1) >> 5 : 0;
-        c_lo = __reduce_min_sync(0xffffffffu, my_lo);
-        const int c_hi = __reduce_max_sync(0xffffffffu, my_hi);
-        two_chunk = c_hi <= c_lo + 1;
-        if (two_chunk && c_lo <= c_hi) {
+    uint8_t* stage_out = smem + kOffOut + (set * 4 + quarter) * (32 * HD * 2);
+    const bool tracer = warp == 2 && lane == 0;
+    for (int k = set; k < n_mine; k += 2) {
+      const int b = set;                                          // = k & 1
+      const uint32_t ph = (uint32_t)(k >> 1) & 1u;
+      const uint32_t sbuf = tmem + lane_addr + b * BR;
+      // ---- softmax of item k
+      if (tracer) ZV_TRACE(6, k);
+      mbar_wait(s_full + b, ph);                                  // S is complete, so the stage (and its meta block) has landed
+      if (tracer) ZV_TRACE(7, k);
+      tc_fence_after();
+      const uint8_t* meta = smem + kOffMeta + (k % STAGES) * kMetaBytes;
+      const int4 tl = *reinterpret_cast<const int4*>(meta);
+      const bool valid = row < tl.y;
+      int cb = 0, ce = 0;
+      if (valid) { const int2 w = reinterpret_cast<const int2*>(meta + 32)[(tl.x & 1) + row]; cb = w.x - tl.x; ce = w.y - tl.x; }
+      // 32-column chunks of S this warp needs: [c_lo, c_hi]; at most two for windows aligned to 32 rows (the usual case)
+      const int c_lo = __reduce_min_sync(0xffffffffu, valid ? cb >> 5 : 3);
+      const int c_hi = __reduce_max_sync(0xffffffffu, valid ? (ce - 1) >> 5 : 0);
+      float l4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (c_hi <= c_lo + 1) {
+        uint32_t sr0[32], sr1[32];
+        if (c_lo <= c_hi) {
           tmem_ld_x32(sbuf + 32 * c_lo, sr0);
           if (c_lo < 3) tmem_ld_x32(sbuf + 32 * (c_lo + 1), sr1);
+          tmem_ld_wait();
         }
-      }
-      if (kc >= 0) {
-        const int b = kc & 1;
-        if (warp == 2 && lane == 0) ZV_TRACE(10, kc);
-        mbar_wait(o_full + b, (kc >> 1) & 1);
-        if (warp == 2 && lane == 0) ZV_TRACE(11, kc);
-        tc_fence_after();
+        if (tracer) ZV_TRACE(8, k);
+        const int col0 = 32 * c_lo;
+        const bool full = __all_sync(0xffffffffu, cb <= col0 && ce >= col0 + 64);
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        if (full) {
 #pragma unroll
-        for (int c = 0; c < HD; c += 16) tmem_ld_x16(tmem + lane_addr + kOCol + b * HD + c, *reinterpret_cast<uint32_t(*)[16]>(o + c));
-      }
-      tmem_ld_wait();
-      if (kc >= 0) {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(o_empty + (kc & 1));
-      }
-      if (warp == 2 && lane == 0 && kn >= 0) ZV_TRACE(8, kn);
-
-      // ---- softmax of item kn
-      if (kn >= 0) {
-        const int b = kn & 1;
-        float l4[4] = {0.f, 0.f, 0.f, 0.f};
-        if (two_chunk) {
-          const int col0 = 32 * c_lo;
-          const bool full = __all_sync(0xffffffffu, cb <= col0 && ce >= col0 + 64);
-          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-          if (full) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              m4[(i >> 1) & 3] = fmax3(m4[(i >> 1) & 3], __uint_as_float(sr0[i]), __uint_as_float(sr0[i + 1]));
-              m4[(i >> 1) & 3] = fmax3(m4[(i >> 1) & 3], __uint_as_float(sr1[i]), __uint_as_float(sr1[i + 1]));
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int c0 = col0 + i, c1 = col0 + 32 + i;
-              m4[i & 3] = fmaxf(m4[i & 3], (c0 >= cb && c0 < ce) ? __uint_as_float(sr0[i]) : -INFINITY);
-              m4[i & 3] = fmaxf(m4[i & 3], (c1 >= cb && c1 < ce) ? __uint_as_float(sr1[i]) : -INFINITY);
-            }
-          }
-          const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-          const float ms = valid_n ? m * sl2 : 0.f;
-          if (warp == 2 && lane == 0) ZV_TRACE(13, kn);           // row max done
-          uint32_t pk0[16], pk1[16];
-          if (full) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float p0 = ex2_approx(fmaf(__uint_as_float(sr0[2 * i]), sl2, -ms)), p1 = ex2_approx(fmaf(__uint_as_float(sr0[2 * i + 1]), sl2, -ms));
-              const float p2 = ex2_approx(fmaf(__uint_as_float(sr1[2 * i]), sl2, -ms)), p3 = ex2_approx(fmaf(__uint_as_float(sr1[2 * i + 1]), sl2, -ms));
-              l4[i & 3] += (p0 + p1) + (p2 + p3);
-              pk0[i] = pack2<F16>(p0, p1);
-              pk1[i] = pack2<F16>(p2, p3);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int c0 = col0 + 2 * i, c1 = col0 + 32 + 2 * i;
-              const float p0 = (c0 >= cb && c0 < ce) ? ex2_approx(fmaf(__uint_as_float(sr0[2 * i]), sl2, -ms)) : 0.f;
-              const float p1 = (c0 + 1 >= cb && c0 + 1 < ce) ? ex2_approx(fmaf(__uint_as_float(sr0[2 * i + 1]), sl2, -ms)) : 0.f;
-              const float p2 = (c1 >= cb && c1 < ce) ? ex2_approx(fmaf(__uint_as_float(sr1[2 * i]), sl2, -ms)) : 0.f;
-              const float p3 = (c1 + 1 >= cb && c1 + 1 < ce) ? ex2_approx(fmaf(__uint_as_float(sr1[2 * i + 1]), sl2, -ms)) : 0.f;
-              l4[i & 3] += (p0 + p1) + (p2 + p3);
-              pk0[i] = pack2<F16>(p0, p1);
-              pk1[i] = pack2<F16>(p2, p3);
-            }
-          }
-          if (warp == 2 && lane == 0) ZV_TRACE(14, kn);           // exponentials done
-          // P over the S columns (all of this warp's S is in registers by now); zeros for the chunks of other windows
-          uint32_t zero[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) zero[i] = 0u;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            if (c == c_lo) tmem_st_x16(sbuf + 16 * c, pk0);
-            else if (c == c_lo + 1) tmem_st_x16(sbuf + 16 * c, pk1);
-            else tmem_st_x16(sbuf + 16 * c, zero);
+          for (int i = 0; i < 32; i += 2) {
+            m4[(i >> 1) & 3] = fmax3(m4[(i >> 1) & 3], __uint_as_float(sr0[i]), __uint_as_float(sr0[i + 1]));
+            m4[(i >> 1) & 3] = fmax3(m4[(i >> 1) & 3], __uint_as_float(sr1[i]), __uint_as_float(sr1[i + 1]));
           }
         } else {
-          // general case (a warp's rows span three or four chunks: windows not aligned to 32 rows): two passes over TMEM
-          float m = -INFINITY;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const bool need = cb < 32 * (c + 1) && ce > 32 * c;
-            if (!__any_sync(0xffffffffu, need)) continue;
+          for (int i = 0; i < 32; ++i) {
+            const int c0 = col0 + i, c1 = col0 + 32 + i;
+            m4[i & 3] = fmaxf(m4[i & 3], (c0 >= cb && c0 < ce) ? __uint_as_float(sr0[i]) : -INFINITY);
+            m4[i & 3] = fmaxf(m4[i & 3], (c1 >= cb && c1 < ce) ? __uint_as_float(sr1[i]) : -INFINITY);
+          }
+        }
+        const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        const float ms = valid ? m * sl2 : 0.f;
+        if (tracer) ZV_TRACE(13, k);
+        uint32_t pk0[16], pk1[16];
+        if (full) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(sr0[2 * i]), sl2, -ms)), p1 = ex2_approx(fmaf(__uint_as_float(sr0[2 * i + 1]), sl2, -ms));
+            const float p2 = ex2_approx(fmaf(__uint_as_float(sr1[2 * i]), sl2, -ms)), p3 = ex2_approx(fmaf(__uint_as_float(sr1[2 * i + 1]), sl2, -ms));
+            l4[i & 3] += (p0 + p1) + (p2 + p3);
+            pk0[i] = pack2<F16>(p0, p1);
+            pk1[i] = pack2<F16>(p2, p3);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int c0 = col0 + 2 * i, c1 = col0 + 32 + 2 * i;
+            const float p0 = (c0 >= cb && c0 < ce) ? ex2_approx(fmaf(__uint_as_float(sr0[2 * i]), sl2, -ms)) : 0.f;
+            const float p1 = (c0 + 1 >= cb && c0 + 1 < ce) ? ex2_approx(fmaf(__uint_as_float(sr0[2 * i + 1]), sl2, -ms)) : 0.f;
+            const float p2 = (c1 >= cb && c1 < ce) ? ex2_approx(fmaf(__uint_as_float(sr1[2 * i]), sl2, -ms)) : 0.f;
+            const float p3 = (c1 + 1 >= cb && c1 + 1 < ce) ? ex2_approx(fmaf(__uint_as_float(sr1[2 * i + 1]), sl2, -ms)) : 0.f;
+            l4[i & 3] += (p0 + p1) + (p2 + p3);
+            pk0[i] = pack2<F16>(p0, p1);
+            pk1[i] = pack2<F16>(p2, p3);
+          }
+        }
+        if (tracer) ZV_TRACE(14, k);
+        // P over the S columns (all of this warp's S is in registers by now); zeros for the chunks of other windows
+        uint32_t zero[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) zero[i] = 0u;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c == c_lo) tmem_st_x16(sbuf + 16 * c, pk0);
+          else if (c == c_lo + 1) tmem_st_x16(sbuf + 16 * c, pk1);
+          else tmem_st_x16(sbuf + 16 * c, zero);
+        }
+      } else {
+        // general case (a warp's rows span three or four chunks: windows not aligned to 32 rows): two passes over TMEM
+        float m = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const bool need = cb < 32 * (c + 1) && ce > 32 * c;
+          if (!__any_sync(0xffffffffu, need)) continue;
+          uint32_t r[32];
+          tmem_ld_x32(sbuf + 32 * c, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int col = 32 * c + i;
+            m = fmaxf(m, (col >= cb && col < ce) ? __uint_as_float(r[i]) : -INFINITY);
+          }
+        }
+        const float ms = valid ? m * sl2 : 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const bool need = cb < 32 * (c + 1) && ce > 32 * c;
+          uint32_t pk[16];
+          if (__any_sync(0xffffffffu, need)) {
             uint32_t r[32];
             tmem_ld_x32(sbuf + 32 * c, r);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int col = 32 * c + i;
-              m = fmaxf(m, (col >= cb && col < ce) ? __uint_as_float(r[i]) : -INFINITY);
+            for (int i = 0; i < 16; ++i) {
+              const int col = 32 * c + 2 * i;
+              const float p0 = (col >= cb && col < ce) ? ex2_approx(fmaf(__uint_as_float(r[2 * i]), sl2, -ms)) : 0.f;
+              const float p1 = (col + 1 >= cb && col + 1 < ce) ? ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), sl2, -ms)) : 0.f;
+              l4[i & 3] += p0 + p1;
+              pk[i] = pack2<F16>(p0, p1);
             }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pk[i] = 0u;
           }
-          const float ms = valid_n ? m * sl2 : 0.f;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const bool need = cb < 32 * (c + 1) && ce > 32 * c;
-            uint32_t pk[16];
-            if (__any_sync(0xffffffffu, need)) {
-              uint32_t r[32];
-              tmem_ld_x32(sbuf + 32 * c, r);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const int col = 32 * c + 2 * i;
-                const float p0 = (col >= cb && col < ce) ? ex2_approx(fmaf(__uint_as_float(r[2 * i]), sl2, -ms)) : 0.f;
-                const float p1 = (col + 1 >= cb && col + 1 < ce) ? ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), sl2, -ms)) : 0.f;
-                l4[i & 3] += p0 + p1;
-                pk[i] = pack2<F16>(p0, p1);
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) pk[i] = 0u;
-            }
-            tmem_st_x16(sbuf + 16 * c, pk);       // P chunk c only overlaps S chunks <= c / 2: already consumed
-          }
+          tmem_st_x16(sbuf + 16 * c, pk);       // P chunk c only overlaps S chunks <= c / 2: already consumed
         }
-        if (warp == 2 && lane == 0) ZV_TRACE(15, kn);             // P stores issued
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(p_full + b);
-        if (warp == 2 && lane == 0) ZV_TRACE(9, kn);
-        l_next = (l4[0] + l4[1]) + (l4[2] + l4[3]);
       }
+      if (tracer) ZV_TRACE(15, k);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full + b);
+      if (tracer) ZV_TRACE(9, k);
+      const float l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
 
-      // ---- epilogue of item kc: O row * 1/l -> 16 bit -> global
-      if (kc >= 0) {
-        const int item = first + kc * step;
-        const int head = item % a.heads;
-        // A thread's row is 160 contiguous bytes, but 32 lanes x 16 bytes of 32 different rows per store instruction cost
-        // the LSU ~300 clk each under load (measured: 3 100 clk per item for the ten of them).  A warp whose 32 rows are all
-        // inside the block stages them in shared memory and hands them to the TMA unit as one [32][80] box; warps at the
-        // ragged end of a block keep the per-thread stores.
-        const bool row_ok = row < nr_cur;
-        const float inv = row_ok ? 1.f / l_cur : 0.f;
-        uint4 ov[HD / 8];
+      // ---- epilogue of item k: O row * 1/l -> 16 bit -> global
+      const int head = (first + k * step) % a.heads;
+      if (tracer) ZV_TRACE(10, k);
+      mbar_wait(o_full + b, ph);
+      if (tracer) ZV_TRACE(11, k);
+      tc_fence_after();
+      uint32_t o[HD];
 #pragma unroll
-        for (int j = 0; j < HD / 8; ++j)
-          ov[j] = make_uint4(pack2<F16>(__uint_as_float(o[8 * j]) * inv, __uint_as_float(o[8 * j + 1]) * inv),
-                             pack2<F16>(__uint_as_float(o[8 * j + 2]) * inv, __uint_as_float(o[8 * j + 3]) * inv),
-                             pack2<F16>(__uint_as_float(o[8 * j + 4]) * inv, __uint_as_float(o[8 * j + 5]) * inv),
-                             pack2<F16>(__uint_as_float(o[8 * j + 6]) * inv, __uint_as_float(o[8 * j + 7]) * inv));
-        if (__all_sync(0xffffffffu, row_ok)) {
-          uint4* stg = reinterpret_cast<uint4*>(smem + kOffOut + quarter * (32 * HD * 2) + lane * (HD * 2));
-          if (lane == 0) bulk_store_wait_read();               // the previous box has left this staging area
-          __syncwarp();
+      for (int c = 0; c < HD; c += 16) tmem_ld_x16(tmem + lane_addr + kOCol + b * HD + c, *reinterpret_cast<uint32_t(*)[16]>(o + c));
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty + b);
+      if (tracer) ZV_TRACE(1, k);                                 // (trace slots 1-5 are reused by the tracer warp here)
+      // A thread's row is 160 contiguous bytes, but 32 lanes x 16 bytes of 32 different rows per store instruction cost the
+      // LSU ~300 clk each under load (measured: 3 100 clk per item for the ten of them).  A warp whose 32 rows are all inside
+      // the block stages them in shared memory and hands them to the TMA unit as one [32][80] box; warps at the ragged end
+      // of a block keep the per-thread stores.
+      const float inv = valid ? 1.f / l : 0.f;
+      uint4 ov[HD / 8];
 #pragma unroll
-          for (int j = 0; j < HD / 8; ++j) stg[j] = ov[j];
-          fence_proxy_async_smem();                            // generic-proxy writes -> visible to the TMA unit
-          __syncwarp();
-          if (lane == 0) tma_store_2d(&tm_out, smem + kOffOut + quarter * (32 * HD * 2), head * HD, r0_cur + quarter * 32);
-        } else if (row_ok) {
-          uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(a.out) + (int64_t)(r0_cur + row) * a.hidden + head * HD);
+      for (int j = 0; j < HD / 8; ++j)
+        ov[j] = make_uint4(pack2<F16>(__uint_as_float(o[8 * j]) * inv, __uint_as_float(o[8 * j + 1]) * inv),
+                           pack2<F16>(__uint_as_float(o[8 * j + 2]) * inv, __uint_as_float(o[8 * j + 3]) * inv),
+                           pack2<F16>(__uint_as_float(o[8 * j + 4]) * inv, __uint_as_float(o[8 * j + 5]) * inv),
+                           pack2<F16>(__uint_as_float(o[8 * j + 6]) * inv, __uint_as_float(o[8 * j + 7]) * inv));
+      if (__all_sync(0xffffffffu, valid)) {
+        uint4* stg = reinterpret_cast<uint4*>(stage_out + lane * (HD * 2));
+        if (tracer) ZV_TRACE(2, k);
+        if (lane == 0) bulk_store_wait_read();                   // the previous box has left this staging area
+        __syncwarp();
+        if (tracer) ZV_TRACE(3, k);
 #pragma unroll
-          for (int j = 0; j < HD / 8; ++j) dst[j] = ov[j];
-        }
-        if (warp == 2 && lane == 0) ZV_TRACE(12, kc);
+        for (int j = 0; j < HD / 8; ++j) stg[j] = ov[j];
+        fence_proxy_async_smem();                                // generic-proxy writes -> visible to the TMA unit
+        __syncwarp();
+        if (tracer) ZV_TRACE(4, k);
+        if (lane == 0) tma_store_2d(&tm_out, stage_out, head * HD, tl.x + quarter * 32);
+      } else if (valid) {
+        uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(a.out) + (int64_t)(tl.x + row) * a.hidden + head * HD);
+#pragma unroll
+        for (int j = 0; j < HD / 8; ++j) dst[j] = ov[j];
       }
-      l_cur = l_next; r0_cur = r0_next; nr_cur = nr_next;
-    };
-    for (int k = -1; k < n_mine; ++k) step_items(k + 1 < n_mine ? k + 1 : -1, k);      // the products of item k + 1 run under the softmax of item k
-    if (lane == 0) bulk_store_wait_all();           // this warp's TMA stores have been written before the CTA exits
+      if (tracer) ZV_TRACE(12, k);
+    }
+    if (lane == 0) bulk_store_wait_all();             // this warp's TMA stores have been written before the CTA exits
   }
   pdl_trigger();
   tc_fence_before();
