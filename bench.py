@@ -415,13 +415,23 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         n_e2e = min(n_img, args.e2e_images)
+        e2e_schedule = [int(v) for v in args.e2e_schedule.split(",")] if args.e2e_schedule else None
         host = [im.cpu().pin_memory() for im in images[:n_e2e]]
         out_host = torch.empty((n_e2e * T_img, 2048), dtype=op_dtype).pin_memory()
 
         def step_e2e():
             # H2D of this step's pixels and D2H of its embeddings, pipelined in chunks behind the compute
-            enc.encode_host(host, chunk=args.e2e_chunk, out_host=out_host)
+            enc.encode_host(host, chunk=args.e2e_chunk, out_host=out_host, schedule=e2e_schedule)
 
+        # the link the e2e figure is bound by: pinned host -> device bandwidth of this box (8 images, 600 MB)
+        torch.cuda.synchronize()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record()
+        tmp_dev = [h.to(dev, non_blocking=True) for h in host[:8]]
+        h1.record()
+        torch.cuda.synchronize()
+        h2d_gbps = sum(h.numel() for h in host[:8]) / (h0.elapsed_time(h1) / 1e3) / 1e9
+        del tmp_dev
         for _ in range(2):
             step_e2e()
         barrier()
@@ -437,7 +447,10 @@ def run_ours(args):
             dt = t.item()
         e2e = {"value": world * n_e2e * T_img / dt, "unit": "tokens/s", "h2d_bytes_per_step": n_e2e * IMG * IMG * 3,
                "d2h_bytes_per_step": n_e2e * T_img * 2048 * 2, "images_per_step": n_e2e, "ms_per_step": dt * 1e3,
-               "pipeline": f"chunks of {args.e2e_chunk} images: H2D on a copy stream, K1+tower, D2H on a third stream"}
+               "h2d_gbps_measured": h2d_gbps, "h2d_ms_per_step_at_that_rate": n_e2e * IMG * IMG * 3 / h2d_gbps / 1e6,
+               "pipeline": (f"chunks of {e2e_schedule} images (ramp: a short first chunk keeps the exposed upload small, long later "
+                            f"chunks keep the tower's batches large)" if e2e_schedule else f"chunks of {args.e2e_chunk} images") +
+                           ": H2D on a copy stream, K1+tower, D2H on a third stream"}
         del host
 
     cpu_base = None
@@ -511,6 +524,7 @@ def main():
     ap.add_argument("--images", type=int, default=64, help="images per step per GPU (BASELINE configs[1]: 64)")
     ap.add_argument("--e2e-images", type=int, default=64)
     ap.add_argument("--e2e-chunk", type=int, default=8, help="images per pipelined upload/compute chunk in the e2e leg")
+    ap.add_argument("--e2e-schedule", default="2,6,8,16,32", help="chunk sizes of the e2e pipeline (the last repeats); '' = --e2e-chunk")
     ap.add_argument("--ref-images", type=int, default=4, help="images in the CPU reference sample (BASELINE.md 3: 4 items)")
     ap.add_argument("--operand-dtype", default="fp16", choices=["fp16", "bf16"],
                     help="16-bit type of the GEMM / attention operands (fp16 = the shipped default; same tensor-core rate)")
