@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
 rc=0
-for f in tests/test_gpu_gemm.py tests/test_gpu_k1.py tests/test_gpu_attn.py tests/test_gpu_tower.py; do
+for f in tests/test_gpu_*.py; do
   n=$(basename $f .py)
   timeout 600 python -m pytest $f -q -m gpu --timeout 300 -p no:cacheprovider > gpurun_out/$n.log 2>&1
   r=$?
