@@ -10,7 +10,8 @@ pytestmark = pytest.mark.gpu
                                   # window layers (every segment <= 64 rows: the tcgen05 window kernel): the bench shape's window
                                   # sizes, every multiple of 4, blocks that end with tiny windows, odd sizes, hundreds of windows
                                   [64] * 8 + [48] + [64] * 8 + [48] + [48] * 8 + [36], list(range(4, 68, 4)), [64, 60, 4, 4, 4, 64, 12],
-                                  [4], [1, 7, 33, 64, 5, 63, 2], [64] * 300 + [16] * 7 + [48] * 41])
+                                  [4], [1, 7, 33, 64, 5, 63, 2], [64] * 300 + [16] * 7 + [48] * 41,
+                                  [4] * 301 + [8] * 50 + [60, 64, 4] * 9])
 def test_attention_vs_sdpa(cuda, lib, segs, dtype):
     import numpy as np
     from zoomearth_b200 import _lib

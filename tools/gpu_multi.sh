@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round-2 run C (2 GPUs): fused-gather correctness logs, the N=2 bench line (double-buffered gather + configs[3] sharded
+# Multi-GPU run (N=2 by default): fused-gather correctness logs, the bench line at N ranks (double-buffered gather + configs[3]
 # sub-record), and the new single-GPU tests.
 mkdir -p gpurun_out
 N=${N:-2}
