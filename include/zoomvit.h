@@ -132,6 +132,16 @@ ZV_API int zv_resize_u8(int32_t n, const uint8_t* const* src_dev, const int32_t*
                         const int32_t* crop_box, const int32_t* out_hw, uint8_t* const* dst_dev, const int64_t* dst_pitch,
                         void* workspace_dev, int64_t workspace_bytes, void* stream);
 
+/* Test hook (CPU, no GPU needed): runs the HOST side of zv_preprocess / zv_resize_u8 - descriptors, tap tables, work
+ * lists of the tensor-core route (csrc/zv_k1_tc.cuh) - over HOST pointers and emulates that route's kernels lane by lane
+ * on the CPU.  took_tc[i] = 1 for the crops the route accepts (inside the image, 16-byte aligned base, <= 4 K blocks);
+ * only those are written.  u8_dst_host == NULL: fp32 patches into out_host (zv_preprocess), else uint8 images
+ * (zv_resize_u8).  Checks everything but the hardware layouts (swizzle, descriptors, TMEM), which the GPU tests cover. */
+ZV_API int zv_debug_k1_tc_host(const zv_cfg* cfg, int32_t n, const uint8_t* const* src_host, const int32_t* src_hw,
+                               const int64_t* src_pitch, const int32_t* crop_box, const int32_t* resized_hw, float* out_host,
+                               int32_t row_order, uint8_t* const* u8_dst_host, const int64_t* u8_pitch, void* workspace_host,
+                               int64_t workspace_bytes, int32_t* took_tc);
+
 /* ---------------------------------------------------------------- plan: per-batch integer bookkeeping */
 typedef struct zv_plan zv_plan;
 ZV_API int zv_plan_create(const zv_cfg* cfg, int32_t n, const int64_t* grid_thw, zv_plan** out);

@@ -632,6 +632,25 @@ int make_tmap_2d(void* tm_, const void* base, int64_t rows, int64_t cols, int64_
   return ZV_OK;
 }
 
+// 2-D uint8 tensor (dim1 rows of dim0 bytes, row pitch stride1 bytes, a multiple of 16), box0 x box1 box, 128-byte swizzle,
+// OOB = 0.  K1's tensor-core route: an image seen as super-rows of four rows (zv_k1_tc.cuh).
+int make_tmap_u8(void* tm_, const void* base, uint64_t dim0, uint64_t dim1, uint64_t stride1, int box0, int box1) {
+  CUtensorMap* tm = static_cast<CUtensorMap*>(tm_);
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(ZV_ECUDA, "tma: cuTensorMapEncodeTiled is not available from the driver");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || stride1 % 16 || dim0 == 0 || dim1 == 0)
+    return fail(ZV_EINVAL, "tma: uint8 operand base/pitch must be 16-byte aligned (base %p, pitch %llu)", base, (unsigned long long)stride1);
+  cuuint64_t dims[2] = {(cuuint64_t)dim0, (cuuint64_t)dim1};
+  cuuint64_t strides[1] = {(cuuint64_t)stride1};
+  cuuint32_t box[2] = {(cuuint32_t)box0, (cuuint32_t)box1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ZV_ECUDA, "tma: cuTensorMapEncodeTiled (uint8) failed with CUresult %d", (int)r);
+  return ZV_OK;
+}
+
 int gemm(int epi, const GemmArgs& g, const void* a, int64_t lda, const void* b, int64_t ldb, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return fail(ZV_EINVAL, "gemm: empty problem %dx%dx%d", g.M, g.N, g.K);

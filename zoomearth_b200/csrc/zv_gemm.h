@@ -71,6 +71,8 @@ int gemm(int epi, const GemmArgs& g, const void* a, int64_t lda, const void* b, 
 // cuTensorMapEncodeTiled wrapper (tm points at a CUtensorMap): 16-bit 2-D tensor, box_cols x box_rows box.
 int make_tmap_2d(void* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
                  int swizzle_bytes, bool f16);
+// 2-D uint8 tensor map (dim1 rows of dim0 bytes, row pitch stride1 bytes), 128-byte swizzle, OOB = 0 (zv_gemm.cu).
+int make_tmap_u8(void* tm, const void* base, uint64_t dim0, uint64_t dim1, uint64_t stride1, int box0, int box1);
 // tcgen05 flash attention for long segments (zv_attn_tc.cu): qkv (S, 3*H) 16-bit with rotary applied; tiles
 // (q0, q_len, seg_begin, seg_end) with q_len <= 128.
 int attention_tc(const void* qkv, void* out, int64_t S, int heads, int head_dim, const int32_t* tiles_dev, int n_tiles,

@@ -24,6 +24,7 @@
 //               in registers and sweeps the columns coalesced; the CTA assembles two merge groups' patch rows in shared
 //               memory and streams them out with 16-byte stores.
 // Everything else (huge downscales, unaligned pitches) takes the plain per-tap kernels k1_hpass / k1_vpass.
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -67,7 +68,7 @@ struct K1Crop {
   int32_t fast;            // 1: tmp is row-quad packed (fast path), 0: plain rows
   int32_t ks_mma;          // horizontal pass on IMMA: 32-byte K steps per 8-column block (1..4), 0 = dp4a kernel
   int32_t off_mh;          // int32 offset of the IMMA fragment table of the horizontal axis
-  int32_t pad_;
+  int32_t tc;               // 1: both passes on the tensor cores (k1_resample_tc), the kernels below are not used
   uint8_t* dst;            // uint8 output mode (zv_resize_u8): (oh, ow, 3) image, row pitch dst_pitch bytes
   int64_t dst_pitch;
 };
@@ -108,10 +109,10 @@ __device__ __forceinline__ uint32_t pack4_sat(int v0, int v1, int v2, int v3) {
 
 // Position of merge group (my, mx) in the tower's window order (closed form of argsort(window_index),
 // HF modeling_qwen2_5_vl.py:411-451): windows of ws x ws merge groups, row-major over windows, row-major inside.
-__device__ __forceinline__ int window_pos(int my, int mx, int lh, int lw, int ws) {
+__host__ __device__ __forceinline__ int window_pos(int my, int mx, int lh, int lw, int ws) {
   // ws = 4 for every Qwen2.5-VL tower (window 112 / merge 2 / patch 14): shifts instead of two runtime divisions
   const int wy = ws == 4 ? my >> 2 : my / ws, wx = ws == 4 ? mx >> 2 : mx / ws;
-  const int bh = min(ws, lh - wy * ws), bw = min(ws, lw - wx * ws);
+  const int bh = ws < lh - wy * ws ? ws : lh - wy * ws, bw = ws < lw - wx * ws ? ws : lw - wx * ws;
   return wy * ws * lw + wx * ws * bh + (my - wy * ws) * bw + (mx - wx * ws);
 }
 
@@ -703,6 +704,8 @@ __global__ void __launch_bounds__(256) k1_vpass_u8(const K1Crop* __restrict__ cr
   c.dst[(int64_t)yy * c.dst_pitch + col] = (uint8_t)clip8(acc >> kPrecisionBits);
 }
 
+#include "zv_k1_tc.cuh"
+
 // ------------------------------------------------------------------------------------------------ host side
 inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 inline int nw_class(int ksize) {                   // words per tap window (<= 3 samples of misalignment + ksize taps)
@@ -712,7 +715,8 @@ inline int nw_class(int ksize) {                   // words per tap window (<= 3
 }
 
 struct AxisTables { int32_t off_bounds = 0, off_kk = 0, off_limbs = 0, ksize = 0, nw = 0, seg_words = 0, tile_quads = 0;
-                    int32_t off_mma = 0, ks_mma = 0, pitch_mma = 0; };
+                    int32_t off_mma = 0, ks_mma = 0, pitch_mma = 0;
+                    int32_t nkb3 = 0, nkb1 = 0; };      // tensor-core route: 128-byte K blocks per 32-byte chunk, 3 channels / 1 channel
 // 32-byte K steps the IMMA horizontal pass needs per 8-column block, from the geometry alone (so that the workspace size
 // does not depend on the tables): 8 neighbouring outputs span at most floor(7 scale) + 2 source samples between their first
 // taps, + ksize taps, + 3 samples of word alignment.  0 = more than 4 steps (the dp4a kernel handles those).
@@ -724,6 +728,10 @@ inline int32_t mma_ksteps(int32_t in_size, int32_t out_size, int32_t ksize) {
 }
 struct Layout {
   int64_t off_desc = 0, off_lut = 0, off_coef = 0, off_lists = 0, off_tmp = 0, bytes = 0;
+  int64_t off_tmaps = 0, off_jobs = 0, off_pjobs = 0;     // tensor-core route: 2 tensor maps, 2 RJob and 1 PJob per crop
+  std::vector<int64_t> u_off;                // per crop, relative to off_tmp: the finished uint8 image (zv_preprocess only)
+  std::vector<int64_t> t_pitch;              // per crop: bytes per row of the transposed intermediate T
+  int64_t item_cap_tc = 0;
   std::vector<int64_t> tmp_off;              // per crop, relative to off_tmp
   std::vector<int32_t> ybox0, nrows;
   std::map<std::pair<int32_t, int32_t>, AxisTables> axis;   // (in, out) -> table offsets
@@ -735,14 +743,26 @@ struct Layout {
   int64_t item_cap_h = 0, item_cap_v = 0;
 };
 constexpr int kItemsTarget = 148 * 8;        // aim for at least this many work items per launch
-struct AxisCache { std::vector<int32_t> ints; int32_t seg_words = 0, tile_quads = 0, pitch_mma = 0; };
+struct AxisCache { std::vector<int32_t> ints; int32_t seg_words = 0, tile_quads = 0, pitch_mma = 0, nkb3 = 0, nkb1 = 0; };
+// K blocks (128 input bytes) the widest 32-output-byte chunk of an axis needs when its samples are `ch` bytes apart
+inline int32_t tc_k_blocks(const zv::AxisCoeffs& ac, int32_t n_out, int32_t ch) {
+  int32_t span = 0;
+  const int32_t n_bytes = n_out * ch;
+  for (int32_t b0 = 0; b0 < n_bytes; b0 += kTcCols) {
+    const int32_t o0 = b0 / ch, o1 = std::min(n_out - 1, (b0 + kTcCols - 1) / ch);
+    int32_t end = 0;
+    for (int32_t o = o0; o <= o1; ++o) end = std::max(end, ac.bounds[2 * o] + ac.bounds[2 * o + 1]);
+    span = std::max(span, ch * (end - ac.bounds[2 * o0]));
+  }
+  return (span + 127) / 128;
+}
 std::mutex g_axis_mu;
 std::map<std::pair<int32_t, int32_t>, std::shared_ptr<const AxisCache>> g_axis_cache;
 
 // Workspace layout shared by zv_preprocess_workspace_bytes and zv_preprocess.
 // u8_out: the vertical pass writes plain uint8 images (zv_resize_u8): any positive output size, row-group work items.
 int build_layout(int32_t n, const int32_t* crop_box, const int32_t* resized_hw, Layout* L, bool fill, bool u8_out = false) {
-  L->tmp_off.resize(n); L->ybox0.resize(n); L->nrows.resize(n);
+  L->tmp_off.resize(n); L->ybox0.resize(n); L->nrows.resize(n); L->u_off.resize(n); L->t_pitch.resize(n);
   int64_t coef_ints = 0, tmp_bytes = 0;
   for (int32_t i = 0; i < n; ++i) {
     const int32_t cw = crop_box[4 * i + 2] - crop_box[4 * i], ch = crop_box[4 * i + 3] - crop_box[4 * i + 1];
@@ -775,6 +795,7 @@ int build_layout(int32_t n, const int32_t* crop_box, const int32_t* resized_hw, 
       if (fill && hit) {
         L->coef.insert(L->coef.end(), hit->ints.begin(), hit->ints.end());
         t.seg_words = hit->seg_words; t.tile_quads = hit->tile_quads; t.pitch_mma = hit->pitch_mma;
+        t.nkb3 = hit->nkb3; t.nkb1 = hit->nkb1;
       } else if (fill) {
         const size_t coef_start = L->coef.size();
         zv::AxisCoeffs ac;
@@ -854,9 +875,12 @@ int build_layout(int32_t n, const int32_t* crop_box, const int32_t* resized_hw, 
           }
           t.pitch_mma = span + ((4 - span % 8) + 8) % 8;
         }
+        t.nkb3 = tc_k_blocks(ac, key.second, 3);
+        t.nkb1 = tc_k_blocks(ac, key.second, 1);
         auto entry = std::make_shared<AxisCache>();
         entry->ints.assign(L->coef.begin() + coef_start, L->coef.end());
         entry->seg_words = t.seg_words; entry->tile_quads = t.tile_quads; entry->pitch_mma = t.pitch_mma;
+        entry->nkb3 = t.nkb3; entry->nkb1 = t.nkb1;
         std::lock_guard<std::mutex> lock(g_axis_mu);
         if (g_axis_cache.size() >= 512) g_axis_cache.clear();              // bounded: a few hundred KB per entry at most
         g_axis_cache[key] = entry;
@@ -879,7 +903,16 @@ int build_layout(int32_t n, const int32_t* crop_box, const int32_t* resized_hw, 
     L->tmp_off[i] = tmp_bytes;
     // fast path: 4 rows per word, quads counted from ybox0 rounded down to 4, spare quads for zero-tap window padding
     const int64_t quads = (int64_t)((y_last + 3) / 4 - y_first / 4) + kMaxNW + 1;
-    tmp_bytes += align_up(std::max<int64_t>((int64_t)L->nrows[i] * ow * 3, quads * ow * 3 * 4), 256);
+    // tensor-core route: T[3 ow rounded up to 4][t_pitch], one byte per (output column byte, crop row from ybox0 & ~3)
+    L->t_pitch[i] = align_up(4 * (int64_t)((y_last + 3) / 4 - y_first / 4), 16);
+    const int64_t t_bytes = align_up(3 * (int64_t)ow, 4) * L->t_pitch[i];
+    tmp_bytes += align_up(std::max<int64_t>(std::max<int64_t>((int64_t)L->nrows[i] * ow * 3, quads * ow * 3 * 4), t_bytes), 256);
+    if (!u8_out) {                        // ... and the finished uint8 image the patchify kernel reads
+      L->u_off[i] = tmp_bytes;
+      tmp_bytes += align_up((int64_t)oh * ow * 3, 256);
+    }
+    const int64_t tiles1 = ((y_last + 3) / 4 - y_first / 4 + 127) / 128, tiles2 = ((3 * (int64_t)ow + 3) / 4 + 127) / 128;
+    L->item_cap_tc += ((3 * (int64_t)ow + kTcCols - 1) / kTcCols) * tiles1 + (((int64_t)oh + kTcCols - 1) / kTcCols) * tiles2;
   }
   // work-list sizing (geometry only, so that the workspace size does not depend on the tables)
   int64_t units_h = 0, units_v = 0;
@@ -899,14 +932,17 @@ int build_layout(int32_t n, const int32_t* crop_box, const int32_t* resized_hw, 
     L->item_cap_h += ((ow + kHCols - 1) / kHCols) * std::max((strips + L->strips_per_item - 1) / L->strips_per_item, (strips16 + per16 - 1) / per16);
     L->item_cap_v += u8_out ? (oh + 7) / 8 : (int64_t)(oh / 28) * ((pairs + L->pairs_per_item - 1) / L->pairs_per_item);
   }
-  if (L->item_cap_h > INT32_MAX / 8 || L->item_cap_v > INT32_MAX / 8) return zv::fail(ZV_EINVAL, "zv_preprocess: batch too large for one launch");
+  if (L->item_cap_h > INT32_MAX / 8 || L->item_cap_v > INT32_MAX / 8 || L->item_cap_tc > INT32_MAX / 8) return zv::fail(ZV_EINVAL, "zv_preprocess: batch too large for one launch");
   int64_t off = 0;
   L->off_desc = off; off = align_up(off + (int64_t)n * sizeof(K1Crop), 256);
   L->off_lut = off; off = align_up(off + 768 * sizeof(float), 256);
   L->off_coef = off; off = align_up(off + coef_ints * (int64_t)sizeof(int32_t), 256);
   // work lists of the fast kernels (int4 items) first, then, for the per-tap kernels, crop ids + block prefix per pass
-  L->list_ints = 4 * (L->item_cap_h + L->item_cap_v) + 4 * ((int64_t)n + 16);
+  L->list_ints = 4 * (L->item_cap_h + L->item_cap_v + L->item_cap_tc) + 4 * ((int64_t)n + 16);
   L->off_lists = off; off = align_up(off + L->list_ints * (int64_t)sizeof(int32_t), 256);
+  L->off_tmaps = off; off = align_up(off + 2 * (int64_t)n * (int64_t)sizeof(CUtensorMap), 256);
+  L->off_jobs = off; off = align_up(off + 2 * (int64_t)n * (int64_t)sizeof(RJob), 256);
+  L->off_pjobs = off; off = align_up(off + (int64_t)n * (int64_t)sizeof(PJob), 256);
   L->off_tmp = off; off += tmp_bytes;
   L->bytes = off;
   return ZV_OK;
@@ -973,10 +1009,13 @@ void launch_vpass(int nw, int count, cudaStream_t s, const K1Crop* d, const int3
 int k1_run(const char* who, const zv_cfg* cfg, int32_t n, const uint8_t* const* src_dev, const int32_t* src_hw,
            const int64_t* src_pitch, const int32_t* crop_box, const int32_t* resized_hw, const int64_t* row_off,
            void* out_dev, int32_t out_dtype, int32_t row_order, uint8_t* const* u8_dst, const int64_t* u8_pitch,
-           void* workspace_dev, int64_t workspace_bytes, void* stream_) {
+           void* workspace_dev, int64_t workspace_bytes, void* stream_, int32_t* emulate_tc = nullptr) {
+  // emulate_tc != nullptr (zv_debug_k1_tc_host, CPU tests): every pointer is HOST memory; nothing is launched, the
+  // tensor-core route's kernels are emulated on the CPU over the very tables built here and emulate_tc[i] tells which
+  // crops took that route (the others are left untouched).
   const bool u8_out = u8_dst != nullptr;
   int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return zv::fail(ZV_ENODEV, "%s: no CUDA device", who);
+  if (!emulate_tc && (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)) return zv::fail(ZV_ENODEV, "%s: no CUDA device", who);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   Layout L;
   int rc = build_layout(n, crop_box, resized_hw, &L, true, u8_out);
@@ -993,6 +1032,12 @@ int k1_run(const char* who, const zv_cfg* cfg, int32_t n, const uint8_t* const* 
   const bool generic_only = false;
 #endif
   std::vector<int32_t> seg_h(n, 0), tq_v(n, 0), pitch_m(n, 0);
+#ifdef ZV_DEBUG_K1_NO_TC                // compile-time debug build: keep every crop on the IMMA / dp4a kernels
+  const bool tc_enabled = false;
+#else
+  const bool tc_enabled = !generic_only;
+#endif
+  int32_t n_tc = 0;
   int64_t row = 0;
   for (int32_t i = 0; i < n; ++i) {
     K1Crop& c = d[i];
@@ -1023,7 +1068,20 @@ int k1_run(const char* who, const zv_cfg* cfg, int32_t n, const uint8_t* const* 
     seg_h[i] = h.seg_words;
     tq_v[i] = v.tile_quads;
     c.ybox0 = L.ybox0[i]; c.nrows = L.nrows[i];
-    if (c.fast) {                       // row quads are counted from ybox0 rounded down to 4
+    // Tensor-core route (k1_resample_tc): the crop lies inside the image (no zero fill needed), the row pitch is a
+    // multiple of 4 bytes (four image rows = one TMA row with a 16-byte-multiple stride), every row the pass reads lies in
+    // a complete group of four image rows, and a 32-byte chunk of either axis spans at most kTcMaxNkb K blocks.  A base
+    // that is not 16-byte aligned (a cropped view) is rounded down and the difference added to the byte offset, which
+    // works as long as the four-row group still fits its pitch.
+    {
+      const int64_t delta = (int64_t)(reinterpret_cast<uintptr_t>(c.src) & 15);
+      const int64_t y_lo = (int64_t)c.y0 + (c.ybox0 & ~3), y_hi = (int64_t)c.y0 + c.ybox0 + c.nrows;
+      const bool inside = c.x0 >= 0 && c.x0 + c.cw <= c.src_w && y_lo >= 0 && y_hi <= (int64_t)(c.src_h / 4) * 4;
+      c.tc = (tc_enabled && inside && (c.pitch & 3) == 0 && (delta == 0 || 3 * (int64_t)c.src_w + delta <= c.pitch) &&
+              4 * c.pitch < (int64_t)1 << 30 && h.nkb3 >= 1 && h.nkb3 <= kTcMaxNkb && v.nkb1 >= 1 && v.nkb1 <= kTcMaxNkb) ? 1 : 0;
+      if (c.tc) { c.fast = 0; c.nwh = -1; c.nwv = -1; c.ks_mma = 0; ++n_tc; }
+    }
+    if (c.fast || c.tc) {               // row quads are counted from ybox0 rounded down to 4
       const int32_t al = c.ybox0 & ~3;
       c.nrows += c.ybox0 - al; c.ybox0 = al;
     }
@@ -1107,12 +1165,97 @@ int k1_run(const char* who, const zv_cfg* cfg, int32_t n, const uint8_t* const* 
   };
   rc = build(false, &hl);
   if (!rc) rc = build(true, &vl);
+  // tensor-core route: job descriptors, tensor maps and the two work lists (job, 32-byte chunk, first tile, tiles)
+  struct TcLaunch { int64_t list_off = 0, count = 0; int nkb = 1; } tc1, tc2;
+  int32_t n_pjobs = 0;
+  int64_t patch_blocks = 0;
+  if (!rc && n_tc) {
+    RJob* jobs = reinterpret_cast<RJob*>(host.data() + L.off_jobs);
+    PJob* pjobs = reinterpret_cast<PJob*>(host.data() + L.off_pjobs);
+    uint8_t* tmaps = host.data() + L.off_tmaps;
+    uint8_t* ws_dev = static_cast<uint8_t*>(workspace_dev);
+    int64_t tile_units = 0;
+    for (int32_t i = 0; i < n && !rc; ++i) {
+      const K1Crop& c = d[i];
+      if (!c.tc) continue;
+      const AxisTables& h = L.axis[{c.cw, c.ow}];
+      const AxisTables& v = L.axis[{c.ch, c.oh}];
+      const int64_t t_pitch = L.t_pitch[i];
+      uint8_t* t_dev = ws_dev + c.tmp_off;
+      RJob& j1 = jobs[2 * i];
+      const int64_t delta = (int64_t)(reinterpret_cast<uintptr_t>(c.src) & 15);
+      j1.x_off = 3 * (int64_t)c.x0 + delta; j1.in_pitch = c.pitch; j1.out = t_dev; j1.out_pitch = t_pitch;
+      j1.row0 = c.y0 + c.ybox0; j1.n_rows = c.nrows; j1.n_out = c.ow; j1.ch = 3;
+      j1.off_b = c.off_bh; j1.off_k = c.off_kh; j1.ksize = c.ksh; j1.origin = 0; j1.tmap = 2 * i; j1.nkb = h.nkb3;
+      j1.in_base = c.src - delta; j1.in_dim0 = 3 * c.pitch + 3 * (int64_t)c.src_w + delta; j1.in_dim1 = c.src_h / 4;
+      RJob& j2 = jobs[2 * i + 1];
+      j2.x_off = 0; j2.in_pitch = t_pitch;
+      j2.out = u8_out ? c.dst : ws_dev + L.off_tmp + L.u_off[i];
+      j2.out_pitch = u8_out ? c.dst_pitch : 3 * (int64_t)c.ow;
+      j2.row0 = 0; j2.n_rows = 3 * c.ow; j2.n_out = c.oh; j2.ch = 1;
+      j2.off_b = c.off_bv; j2.off_k = c.off_kv; j2.ksize = c.ksv; j2.origin = c.ybox0; j2.tmap = 2 * i + 1; j2.nkb = v.nkb1;
+      j2.in_base = t_dev; j2.in_dim0 = 4 * t_pitch; j2.in_dim1 = (3 * c.ow + 3) / 4;
+      tc1.nkb = std::max(tc1.nkb, h.nkb3); tc2.nkb = std::max(tc2.nkb, v.nkb1);
+      // source: super-rows of four image rows (the last image row's padding is not touched); T likewise
+      if (!emulate_tc) {
+        CUtensorMap tm;
+        rc = zv::make_tmap_u8(&tm, j1.in_base, (uint64_t)j1.in_dim0, (uint64_t)j1.in_dim1, 4 * (uint64_t)j1.in_pitch, 128, 128);
+        if (rc) break;
+        std::memcpy(tmaps + (size_t)(2 * i) * sizeof(CUtensorMap), &tm, sizeof(tm));
+        rc = zv::make_tmap_u8(&tm, j2.in_base, (uint64_t)j2.in_dim0, (uint64_t)j2.in_dim1, 4 * (uint64_t)j2.in_pitch, 128, 128);
+        if (rc) break;
+        std::memcpy(tmaps + (size_t)(2 * i + 1) * sizeof(CUtensorMap), &tm, sizeof(tm));
+      }
+      if (!u8_out) {
+        PJob& pj = pjobs[n_pjobs++];
+        pj.u = j2.out; pj.u_pitch = j2.out_pitch; pj.out_row0 = c.out_row0; pj.lh = c.lh; pj.lw = c.lw;
+        pj.blk0 = (int32_t)patch_blocks;
+        patch_blocks += (int64_t)c.lh * c.lw;
+        if (patch_blocks > INT32_MAX) rc = zv::fail(ZV_EINVAL, "zv_preprocess: batch too large for one launch");
+      }
+      tile_units += (((int64_t)3 * c.ow + kTcCols - 1) / kTcCols) * (((c.nrows + 3) / 4 + 127) / 128);
+    }
+    // tiles per item: whole columns when the batch is large (the B operand of a chunk is built once per item),
+    // single tiles when it is small (spread over every SM)
+    const int per = (int)std::min<int64_t>(16, std::max<int64_t>(1, tile_units / (std::max(1, emulate_tc ? 148 : zv::num_sms()) * 4)));
+    for (int pass = 0; pass < 2 && !rc; ++pass) {
+      TcLaunch& tl = pass ? tc2 : tc1;
+      tl.list_off = cur;
+      for (int32_t i = 0; i < n; ++i) {
+        const K1Crop& c = d[i];
+        if (!c.tc) continue;
+        const int chunks = pass ? (c.oh + kTcCols - 1) / kTcCols : (3 * c.ow + kTcCols - 1) / kTcCols;
+        const int tiles = pass ? ((3 * c.ow + 3) / 4 + 127) / 128 : ((c.nrows + 3) / 4 + 127) / 128;
+        for (int t0 = 0; t0 < tiles; t0 += per)
+          for (int ck = 0; ck < chunks; ++ck) {
+            lists[cur++] = 2 * i + pass; lists[cur++] = ck; lists[cur++] = t0; lists[cur++] = std::min(per, tiles - t0);
+          }
+      }
+      tl.count = (cur - tl.list_off) / 4;
+    }
+  }
   if (!rc) rc = build_generic(false, &hl);
   if (!rc) rc = build_generic(true, &vl);
   if (rc) return rc;
   if (cur > L.list_ints) return zv::fail(ZV_EINVAL, "zv_preprocess: launch lists overflow");
 
   uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
+  if (emulate_tc) {
+    std::memcpy(ws, host.data(), host.size());
+    for (int32_t i = 0; i < n; ++i) emulate_tc[i] = d[i].tc;
+    if (!n_tc) return ZV_OK;
+    const RJob* jobs = reinterpret_cast<const RJob*>(ws + L.off_jobs);
+    const int32_t* coef = reinterpret_cast<const int32_t*>(ws + L.off_coef);
+    const int4* items = reinterpret_cast<const int4*>(reinterpret_cast<const int32_t*>(ws + L.off_lists));
+    tc_emulate_resample(jobs, items + tc1.list_off / 4, (int)tc1.count, coef);
+    tc_emulate_resample(jobs, items + tc2.list_off / 4, (int)tc2.count, coef);
+    if (!u8_out) {
+      if (out_dtype != ZV_F32) return zv::fail(ZV_EINVAL, "%s: the host emulation writes fp32 patches only", who);
+      tc_emulate_patchify<float>(reinterpret_cast<const PJob*>(ws + L.off_pjobs), n_pjobs, reinterpret_cast<const float*>(ws + L.off_lut),
+                                 static_cast<float*>(out_dev), row_order, cfg->window / cfg->merge / cfg->patch, &window_pos);
+    }
+    return ZV_OK;
+  }
   cudaError_t e = cudaMemcpyAsync(ws, host.data(), host.size(), cudaMemcpyHostToDevice, stream);
   if (e != cudaSuccess) return zv::fail(ZV_ECUDA, "%s: table upload: %s", who, cudaGetErrorString(e));
   const K1Crop* dcrops = reinterpret_cast<const K1Crop*>(ws + L.off_desc);
@@ -1168,6 +1311,39 @@ int k1_run(const char* who, const zv_cfg* cfg, int32_t n, const uint8_t* const* 
       zv::count_launch();
     }
   }
+  if (n_tc) {
+    const RJob* djobs = reinterpret_cast<const RJob*>(ws + L.off_jobs);
+    const CUtensorMap* dtmaps = reinterpret_cast<const CUtensorMap*>(ws + L.off_tmaps);
+    static std::atomic<uint64_t> attr{0};
+    const int dev = zv::current_device();
+    if (zv::device_needs_setup(attr, dev)) {
+      cudaFuncSetAttribute(k1_resample_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      zv::mark_device(attr, dev);
+    }
+    auto launch_tc = [&](const TcLaunch& tl) {
+      const int stages = tc_stages(tl.nkb);
+      const int grid = (int)std::min<int64_t>(tl.count, zv::num_sms());
+      zv::launch_pdl(k1_resample_tc, dim3((unsigned)grid), dim3(kTcThreads), (size_t)tc_smem_bytes(stages, tl.nkb), stream, 1,
+                     djobs, reinterpret_cast<const int4*>(dlists + tl.list_off), (int)tl.count, dcoef, dtmaps, stages, tl.nkb);
+      zv::count_launch();
+    };
+    {
+      zv::KernelTimer timer(zv::KC_K1_HPASS, stream);
+      launch_tc(tc1);
+    }
+    {
+      zv::KernelTimer timer(zv::KC_K1_VPASS, stream);
+      launch_tc(tc2);
+      if (!u8_out) {
+        const PJob* dpj = reinterpret_cast<const PJob*>(ws + L.off_pjobs);
+        const unsigned blocks = (unsigned)patch_blocks;
+        if (out_dtype == ZV_BF16) zv::launch_pdl(k1_patchify_u8<__nv_bfloat16>, dim3(blocks), dim3(256), 0, stream, 1, dpj, (int)n_pjobs, dlut, static_cast<__nv_bfloat16*>(out_dev), (int)row_order, wsz);
+        else if (out_dtype == ZV_F16) zv::launch_pdl(k1_patchify_u8<__half>, dim3(blocks), dim3(256), 0, stream, 1, dpj, (int)n_pjobs, dlut, static_cast<__half*>(out_dev), (int)row_order, wsz);
+        else zv::launch_pdl(k1_patchify_u8<float>, dim3(blocks), dim3(256), 0, stream, 1, dpj, (int)n_pjobs, dlut, static_cast<float*>(out_dev), (int)row_order, wsz);
+        zv::count_launch();
+      }
+    }
+  }
   e = cudaGetLastError();
   if (e != cudaSuccess) return zv::fail(ZV_ECUDA, "%s: launch: %s", who, cudaGetErrorString(e));
   return ZV_OK;
@@ -1198,6 +1374,17 @@ int zv_preprocess(const zv_cfg* cfg, int32_t n, const uint8_t* const* src_dev, c
   if (row_order != ZV_ORDER_HF && row_order != ZV_ORDER_WINDOW) return zv::fail(ZV_EINVAL, "zv_preprocess: bad row_order");
   return k1_run("zv_preprocess", cfg, n, src_dev, src_hw, src_pitch, crop_box, resized_hw, row_off, out_dev, out_dtype, row_order,
                 nullptr, nullptr, workspace_dev, workspace_bytes, stream_);
+}
+
+int zv_debug_k1_tc_host(const zv_cfg* cfg, int32_t n, const uint8_t* const* src_host, const int32_t* src_hw,
+                        const int64_t* src_pitch, const int32_t* crop_box, const int32_t* resized_hw, float* out_host,
+                        int32_t row_order, uint8_t* const* u8_dst_host, const int64_t* u8_pitch, void* workspace_host,
+                        int64_t workspace_bytes, int32_t* took_tc) {
+  if (n <= 0 || !src_host || !src_hw || !src_pitch || !crop_box || !resized_hw || !workspace_host || !took_tc)
+    return zv::fail(ZV_EINVAL, "zv_debug_k1_tc_host: null argument");
+  if (!u8_dst_host && (!cfg || !out_host)) return zv::fail(ZV_EINVAL, "zv_debug_k1_tc_host: patch mode needs cfg and out_host");
+  return k1_run("zv_debug_k1_tc_host", cfg, n, src_host, src_hw, src_pitch, crop_box, resized_hw, nullptr, out_host, ZV_F32, row_order,
+                u8_dst_host, u8_pitch, workspace_host, workspace_bytes, nullptr, took_tc);
 }
 
 int64_t zv_resize_u8_workspace_bytes(int32_t n, const int32_t* crop_box, const int32_t* out_hw) {
