@@ -66,6 +66,8 @@ CASES = [
     (1200, 1600, (3, 5, 1599, 1197), (224, 308), "5.2x downscale, 23 taps"),
     (504, 700, (0, 0, 700, 504), (504, 728), "vertical identity"),
     (2000, 2000, (0, 0, 2000, 2000), (196, 196), "10x downscale, 4 K blocks"),
+    (400, 1000, (1, 2, 999, 398), (140, 196), "pitch = 8 mod 16: two B variants (the 5000-pixel case)"),
+    (800, 1300, (0, 0, 1300, 800), (168, 252), "pitch = 12 mod 16, two K blocks: four B variants, single-buffered B"),
 ]
 
 

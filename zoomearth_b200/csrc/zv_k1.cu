@@ -754,8 +754,10 @@ inline int32_t tc_k_blocks(const zv::AxisCoeffs& ac, int32_t n_out, int32_t ch) 
     for (int32_t o = o0; o <= o1; ++o) end = std::max(end, ac.bounds[2 * o] + ac.bounds[2 * o + 1]);
     span = std::max(span, ch * (end - ac.bounds[2 * o0]));
   }
-  return (span + 127) / 128;
+  return (span + 15 + 127) / 128;            // + up to 15 bytes between the 16-byte aligned TMA box start and the window
 }
+// B variants of an input with this row pitch: distinct values of (q pitch) mod 16 over the four row phases
+inline int32_t tc_variants(int64_t pitch) { return (pitch & 15) == 0 ? 1 : (pitch & 7) == 0 ? 2 : 4; }
 std::mutex g_axis_mu;
 std::map<std::pair<int32_t, int32_t>, std::shared_ptr<const AxisCache>> g_axis_cache;
 
@@ -1070,7 +1072,7 @@ int k1_run(const char* who, const zv_cfg* cfg, int32_t n, const uint8_t* const* 
     c.ybox0 = L.ybox0[i]; c.nrows = L.nrows[i];
     // Tensor-core route (k1_resample_tc): the crop lies inside the image (no zero fill needed), the row pitch is a
     // multiple of 4 bytes (four image rows = one TMA row with a 16-byte-multiple stride), every row the pass reads lies in
-    // a complete group of four image rows, and a 32-byte chunk of either axis spans at most kTcMaxNkb K blocks.  A base
+    // a complete group of four image rows, and a 32-byte chunk of either axis spans at most kTcMaxNkb K blocks (and its B variants fit 96 KB).  A base
     // that is not 16-byte aligned (a cropped view) is rounded down and the difference added to the byte offset, which
     // works as long as the four-row group still fits its pitch.
     {
@@ -1078,7 +1080,8 @@ int k1_run(const char* who, const zv_cfg* cfg, int32_t n, const uint8_t* const* 
       const int64_t y_lo = (int64_t)c.y0 + (c.ybox0 & ~3), y_hi = (int64_t)c.y0 + c.ybox0 + c.nrows;
       const bool inside = c.x0 >= 0 && c.x0 + c.cw <= c.src_w && y_lo >= 0 && y_hi <= (int64_t)(c.src_h / 4) * 4;
       c.tc = (tc_enabled && inside && (c.pitch & 3) == 0 && (delta == 0 || 3 * (int64_t)c.src_w + delta <= c.pitch) &&
-              4 * c.pitch < (int64_t)1 << 30 && h.nkb3 >= 1 && h.nkb3 <= kTcMaxNkb && v.nkb1 >= 1 && v.nkb1 <= kTcMaxNkb) ? 1 : 0;
+              4 * c.pitch < (int64_t)1 << 30 && h.nkb3 >= 1 && h.nkb3 <= kTcMaxNkb &&
+              h.nkb3 * tc_variants(c.pitch) <= kTcMaxBBlocks && v.nkb1 >= 1 && v.nkb1 <= kTcMaxNkb) ? 1 : 0;
       if (c.tc) { c.fast = 0; c.nwh = -1; c.nwv = -1; c.ks_mma = 0; ++n_tc; }
     }
     if (c.fast || c.tc) {               // row quads are counted from ybox0 rounded down to 4
@@ -1166,7 +1169,9 @@ int k1_run(const char* who, const zv_cfg* cfg, int32_t n, const uint8_t* const* 
   rc = build(false, &hl);
   if (!rc) rc = build(true, &vl);
   // tensor-core route: job descriptors, tensor maps and the two work lists (job, 32-byte chunk, first tile, tiles)
-  struct TcLaunch { int64_t list_off = 0, count = 0; int nkb = 1; } tc1, tc2;
+  // pass 1 is launched per B-variant class (1, 2, 4 variants: the shared-memory split depends on it), pass 2 has one
+  struct TcLaunch { int64_t list_off = 0, count = 0; int nkb = 1, nvar = 1; } tcl[4];      // [0..2]: pass 1 with 1 / 2 / 4 variants, [3]: pass 2
+  auto tc_class = [](int nvar) { return nvar == 1 ? 0 : nvar == 2 ? 1 : 2; };
   int32_t n_pjobs = 0;
   int64_t patch_blocks = 0;
   if (!rc && n_tc) {
@@ -1188,6 +1193,7 @@ int k1_run(const char* who, const zv_cfg* cfg, int32_t n, const uint8_t* const* 
       j1.row0 = c.y0 + c.ybox0; j1.n_rows = c.nrows; j1.n_out = c.ow; j1.ch = 3;
       j1.off_b = c.off_bh; j1.off_k = c.off_kh; j1.ksize = c.ksh; j1.origin = 0; j1.tmap = 2 * i; j1.nkb = h.nkb3;
       j1.in_base = c.src - delta; j1.in_dim0 = 3 * c.pitch + 3 * (int64_t)c.src_w + delta; j1.in_dim1 = c.src_h / 4;
+      j1.nvar = tc_variants(c.pitch);
       RJob& j2 = jobs[2 * i + 1];
       j2.x_off = 0; j2.in_pitch = t_pitch;
       j2.out = u8_out ? c.dst : ws_dev + L.off_tmp + L.u_off[i];
@@ -1195,7 +1201,9 @@ int k1_run(const char* who, const zv_cfg* cfg, int32_t n, const uint8_t* const* 
       j2.row0 = 0; j2.n_rows = 3 * c.ow; j2.n_out = c.oh; j2.ch = 1;
       j2.off_b = c.off_bv; j2.off_k = c.off_kv; j2.ksize = c.ksv; j2.origin = c.ybox0; j2.tmap = 2 * i + 1; j2.nkb = v.nkb1;
       j2.in_base = t_dev; j2.in_dim0 = 4 * t_pitch; j2.in_dim1 = (3 * c.ow + 3) / 4;
-      tc1.nkb = std::max(tc1.nkb, h.nkb3); tc2.nkb = std::max(tc2.nkb, v.nkb1);
+      j2.nvar = 1;                          // t_pitch is a multiple of 16
+      TcLaunch& l1 = tcl[tc_class(j1.nvar)];
+      l1.nvar = j1.nvar; l1.nkb = std::max(l1.nkb, h.nkb3); tcl[3].nkb = std::max(tcl[3].nkb, v.nkb1);
       // source: super-rows of four image rows (the last image row's padding is not touched); T likewise
       if (!emulate_tc) {
         CUtensorMap tm;
@@ -1218,12 +1226,13 @@ int k1_run(const char* who, const zv_cfg* cfg, int32_t n, const uint8_t* const* 
     // tiles per item: whole columns when the batch is large (the B operand of a chunk is built once per item),
     // single tiles when it is small (spread over every SM)
     const int per = (int)std::min<int64_t>(16, std::max<int64_t>(1, tile_units / (std::max(1, emulate_tc ? 148 : zv::num_sms()) * 4)));
-    for (int pass = 0; pass < 2 && !rc; ++pass) {
-      TcLaunch& tl = pass ? tc2 : tc1;
+    for (int cls = 0; cls < 4 && !rc; ++cls) {
+      TcLaunch& tl = tcl[cls];
+      const int pass = cls == 3;
       tl.list_off = cur;
       for (int32_t i = 0; i < n; ++i) {
         const K1Crop& c = d[i];
-        if (!c.tc) continue;
+        if (!c.tc || (!pass && tc_class(jobs[2 * i].nvar) != cls)) continue;
         const int chunks = pass ? (c.oh + kTcCols - 1) / kTcCols : (3 * c.ow + kTcCols - 1) / kTcCols;
         const int tiles = pass ? ((3 * c.ow + 3) / 4 + 127) / 128 : ((c.nrows + 3) / 4 + 127) / 128;
         for (int t0 = 0; t0 < tiles; t0 += per)
@@ -1247,8 +1256,8 @@ int k1_run(const char* who, const zv_cfg* cfg, int32_t n, const uint8_t* const* 
     const RJob* jobs = reinterpret_cast<const RJob*>(ws + L.off_jobs);
     const int32_t* coef = reinterpret_cast<const int32_t*>(ws + L.off_coef);
     const int4* items = reinterpret_cast<const int4*>(reinterpret_cast<const int32_t*>(ws + L.off_lists));
-    tc_emulate_resample(jobs, items + tc1.list_off / 4, (int)tc1.count, coef);
-    tc_emulate_resample(jobs, items + tc2.list_off / 4, (int)tc2.count, coef);
+    for (const TcLaunch& tl : tcl)
+      if (tl.count) tc_emulate_resample(jobs, items + tl.list_off / 4, (int)tl.count, coef);
     if (!u8_out) {
       if (out_dtype != ZV_F32) return zv::fail(ZV_EINVAL, "%s: the host emulation writes fp32 patches only", who);
       tc_emulate_patchify<float>(reinterpret_cast<const PJob*>(ws + L.off_pjobs), n_pjobs, reinterpret_cast<const float*>(ws + L.off_lut),
@@ -1321,19 +1330,22 @@ int k1_run(const char* who, const zv_cfg* cfg, int32_t n, const uint8_t* const* 
       zv::mark_device(attr, dev);
     }
     auto launch_tc = [&](const TcLaunch& tl) {
-      const int stages = tc_stages(tl.nkb);
+      if (!tl.count) return;
+      const int nbuf = tc_b_buffers(tl.nvar, tl.nkb), b_blocks = nbuf * tl.nvar * tl.nkb;
+      const int stages = tc_stages(b_blocks);
       const int grid = (int)std::min<int64_t>(tl.count, zv::num_sms());
-      zv::launch_pdl(k1_resample_tc, dim3((unsigned)grid), dim3(kTcThreads), (size_t)tc_smem_bytes(stages, tl.nkb), stream, 1,
-                     djobs, reinterpret_cast<const int4*>(dlists + tl.list_off), (int)tl.count, dcoef, dtmaps, stages, tl.nkb);
+      zv::launch_pdl(k1_resample_tc, dim3((unsigned)grid), dim3(kTcThreads), (size_t)tc_smem_bytes(stages, b_blocks), stream, 1,
+                     djobs, reinterpret_cast<const int4*>(dlists + tl.list_off), (int)tl.count, dcoef, dtmaps, stages, tl.nkb,
+                     tl.nvar, nbuf);
       zv::count_launch();
     };
     {
       zv::KernelTimer timer(zv::KC_K1_HPASS, stream);
-      launch_tc(tc1);
+      for (int cls = 0; cls < 3; ++cls) launch_tc(tcl[cls]);
     }
     {
       zv::KernelTimer timer(zv::KC_K1_VPASS, stream);
-      launch_tc(tc2);
+      launch_tc(tcl[3]);
       if (!u8_out) {
         const PJob* dpj = reinterpret_cast<const PJob*>(ws + L.off_pjobs);
         const unsigned blocks = (unsigned)patch_blocks;

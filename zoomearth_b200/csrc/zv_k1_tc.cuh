@@ -11,13 +11,18 @@
 //
 // Tile = 512 input rows x 32 output bytes.  The rows enter as four A operands of 128 rows each (rows 4 m + q for
 // q = 0..3, one TMA box over the input viewed as super-rows of four image rows: any row pitch that is a multiple of
-// 4 bytes becomes a legal 16-byte-multiple TMA stride, and a box may start at any byte), so TMEM lane m of the four
+// 4 bytes becomes a legal 16-byte-multiple TMA stride), so TMEM lane m of the four
 // accumulator blocks holds the four rows 4 m .. 4 m + 3 of one output column: a thread packs them into one 32-bit
 // word, and the 32 lanes of a warp store 128 contiguous bytes of the transposed output - no shuffles, no staging.
 // B[96][128 NKB] holds, for the chunk's 32 output bytes, the three signed base-256 digits of every 22-bit tap at the
 // K position (= input byte) it multiplies, zero elsewhere; it is built in shared memory from the compact tap tables
 // by two otherwise idle warps while the previous chunk computes.  D[128][96] per q: digit sums; the epilogue folds
 // them (a0 + 256 a1 + 65536 a2 + 2^21) >> 22 and saturates exactly like Pillow's clip8.
+// A TMA box must start on a 16-byte boundary of global memory (measured with tools/micro/tc_probe.cu: any other start
+// coordinate is an illegal instruction), so every box starts at its window's first byte rounded down to 16 and the 0..15
+// bytes of slack move the taps inside B instead: one B variant per distinct slack.  The slack of row 4 m + q is
+// ((q' pitch) + offset) mod 16 with q' = row mod 4, so there is 1 variant when the pitch is a multiple of 16 (T always),
+// 2 for pitch = 8 mod 16 (a 5000-pixel row), 4 otherwise.
 //
 // 384 threads: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-3 = B builder (warp 2 owns the TMEM allocation),
 // warps 4-11 = epilogue (lane quarter = warp & 3, output bytes 16 (warp - 4) / 4 ..).  mbarrier pipelines: A ring
@@ -41,7 +46,8 @@ struct RJob {                 // one resample pass over one crop
   int32_t nkb;                // 128-byte K blocks per chunk
   const uint8_t* in_base;     // the tensor map's base and extent, for the host emulation of the kernel (tests): the
   int64_t in_dim0;            // device kernel reaches the input through TMA only
-  int32_t in_dim1, pad_;
+  int32_t in_dim1;
+  int32_t nvar;               // B variants (1, 2 or 4): distinct box-start slacks of the four row phases
 };
 
 constexpr int kTcThreads = 384;
@@ -52,12 +58,20 @@ constexpr int kTcBBlock = kTcN * 128;       // one B K block
 constexpr int kTcMaxNkb = 4;
 constexpr int kTcBarBytes = 512;
 
-__host__ __device__ constexpr int tc_smem_bytes(int stages, int nkb) {
-  return 1024 + stages * kTcStageBytes + 2 * nkb * kTcBBlock + kTcBarBytes;
+constexpr int kTcMaxBBlocks = 8;            // variants x K blocks of one B buffer (96 KB)
+// B blocks = buffers x variants x K blocks
+__host__ __device__ constexpr int tc_smem_bytes(int stages, int b_blocks) {
+  return 1024 + stages * kTcStageBytes + b_blocks * kTcBBlock + kTcBarBytes;
 }
-inline int tc_stages(int nkb) {             // as many A stages as fit beside the two B buffers (<= 12)
-  const int room = 227 * 1024 - tc_smem_bytes(0, nkb);
+inline int tc_b_buffers(int nvar, int nkb) { return nvar * nkb <= kTcMaxBBlocks / 2 ? 2 : 1; }   // double-buffered while it fits 96 KB
+inline int tc_stages(int b_blocks) {        // as many A stages as fit beside B (<= 12)
+  const int room = 227 * 1024 - tc_smem_bytes(0, b_blocks);
   return std::min(12, room / kTcStageBytes);
+}
+// Slack of B variant v: bytes between the 16-byte aligned start of the TMA boxes of the rows with row mod nvar = v and
+// the first byte of the chunk's window in those rows.
+__host__ __device__ __forceinline__ int tc_slack(const RJob& j, int wb0, int v) {
+  return (int)(((int64_t)v * j.in_pitch + j.x_off + wb0) & 15);
 }
 
 // signed base-256 digits of a 22-bit tap: k = d[0] + 256 d[1] + 65536 d[2], d[0], d[1] in [-128, 127]
@@ -93,13 +107,15 @@ __host__ __device__ __forceinline__ int tc_chunk_wb0(const RJob& j, const int32_
 
 __global__ void __launch_bounds__(kTcThreads, 1) k1_resample_tc(const RJob* __restrict__ jobs, const int4* __restrict__ items,
                                                                 int n_items, const int32_t* __restrict__ coef,
-                                                                const CUtensorMap* __restrict__ tmaps, int stages, int nkb_max) {
+                                                                const CUtensorMap* __restrict__ tmaps, int stages, int nkb_max,
+                                                                int nvar_max, int nbuf) {
   using namespace zv::ptx;
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
-  uint8_t* sB = smem + stages * kTcStageBytes;                     // [2][nkb_max][96 rows][128 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + 2 * nkb_max * kTcBBlock);
+  uint8_t* sB = smem + stages * kTcStageBytes;                     // [nbuf][nvar_max][nkb_max][96 rows][128 B]
+  const int b_buf_bytes = nvar_max * nkb_max * kTcBBlock;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + nbuf * b_buf_bytes);
   uint64_t* full = bars;                  // [stages]
   uint64_t* empty = bars + 12;            // [stages]
   uint64_t* dfull = bars + 24;            // [4]
@@ -138,7 +154,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k1_resample_tc(const RJob* __re
           for (int q = 0; q < 4; ++q) {
             const int r0 = j.row0 + q + 512 * t;                   // input row of lane 0; lane m holds row r0 + 4 m
             const int32_t cy = r0 >> 2;
-            const int64_t cx = (int64_t)(r0 & 3) * j.in_pitch + xbase;
+            const int64_t cx = ((int64_t)(r0 & 3) * j.in_pitch + xbase) & ~(int64_t)15;     // 16-byte aligned box start
             for (int kb = 0; kb < nkb; ++kb) {
               mbar_wait(empty + stage, phase ^ 1);
               mbar_arrive_expect_tx(full + stage, kTcStageBytes);
@@ -157,17 +173,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) k1_resample_tc(const RJob* __re
       uint32_t n_item = 0, n_tile = 0;
       for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++n_item) {
         const int4 item = __ldg(items + it);
-        const int nkb = jobs[item.x].nkb;
-        const uint32_t buf = n_item & 1;
-        mbar_wait(bfull + buf, (n_item >> 1) & 1);
+        const RJob& j = jobs[item.x];
+        const int nkb = j.nkb, row0 = j.row0, vmask = j.nvar - 1;
+        const uint32_t buf = n_item % (uint32_t)nbuf;
+        mbar_wait(bfull + buf, (n_item / (uint32_t)nbuf) & 1);
         tc_fence_after();
-        const uint32_t b_addr = smem_u32(sB + buf * nkb_max * kTcBBlock);
+        const uint32_t b_buf = smem_u32(sB + buf * b_buf_bytes);
         for (int t = 0; t < item.w; ++t, ++n_tile) {
 #pragma unroll 1
           for (int q = 0; q < 4; ++q) {
             mbar_wait(dempty + q, (n_tile & 1) ^ 1);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + (uint32_t)(q * kTcN);
+            const uint32_t b_addr = b_buf + (uint32_t)(((row0 + q) & vmask) * nkb_max * kTcBBlock);   // the variant of this row phase
             for (int kb = 0; kb < nkb; ++kb) {
               mbar_wait(full + stage, phase);
               tc_fence_after();
@@ -191,17 +209,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) k1_resample_tc(const RJob* __re
     for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++n_item) {
       const int4 item = __ldg(items + it);
       const RJob& j = jobs[item.x];
-      const uint32_t buf = n_item & 1;
-      mbar_wait(bempty + buf, ((n_item >> 1) & 1) ^ 1);
-      uint8_t* B = sB + buf * nkb_max * kTcBBlock;
-      const int nkb = j.nkb, ch = j.ch, ksize = j.ksize;
-      {
-        uint4* z = reinterpret_cast<uint4*>(B);
+      const uint32_t buf = n_item % (uint32_t)nbuf;
+      mbar_wait(bempty + buf, ((n_item / (uint32_t)nbuf) & 1) ^ 1);
+      uint8_t* B = sB + buf * b_buf_bytes;
+      const int nkb = j.nkb, ch = j.ch, ksize = j.ksize, nvar = j.nvar;
+      for (int v = 0; v < nvar; ++v) {
+        uint4* z = reinterpret_cast<uint4*>(B + v * nkb_max * kTcBBlock);
         const int n16 = nkb * kTcBBlock / 16;
         for (int i = tid; i < n16; i += 64) z[i] = make_uint4(0u, 0u, 0u, 0u);
       }
       asm volatile("bar.sync 1, 64;" ::: "memory");
       const int wb0 = tc_chunk_wb0(j, coef, item.y);
+      int slack[4];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) slack[v] = tc_slack(j, wb0, v);
       const int n_bytes = j.n_out * ch;
       for (int idx = tid; idx < kTcCols * ksize; idx += 64) {
         const int c = idx / ksize, t = idx - c * ksize;
@@ -212,15 +233,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) k1_resample_tc(const RJob* __re
         if (t >= cnt) continue;
         int dg[3];
         tc_digits(__ldg(coef + j.off_k + (int64_t)o * ksize + t), dg);
-        const int kbyte = ch * (xmin - j.origin + t) + cc - wb0;      // K position of this tap (0 <= kbyte < 128 nkb by construction)
-        if (kbyte < 0 || kbyte >= 128 * nkb) continue;               // (never: the host sized nkb from the same tables)
-        const int kb = kbyte >> 7, kin = kbyte & 127;
-        uint8_t* blk = B + kb * kTcBBlock + (kin & 15);
-        const int ck = kin >> 4;
+        const int kwin = ch * (xmin - j.origin + t) + cc - wb0;       // input byte of this tap, from the window's first byte
 #pragma unroll
-        for (int l = 0; l < 3; ++l) {
-          const int n = tc_b_row(c, l);
-          blk[(n >> 3) * 1024 + (n & 7) * 128 + ((ck ^ (n & 7)) << 4)] = (uint8_t)dg[l];     // 128B-swizzled K-major row
+        for (int v = 0; v < 4; ++v) {
+          if (v >= nvar) break;
+          const int kbyte = kwin + slack[v];                         // K position (0 <= kbyte < 128 nkb by construction)
+          if (kbyte < 0 || kbyte >= 128 * nkb) continue;             // (never: the host sized nkb from the same tables)
+          const int kb = kbyte >> 7, kin = kbyte & 127;
+          uint8_t* blk = B + (v * nkb_max + kb) * kTcBBlock + (kin & 15);
+          const int ck = kin >> 4;
+#pragma unroll
+          for (int l = 0; l < 3; ++l) {
+            const int n = tc_b_row(c, l);
+            blk[(n >> 3) * 1024 + (n & 7) * 128 + ((ck ^ (n & 7)) << 4)] = (uint8_t)dg[l];   // 128B-swizzled K-major row
+          }
         }
       }
       tc_fence_proxy_async();              // generic-proxy stores -> visible to the tensor core
@@ -340,7 +366,7 @@ inline void tc_emulate_resample(const RJob* jobs, const int4* items, int n_items
     const int4 item = items[it];
     const RJob& j = jobs[item.x];
     const int K = 128 * j.nkb;
-    B.assign((size_t)kTcN * K, 0);
+    B.assign((size_t)j.nvar * kTcN * K, 0);                                  // [variant][row][K]
     const int wb0 = tc_chunk_wb0(j, coef, item.y);
     const int n_bytes = j.n_out * j.ch;
     for (int c = 0; c < kTcCols; ++c) {
@@ -351,9 +377,12 @@ inline void tc_emulate_resample(const RJob* jobs, const int4* items, int n_items
       for (int t = 0; t < cnt; ++t) {
         int dg[3];
         tc_digits(coef[j.off_k + (int64_t)o * j.ksize + t], dg);
-        const int kbyte = j.ch * (xmin - j.origin + t) + cc - wb0;
-        if (kbyte < 0 || kbyte >= K) continue;
-        for (int l = 0; l < 3; ++l) B[(size_t)tc_b_row(c, l) * K + kbyte] = (int8_t)dg[l];
+        const int kwin = j.ch * (xmin - j.origin + t) + cc - wb0;
+        for (int v = 0; v < j.nvar; ++v) {
+          const int kbyte = kwin + tc_slack(j, wb0, v);
+          if (kbyte < 0 || kbyte >= K) continue;
+          for (int l = 0; l < 3; ++l) B[((size_t)v * kTcN + tc_b_row(c, l)) * K + kbyte] = (int8_t)dg[l];
+        }
       }
     }
     std::vector<uint8_t> a((size_t)K);
@@ -362,7 +391,8 @@ inline void tc_emulate_resample(const RJob* jobs, const int4* items, int n_items
         int val[4][kTcCols];
         for (int q = 0; q < 4; ++q) {
           const int r0 = j.row0 + q + 512 * t;
-          const int64_t cy = (r0 >> 2) + m, cx = (int64_t)(r0 & 3) * j.in_pitch + j.x_off + wb0;
+          const int64_t cy = (r0 >> 2) + m, cx = ((int64_t)(r0 & 3) * j.in_pitch + j.x_off + wb0) & ~(int64_t)15;
+          const int var = r0 & (j.nvar - 1);
           for (int k = 0; k < K; ++k) {                                     // one row of the TMA boxes, zero outside the tensor
             const int64_t x = cx + k;
             a[k] = (cy >= 0 && cy < j.in_dim1 && x >= 0 && x < j.in_dim0) ? j.in_base[cy * 4 * j.in_pitch + x] : 0;
@@ -370,7 +400,7 @@ inline void tc_emulate_resample(const RJob* jobs, const int4* items, int n_items
           for (int c = 0; c < kTcCols; ++c) {
             int acc[3];
             for (int l = 0; l < 3; ++l) {
-              const int8_t* b = B.data() + (size_t)tc_b_row(c, l) * K;
+              const int8_t* b = B.data() + ((size_t)var * kTcN + tc_b_row(c, l)) * K;
               int s = 0;
               for (int k = 0; k < K; ++k) s += (int)a[k] * (int)b[k];
               acc[l] = s;
