@@ -1348,10 +1348,11 @@ int k1_run(const char* who, const zv_cfg* cfg, int32_t n, const uint8_t* const* 
       launch_tc(tcl[3]);
       if (!u8_out) {
         const PJob* dpj = reinterpret_cast<const PJob*>(ws + L.off_pjobs);
-        const unsigned blocks = (unsigned)patch_blocks;
-        if (out_dtype == ZV_BF16) zv::launch_pdl(k1_patchify_u8<__nv_bfloat16>, dim3(blocks), dim3(256), 0, stream, 1, dpj, (int)n_pjobs, dlut, static_cast<__nv_bfloat16*>(out_dev), (int)row_order, wsz);
-        else if (out_dtype == ZV_F16) zv::launch_pdl(k1_patchify_u8<__half>, dim3(blocks), dim3(256), 0, stream, 1, dpj, (int)n_pjobs, dlut, static_cast<__half*>(out_dev), (int)row_order, wsz);
-        else zv::launch_pdl(k1_patchify_u8<float>, dim3(blocks), dim3(256), 0, stream, 1, dpj, (int)n_pjobs, dlut, static_cast<float*>(out_dev), (int)row_order, wsz);
+        const int groups = (int)patch_blocks;
+        const unsigned blocks = (unsigned)std::min<int64_t>(patch_blocks, (int64_t)zv::num_sms() * 8);
+        if (out_dtype == ZV_BF16) zv::launch_pdl(k1_patchify_u8<__nv_bfloat16>, dim3(blocks), dim3(256), 0, stream, 1, dpj, (int)n_pjobs, groups, dlut, static_cast<__nv_bfloat16*>(out_dev), (int)row_order, wsz);
+        else if (out_dtype == ZV_F16) zv::launch_pdl(k1_patchify_u8<__half>, dim3(blocks), dim3(256), 0, stream, 1, dpj, (int)n_pjobs, groups, dlut, static_cast<__half*>(out_dev), (int)row_order, wsz);
+        else zv::launch_pdl(k1_patchify_u8<float>, dim3(blocks), dim3(256), 0, stream, 1, dpj, (int)n_pjobs, groups, dlut, static_cast<float*>(out_dev), (int)row_order, wsz);
         zv::count_launch();
       }
     }

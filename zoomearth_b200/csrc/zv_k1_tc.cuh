@@ -24,8 +24,9 @@
 // ((q' pitch) + offset) mod 16 with q' = row mod 4, so there is 1 variant when the pitch is a multiple of 16 (T always),
 // 2 for pitch = 8 mod 16 (a 5000-pixel row), 4 otherwise.
 //
-// 384 threads: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-3 = B builder (warp 2 owns the TMEM allocation),
-// warps 4-11 = epilogue (lane quarter = warp & 3, output bytes 16 (warp - 4) / 4 ..).  mbarrier pipelines: A ring
+// 640 threads: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-3 = B builder (warp 2 owns the TMEM allocation),
+// warps 4-19 = epilogue (lane quarter = warp & 3, output bytes 8 ((warp - 4) / 4) ..: four warps per scheduler hide the
+// TMEM round trips of one another).  mbarrier pipelines: A ring
 // full/empty (TMA <-> MMA), accumulator block full/empty per q (MMA <-> epilogue: block q of the next tile is
 // rewritten as soon as every epilogue warp has read it), B double buffer full/empty (builder <-> MMA).
 #pragma once
@@ -50,8 +51,10 @@ struct RJob {                 // one resample pass over one crop
   int32_t nvar;               // B variants (1, 2 or 4): distinct box-start slacks of the four row phases
 };
 
-constexpr int kTcThreads = 384;
 constexpr int kTcCols = 32;                 // output bytes per chunk
+constexpr int kTcEpiWarps = 16;             // four per TMEM lane quarter, 8 output bytes each
+constexpr int kTcEpiCols = kTcCols * 4 / kTcEpiWarps;
+constexpr int kTcThreads = 128 + 32 * kTcEpiWarps;
 constexpr int kTcN = 96;                    // 2 sub-tiles x 3 digits x 16 columns
 constexpr int kTcStageBytes = 128 * 128;    // one A K block: 128 rows x 128 bytes, 128B-swizzled
 constexpr int kTcBBlock = kTcN * 128;       // one B K block
@@ -94,6 +97,11 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64
 // both K-major, N >> 3 in [17,23), M >> 4 in [24,29).
 constexpr uint32_t kTcIdesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
+__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tc_fence_tensormap(const void* tmap) {
   asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmap) : "memory");
 }
@@ -127,7 +135,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k1_resample_tc(const RJob* __re
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-    for (int q = 0; q < 4; ++q) { mbar_init(dfull + q, 1); mbar_init(dempty + q, 8); }
+    for (int q = 0; q < 4; ++q) { mbar_init(dfull + q, 1); mbar_init(dempty + q, kTcEpiWarps); }
     for (int b = 0; b < 2; ++b) { mbar_init(bfull + b, 1); mbar_init(bempty + b, 1); }
     fence_mbar_init();
   }
@@ -254,36 +262,41 @@ __global__ void __launch_bounds__(kTcThreads, 1) k1_resample_tc(const RJob* __re
       if (tid == 0) mbar_arrive(bfull + buf);
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (8 warps)
-    const int lq = warp & 3, sub = (warp - 4) >> 2;
+    // ------------------------------------------------------------------ epilogue (16 warps)
+    constexpr int EC = kTcEpiCols;
+    const int lq = warp & 3, part = (warp - 4) >> 2;                 // TMEM lane quarter, column part
     const int m = lq * 32 + lane;
+    const int c0 = part * EC;                                        // first chunk column of this thread
+    const uint32_t tcol = (uint32_t)((c0 >> 4) * 48 + (c0 & 15));    // TMEM column of (c0, digit 0) within a q block
     uint32_t n_tile = 0;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
       const int4 item = __ldg(items + it);
       const RJob& j = jobs[item.x];
       const int n_bytes = j.n_out * j.ch;
-      const int jb0 = kTcCols * item.y + 16 * sub;                   // this thread's first output byte
+      const int jb0 = kTcCols * item.y + c0;                         // this thread's first output byte
       const int n_rows = j.n_rows;
-      uint8_t* const out0 = j.out + (int64_t)jb0 * j.out_pitch;
       const int64_t out_pitch = j.out_pitch;
+      uint8_t* const out0 = j.out + (int64_t)jb0 * out_pitch;
+      const bool cols_full = jb0 + EC <= n_bytes;
+      const bool word_ok = ((reinterpret_cast<uintptr_t>(j.out) | (uintptr_t)out_pitch) & 3) == 0;
       for (int t = item.z; t < item.z + item.w; ++t, ++n_tile) {
-        int v[3][16];
-        uint32_t word[16];
+        int v[3][EC];
+        uint32_t word[EC];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           mbar_wait(dfull + q, n_tile & 1);
           tc_fence_after();
-          const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(q * kTcN + sub * 48);
-          uint32_t a0[16], a1[16], a2[16];
-          tmem_ld_x16(taddr, a0);
-          tmem_ld_x16(taddr + 16, a1);
-          tmem_ld_x16(taddr + 32, a2);
+          const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(q * kTcN) + tcol;
+          uint32_t a0[EC], a1[EC], a2[EC];
+          tmem_ld_x8(taddr, a0);
+          tmem_ld_x8(taddr + 16, a1);
+          tmem_ld_x8(taddr + 32, a2);
           tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(dempty + q);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
+          for (int i = 0; i < EC; ++i) {
             const int r = finish_raw((int)a0[i], (int)a1[i], (int)a2[i]);
             if (q < 3) v[q][i] = r; else word[i] = pack4_sat(v[0][i], v[1][i], v[2][i], r);
           }
@@ -293,16 +306,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) k1_resample_tc(const RJob* __re
           uint8_t* o = out0 + row;
           // whole words when the four rows exist and the output rows are word-aligned (T and U always are; a caller's
           // zv_resize_u8 destination with an odd pitch is not), bytes otherwise
-          if (row + 3 < n_rows && ((reinterpret_cast<uintptr_t>(o) | (uintptr_t)out_pitch) & 3) == 0) {
+          if (cols_full && word_ok && row + 3 < n_rows) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (jb0 + i < n_bytes) *reinterpret_cast<uint32_t*>(o + i * out_pitch) = word[i];
+            for (int i = 0; i < EC; ++i, o += out_pitch) *reinterpret_cast<uint32_t*>(o) = word[i];
           } else {
             const int nb = min(4, n_rows - row);
+            const bool wide = word_ok && nb == 4;
+#pragma unroll 1
+            for (int i = 0; i < EC && jb0 + i < n_bytes; ++i, o += out_pitch) {
+              uint32_t wv = word[0];
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (jb0 + i < n_bytes)
-                for (int b = 0; b < nb; ++b) o[i * out_pitch + b] = (uint8_t)(word[i] >> (8 * b));
+              for (int k = 1; k < EC; ++k) wv = i == k ? word[k] : wv;
+              if (wide) *reinterpret_cast<uint32_t*>(o) = wv;
+              else for (int b = 0; b < nb; ++b) o[b] = (uint8_t)(wv >> (8 * b));
+            }
           }
         }
       }
@@ -318,42 +335,62 @@ __global__ void __launch_bounds__(kTcThreads, 1) k1_resample_tc(const RJob* __re
 struct PJob { const uint8_t* u; int64_t u_pitch; int64_t out_row0; int32_t lh, lw; int32_t blk0; int32_t pad_; };
 
 template <typename OutT>
-__global__ void __launch_bounds__(256) k1_patchify_u8(const PJob* __restrict__ jobs, int n_jobs, const float* __restrict__ lut,
+__global__ void __launch_bounds__(256) k1_patchify_u8(const PJob* __restrict__ jobs, int n_jobs, int n_groups, const float* __restrict__ lut,
                                                       OutT* __restrict__ out, int row_order, int wsz) {
-  __shared__ __align__(16) OutT stage[4 * kPatchElems];
+  // persistent: a block walks merge groups with a stride of gridDim.x; two staging buffers, one barrier per group.
+  // thread = (row phase ry = tid / 21 of 12, word w = tid % 21 of the group's 84-byte rows): its four (pixel, channel)
+  // columns, their LUT bases and patch offsets never change
+  __shared__ __align__(16) OutT stage[2][4 * kPatchElems];
   __shared__ float s_lut[768];
   for (int i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i] = lut[i];          // uploaded by a memcpy, not by a kernel
-  int lo = 0, hi = n_jobs - 1;
-  while (lo < hi) {
-    const int mid = (lo + hi + 1) >> 1;
-    if (jobs[mid].blk0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  const int tid = threadIdx.x;
+  const bool active = tid < 252;
+  const int ry = tid / 21, w = tid - ry * 21;
+  int eoff[4], lb[4];
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const int col = 4 * w + b;
+    const int xl = col / 3, ch = col - 3 * xl;
+    eoff[b] = (xl / 14) * kPatchElems + ch * 392 + (xl % 14);
+    lb[b] = ch * 256;
   }
-  const PJob j = jobs[lo];
-  const int g = blockIdx.x - j.blk0;
-  const int my = g / j.lw, mx = g - my * j.lw;
+  int roff[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { const int yl = ry + 12 * k; roff[k] = (yl / 14) * 2 * kPatchElems + (yl % 14) * 14; }
   zv::ptx::pdl_wait();
   __syncthreads();
-  const uint8_t* __restrict__ u = j.u + (int64_t)(my * 28) * j.u_pitch + mx * 84;
-  for (int item = threadIdx.x; item < 28 * 21; item += blockDim.x) {              // 28 rows x 21 words (84 bytes, 4-aligned)
-    const int yl = item / 21, w = item - yl * 21;
-    const uint32_t px = *reinterpret_cast<const uint32_t*>(u + (int64_t)yl * j.u_pitch + 4 * w);
-    const int rowoff = (yl / 14) * 2 * kPatchElems + (yl % 14) * 14;
+  int jn = 0, buf = 0;
+  for (int g = blockIdx.x; g < n_groups; g += gridDim.x, buf ^= 1) {
+    while (jn + 1 < n_jobs && __ldg(&jobs[jn + 1].blk0) <= g) ++jn;                // groups ascend: the job index only moves forward
+    const PJob& j = jobs[jn];
+    const int gl = g - j.blk0, lw = j.lw;
+    const int my = gl / lw, mx = gl - my * lw;
+    OutT* st = stage[buf];
+    if (active) {
+      const uint8_t* __restrict__ u = j.u + (int64_t)(my * 28 + ry) * j.u_pitch + mx * 84 + 4 * w;
+      const int64_t step = 12 * j.u_pitch;
+      uint32_t px[3];
+      px[0] = *reinterpret_cast<const uint32_t*>(u);
+      px[1] = *reinterpret_cast<const uint32_t*>(u + step);
+      px[2] = ry < 4 ? *reinterpret_cast<const uint32_t*>(u + 2 * step) : 0u;
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int col = 4 * w + b;
-      const int xl = col / 3, ch = col - 3 * xl;
-      const OutT o = to_out<OutT>(s_lut[ch * 256 + ((px >> (8 * b)) & 255)]);
-      const int e = rowoff + (xl / 14) * kPatchElems + ch * 392 + (xl % 14);
-      stage[e] = o;
-      stage[e + 196] = o;
+      for (int k = 0; k < 3; ++k) {
+        if (k == 2 && ry >= 4) break;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const OutT o = to_out<OutT>(s_lut[lb[b] + ((px[k] >> (8 * b)) & 255)]);
+          st[roff[k] + eoff[b]] = o;
+          st[roff[k] + eoff[b] + 196] = o;            // the repeated temporal frame
+        }
+      }
     }
+    __syncthreads();                                   // the group is staged (and the other buffer's copy-out of two groups ago is long done)
+    const int pos = row_order == ZV_ORDER_WINDOW ? window_pos(my, mx, j.lh, lw, wsz) : gl;
+    uint4* dst = reinterpret_cast<uint4*>(out + (j.out_row0 + 4 * (int64_t)pos) * kPatchElems);
+    const uint4* srcv = reinterpret_cast<const uint4*>(st);
+    constexpr int kVec = 4 * kPatchElems * (int)sizeof(OutT) / 16;
+    for (int i = tid; i < kVec; i += 256) dst[i] = srcv[i];
   }
-  __syncthreads();
-  const int pos = row_order == ZV_ORDER_WINDOW ? window_pos(my, mx, j.lh, j.lw, wsz) : g;
-  uint4* dst = reinterpret_cast<uint4*>(out + (j.out_row0 + 4 * (int64_t)pos) * kPatchElems);
-  const uint4* srcv = reinterpret_cast<const uint4*>(stage);
-  constexpr int kVec = 4 * kPatchElems * (int)sizeof(OutT) / 16;
-  for (int i = threadIdx.x; i < kVec; i += blockDim.x) dst[i] = srcv[i];
 }
 
 // ------------------------------------------------------------------------------------------------ host emulation
