@@ -334,29 +334,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) k1_resample_tc(const RJob* __re
 // (+ the repeated temporal frame) -> patch rows at their HF / window-order position.  One block = one 2x2 merge group.
 struct PJob { const uint8_t* u; int64_t u_pitch; int64_t out_row0; int32_t lh, lw; int32_t blk0; int32_t pad_; };
 
+// two neighbouring pixels of one channel -> one shared-memory store (element offset e is even)
+template <typename OutT> __device__ __forceinline__ void store_pair(OutT* st, int e, float a, float b) {
+  if constexpr (std::is_same<OutT, __nv_bfloat16>::value) *reinterpret_cast<__nv_bfloat162*>(st + e) = __floats2bfloat162_rn(a, b);
+  else if constexpr (std::is_same<OutT, __half>::value) *reinterpret_cast<__half2*>(st + e) = __floats2half2_rn(a, b);
+  else *reinterpret_cast<float2*>(st + e) = make_float2(a, b);
+}
+
 template <typename OutT>
 __global__ void __launch_bounds__(256) k1_patchify_u8(const PJob* __restrict__ jobs, int n_jobs, int n_groups, const float* __restrict__ lut,
                                                       OutT* __restrict__ out, int row_order, int wsz) {
   // persistent: a block walks merge groups with a stride of gridDim.x; two staging buffers, one barrier per group.
-  // thread = (row phase ry = tid / 21 of 12, word w = tid % 21 of the group's 84-byte rows): its four (pixel, channel)
-  // columns, their LUT bases and patch offsets never change
+  // thread = (row yl = tid / 7 of 28, segment sg = tid % 7 of the group's 84-byte rows): 12 bytes = 4 pixels x 3 channels
+  // -> per channel two pixel pairs, each one shared-memory store (+ one for the repeated temporal frame)
   __shared__ __align__(16) OutT stage[2][4 * kPatchElems];
   __shared__ float s_lut[768];
   for (int i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i] = lut[i];          // uploaded by a memcpy, not by a kernel
   const int tid = threadIdx.x;
-  const bool active = tid < 252;
-  const int ry = tid / 21, w = tid - ry * 21;
-  int eoff[4], lb[4];
-#pragma unroll
-  for (int b = 0; b < 4; ++b) {
-    const int col = 4 * w + b;
-    const int xl = col / 3, ch = col - 3 * xl;
-    eoff[b] = (xl / 14) * kPatchElems + ch * 392 + (xl % 14);
-    lb[b] = ch * 256;
-  }
-  int roff[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) { const int yl = ry + 12 * k; roff[k] = (yl / 14) * 2 * kPatchElems + (yl % 14) * 14; }
+  const bool active = tid < 196;
+  const int yl = tid / 7, sg = tid - yl * 7;
+  const int roff = (yl / 14) * 2 * kPatchElems + (yl % 14) * 14;
+  const int x0 = 4 * sg, x1 = 4 * sg + 2;
+  const int e0 = roff + (x0 / 14) * kPatchElems + (x0 % 14), e1 = roff + (x1 / 14) * kPatchElems + (x1 % 14);
   zv::ptx::pdl_wait();
   __syncthreads();
   int jn = 0, buf = 0;
@@ -367,22 +366,17 @@ __global__ void __launch_bounds__(256) k1_patchify_u8(const PJob* __restrict__ j
     const int my = gl / lw, mx = gl - my * lw;
     OutT* st = stage[buf];
     if (active) {
-      const uint8_t* __restrict__ u = j.u + (int64_t)(my * 28 + ry) * j.u_pitch + mx * 84 + 4 * w;
-      const int64_t step = 12 * j.u_pitch;
-      uint32_t px[3];
-      px[0] = *reinterpret_cast<const uint32_t*>(u);
-      px[1] = *reinterpret_cast<const uint32_t*>(u + step);
-      px[2] = ry < 4 ? *reinterpret_cast<const uint32_t*>(u + 2 * step) : 0u;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        if (k == 2 && ry >= 4) break;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const OutT o = to_out<OutT>(s_lut[lb[b] + ((px[k] >> (8 * b)) & 255)]);
-          st[roff[k] + eoff[b]] = o;
-          st[roff[k] + eoff[b] + 196] = o;            // the repeated temporal frame
-        }
-      }
+      const uint32_t* __restrict__ u = reinterpret_cast<const uint32_t*>(j.u + (int64_t)(my * 28 + yl) * j.u_pitch + mx * 84 + 12 * sg);
+      const uint32_t w0 = u[0], w1 = u[1], w2 = u[2];      // R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
+      const float r0 = s_lut[w0 & 255], r1 = s_lut[w0 >> 24], r2 = s_lut[(w1 >> 16) & 255], r3 = s_lut[(w2 >> 8) & 255];
+      const float g0 = s_lut[256 + ((w0 >> 8) & 255)], g1 = s_lut[256 + (w1 & 255)], g2 = s_lut[256 + (w1 >> 24)], g3 = s_lut[256 + ((w2 >> 16) & 255)];
+      const float b0 = s_lut[512 + ((w0 >> 16) & 255)], b1 = s_lut[512 + ((w1 >> 8) & 255)], b2 = s_lut[512 + (w2 & 255)], b3 = s_lut[512 + (w2 >> 24)];
+      store_pair(st, e0, r0, r1);             store_pair(st, e1, r2, r3);
+      store_pair(st, e0 + 196, r0, r1);       store_pair(st, e1 + 196, r2, r3);        // + 196: the repeated temporal frame
+      store_pair(st, e0 + 392, g0, g1);       store_pair(st, e1 + 392, g2, g3);
+      store_pair(st, e0 + 588, g0, g1);       store_pair(st, e1 + 588, g2, g3);
+      store_pair(st, e0 + 784, b0, b1);       store_pair(st, e1 + 784, b2, b3);
+      store_pair(st, e0 + 980, b0, b1);       store_pair(st, e1 + 980, b2, b3);
     }
     __syncthreads();                                   // the group is staged (and the other buffer's copy-out of two groups ago is long done)
     const int pos = row_order == ZV_ORDER_WINDOW ? window_pos(my, mx, j.lh, lw, wsz) : gl;
