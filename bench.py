@@ -487,7 +487,7 @@ def run_ours(args):
                          "traffic": traffic.get("gemm_bytes_per_launch") if n_img == 64 else None,
                          "traffic_note": traffic.get("gemm_note", "no ncu capture of this tree under profiles/ncu_traffic.json"),
                          "launches": gemm_n, "ms_total": gemm_ms, "share_of_step": gemm_ms / ms},
-            "roofline_k1": {"bound": "hbm", "kernel": "k1_hpass_mma (IMMA) + k1_vpass_fast (dp4a)", "achieved": k1_gbs, "peak": pk["hbm"],
+            "roofline_k1": {"bound": "hbm", "kernel": "k1_resample_tc x2 (tcgen05 kind::i8 + TMA: horizontal, vertical pass) + k1_patchify_u8", "achieved": k1_gbs, "peak": pk["hbm"],
                             "unit": "GB/s", "frac": k1_gbs / pk["hbm"], "ms_total": k1_ms, "share_of_step": k1_ms / ms,
                             "traffic": (traffic.get("k1_bytes_per_image") * n_img) if traffic.get("k1_bytes_per_image") else None,
                             "traffic_note": traffic.get("k1_note", "no ncu capture of this tree under profiles/ncu_traffic.json"),

@@ -55,8 +55,10 @@ def test_gemm_store_bf16_no_bias(cuda, lib):
     _close(out, a.float() @ b.float().t(), 6e-3)
 
 
-def test_gemm_residual(cuda, lib):
-    m, n, k = 700, 1280, 3456
+@pytest.mark.parametrize("m,k", [(700, 3456), (1296, 1280), (20000, 1280)])
+def test_gemm_residual(cuda, lib, m, k):
+    """small M takes the 128-wide residual tile (twice the CTA pairs in flight), large M the 256-wide one"""
+    n = 1280
     a, b, bias = _mk(m, n, k, cuda, seed=4)
     x0 = torch.randn(m, n, device=cuda)
     x = x0.clone()

@@ -21,13 +21,13 @@ for l in open('gpurun_out/configs_n1.jsonl'):
         d=json.loads(l); print({k:d[k] for k in d if k in ('config','tokens','value','tokens_per_s','ms','tower_tflops')})"
 python tools/latency.py > gpurun_out/latency.json 2> gpurun_out/latency.err
 if [ "${NCU:-1}" = "1" ]; then
-  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"gemm_tc|attn_|k1_|rmsnorm|gather|compose|cast_rows" -s 501 -c 167 --csv --log-file gpurun_out/launches.csv \
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"gemm_tc|attn_|k1_|rmsnorm|gather|compose|cast_rows" -s 504 -c 168 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --no-latency --no-sharded --images 8 > gpurun_out/ncu_list.log 2>&1; echo "ncu list exit $?"
   bash tools/gpu_ncu_traffic.sh
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:"gemm_tc" -s 133 -c 4 -o gpurun_out/prof_gemm -f python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --no-latency --no-sharded --images 8 > gpurun_out/ncu_gemm.log 2>&1; echo "ncu gemm exit $?"
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:"attn_tc_kernel" -s 4 -c 1 -o gpurun_out/prof_attn_tc -f python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --no-latency --no-sharded --images 8 > gpurun_out/ncu_attn.log 2>&1; echo "ncu attn_tc exit $?"
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:"attn_win_tc" -s 30 -c 1 -o gpurun_out/prof_attn_win_tc -f python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --no-latency --no-sharded --images 8 > gpurun_out/ncu_win.log 2>&1; echo "ncu attn_win exit $?"
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k1_" -s 6 -c 2 -o gpurun_out/prof_k1 -f python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --no-latency --no-sharded --images 8 > gpurun_out/ncu_k1.log 2>&1; echo "ncu k1 exit $?"
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k1_" -s 6 -c 3 -o gpurun_out/prof_k1 -f python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --no-latency --no-sharded --images 8 > gpurun_out/ncu_k1.log 2>&1; echo "ncu k1 exit $?"
 fi
 if [ "${SAN:-1}" = "1" ]; then
   timeout 1500 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_attn.py tests/test_gpu_gemm.py tests/test_gpu_handoff.py tests/test_gpu_k1.py tests/test_gpu_resize.py -q -m gpu -p no:cacheprovider -k "not 5000px" > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck exit $?"; grep -E "passed|failed|ERROR SUMMARY" gpurun_out/sanitizer_memcheck.log | tail -3

@@ -161,7 +161,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int m_blk, int n_b
         v += __shfl_xor_sync(0xffffffffu, v, 4);
         const int rw = 4 * i + rr;
         if ((lane & 7) == 0 && row_base + rw < g.M)
-          g.ss_out[(int64_t)(row_base + rw) * kSsParts + n_blk * (BN / 128) + half] = v;
+          g.ss_out[(int64_t)(row_base + rw) * kSsParts + (n_blk * BN + half * HALF) / 64] = v;
       }
     }
   } else if constexpr (EPI == EPI_STORE || EPI == EPI_GELU || EPI == EPI_SCATTER) {
@@ -673,7 +673,14 @@ int gemm(int epi, const GemmArgs& g, const void* a, int64_t lda, const void* b, 
       return g.N % 256 == 0 ? launch<256, EPI_STORE, 2>(g, a, lda, b, ldb, stream)
                             : launch<128, EPI_STORE, 1>(g, a, lda, b, ldb, stream);
     case EPI_QKV_ROPE: return launch<240, EPI_QKV_ROPE, 2>(g, a, lda, b, ldb, stream);
-    case EPI_RESID: return launch<256, EPI_RESID, 2>(g, a, lda, b, ldb, stream);
+    case EPI_RESID: {
+      // small batches (a single zoom crop: M = 1296): N = 1280 gives 5 column tiles of 256, i.e. 30 CTA pairs of work for
+      // 74 pair slots.  128-wide tiles double the parallelism; taken when they cut the wave count x tile width by >= 20 %.
+      const int64_t slots = num_sms() / 2, mp = (g.M + 2 * BM - 1) / (2 * BM);
+      const int64_t cost256 = 2 * ((mp * (g.N / 256) + slots - 1) / slots), cost128 = (mp * (g.N / 128) + slots - 1) / slots;
+      if (g.N % 256 == 0 && 5 * cost128 > 4 * cost256) return launch<256, EPI_RESID, 2>(g, a, lda, b, ldb, stream);
+      return launch<128, EPI_RESID, 2>(g, a, lda, b, ldb, stream);
+    }
     case EPI_SWIGLU: return launch<256, EPI_SWIGLU, 2>(g, a, lda, b, ldb, stream);
     case EPI_GELU: return launch<256, EPI_GELU, 2>(g, a, lda, b, ldb, stream);
     case EPI_SCATTER: return launch<256, EPI_SCATTER, 2>(g, a, lda, b, ldb, stream);

@@ -54,7 +54,7 @@ struct GemmArgs {
   int64_t peer_row_off;
   // RMSNorm folded into the GEMMs around it (the norm gain is folded into the consumer's weight columns at pack time):
   //   producer (EPI_RESID, N = hidden): besides X += ..., writes the new rows once more as 16-bit operands to `x16_out`
-  //     (row pitch N) and, per row, kSsParts partial sums of squares to `ss_out` [M][kSsParts] (one per 128 columns);
+  //     (row pitch N) and, per row, partial sums of squares to `ss_out` [M][kSsParts] (slot = first column / 64 of each tile half);
   //   consumer (EPI_QKV_ROPE, EPI_SWIGLU): `row_ss` [M][kSsParts] of its A rows -> every accumulator row is scaled by
   //     rsqrt(sum / norm_dim + norm_eps) before the bias is added:  (x / rms) W'^T = (x W'^T) / rms.
   void* x16_out;
@@ -63,7 +63,7 @@ struct GemmArgs {
   float norm_eps;
   int norm_dim;
 };
-constexpr int kSsParts = 10;   // hidden 1280 = 10 x 128 columns
+constexpr int kSsParts = 20;   // hidden 1280 = 20 x 64 columns (a 256-wide residual tile fills every other one, a 128-wide tile all)
 
 // C = A[M,K] * B[N,K]^T with the chosen epilogue, enqueued on `stream`.
 int gemm(int epi, const GemmArgs& g, const void* a, int64_t lda, const void* b, int64_t ldb, void* stream);
