@@ -1,6 +1,7 @@
 #!/bin/bash
 # Round-2 evidence run on one B200 at HEAD: every GPU test file (own process each), smoke, the full bench line, the ragged
-# configs, ncu launch list + traffic + full captures of the dominant kernels, compute-sanitizer.  Outputs under gpurun_out/.
+# configs, ncu launch list + traffic + full captures of the dominant kernels (FULL=k1: of the K1 kernels only),
+# compute-sanitizer (SAN_TESTS: test files).  Outputs under gpurun_out/.
 mkdir -p gpurun_out
 rc=0
 for f in tests/test_gpu_gemm.py tests/test_gpu_k1.py tests/test_gpu_attn.py tests/test_gpu_tower.py tests/test_gpu_configs.py tests/test_gpu_handoff.py tests/test_gpu_resize.py tests/test_gpu_ingest_plugin.py; do
@@ -24,12 +25,14 @@ if [ "${NCU:-1}" = "1" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"gemm_tc|attn_|k1_|rmsnorm|gather|compose|cast_rows" -s 504 -c 168 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --no-latency --no-sharded --images 8 > gpurun_out/ncu_list.log 2>&1; echo "ncu list exit $?"
   bash tools/gpu_ncu_traffic.sh
+  if [ "${FULL:-all}" = "all" ]; then
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:"gemm_tc" -s 133 -c 4 -o gpurun_out/prof_gemm -f python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --no-latency --no-sharded --images 8 > gpurun_out/ncu_gemm.log 2>&1; echo "ncu gemm exit $?"
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:"attn_tc_kernel" -s 4 -c 1 -o gpurun_out/prof_attn_tc -f python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --no-latency --no-sharded --images 8 > gpurun_out/ncu_attn.log 2>&1; echo "ncu attn_tc exit $?"
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:"attn_win_tc" -s 30 -c 1 -o gpurun_out/prof_attn_win_tc -f python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --no-latency --no-sharded --images 8 > gpurun_out/ncu_win.log 2>&1; echo "ncu attn_win exit $?"
+  fi
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k1_" -s 6 -c 3 -o gpurun_out/prof_k1 -f python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --no-latency --no-sharded --images 8 > gpurun_out/ncu_k1.log 2>&1; echo "ncu k1 exit $?"
 fi
 if [ "${SAN:-1}" = "1" ]; then
-  timeout 1500 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_attn.py tests/test_gpu_gemm.py tests/test_gpu_handoff.py tests/test_gpu_k1.py tests/test_gpu_resize.py -q -m gpu -p no:cacheprovider -k "not 5000px" > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck exit $?"; grep -E "passed|failed|ERROR SUMMARY" gpurun_out/sanitizer_memcheck.log | tail -3
+  timeout 1500 compute-sanitizer --tool memcheck python -m pytest ${SAN_TESTS:-tests/test_gpu_attn.py tests/test_gpu_gemm.py tests/test_gpu_handoff.py tests/test_gpu_k1.py tests/test_gpu_resize.py} -q -m gpu -p no:cacheprovider -k "not 5000px" > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck exit $?"; grep -E "passed|failed|ERROR SUMMARY" gpurun_out/sanitizer_memcheck.log | tail -3
 fi
 exit $rc
