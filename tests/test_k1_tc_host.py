@@ -110,3 +110,29 @@ def test_tc_route_takes_unaligned_views():
     assert took.tolist() == [1, 1]
     assert np.array_equal(outs[0], OR.resize_u8(np.ascontiguousarray(view), 452, 400))
     assert np.array_equal(outs[1], OR.resize_u8(OR.crop_u8(np.ascontiguousarray(view), (7, 9, 507, 409)), 313, 250))
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_tc_route_random_geometries(seed):
+    """random image sizes / pitches / boxes / scales (4x upscale .. 9x downscale), uint8 output of any size: whatever the
+    route accepts must be bit-identical to the oracle; what it declines is a crop it cannot express (border, odd pitch)"""
+    rng = np.random.default_rng(100 + seed)
+    took_any = 0
+    for _ in range(10):
+        h, w = int(rng.integers(40, 420)), int(rng.integers(10, 90)) * 4
+        img = _aligned(_img(int(rng.integers(1 << 30)), h, w))
+        boxes, out_hw = [], []
+        for _ in range(3):
+            bw, bh = int(rng.integers(12, w + 1)), int(rng.integers(12, h + 1))
+            x0, y0 = int(rng.integers(0, w - bw + 1)), int(rng.integers(0, h - bh + 1))
+            boxes.append((x0, y0, x0 + bw, y0 + bh))
+            s = float(rng.uniform(0.25, 9.0))
+            out_hw.append((max(3, int(bh / s)), max(3, int(bw / s))))
+        outs, took = _run([img], [0, 0, 0], boxes, out_hw, patches=False)
+        for o, b, t, (oh, ow) in zip(outs, boxes, took, out_hw):
+            if t:
+                took_any += 1
+                assert np.array_equal(o, OR.resize_u8(OR.crop_u8(img, b), ow, oh)), (h, w, b, oh, ow)
+            else:
+                assert b[3] > (h // 4) * 4 or max((b[2] - b[0]) / ow, (b[3] - b[1]) / oh) > 4.0, (h, w, b, oh, ow)
+    assert took_any >= 15
