@@ -70,8 +70,8 @@ def main():
                             f"(QKV, proj, SwiGLU, down) at {args.images} images, ncu at commit {commit} "
                             f"({', '.join(out['sources'])})")
     if k1:
-        # one launch of each K1 kernel covers the whole batch
-        out["k1_bytes_per_image"] = sum(v["dram_bytes_per_launch"] for v in k1) / args.images
+        # the captured K1 launches of one step together cover the whole batch (two passes of k1_resample_tc + the patchify)
+        out["k1_bytes_per_image"] = sum(v["dram_bytes_per_launch"] * v["launches"] for v in k1) / args.images
         out["k1_note"] = (f"DRAM bytes (read + write) of the K1 launches of one step / {args.images} images, ncu at commit "
                           f"{commit}; algorithmic 86.52 MB per image")
     json.dump(out, open(args.out, "w"), indent=1)

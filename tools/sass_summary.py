@@ -16,7 +16,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "zoomearth_b200", "libzoomvit.so")
 PAT = collections.OrderedDict([
-    ("UTCHMMA", r"\bUTCHMMA"), ("UTCHMMA.2CTA", r"\bUTCHMMA\.2CTA"), ("LDTM", r"\bLDTM"), ("STTM", r"\bSTTM"),
+    ("UTCHMMA", r"\bUTCHMMA"), ("UTCHMMA.2CTA", r"\bUTCHMMA\.2CTA"), ("UTCIMMA", r"\bUTCIMMA"), ("LDTM", r"\bLDTM"), ("STTM", r"\bSTTM"),
     ("UTMALDG", r"\bUTMALDG"), ("UTMALDG.MULTICAST", r"\bUTMALDG\S*MULTICAST"), ("UTMASTG", r"\bUTMASTG"), ("UBLKCP", r"\bUBLKCP"),
     ("SYNCS(mbarrier)", r"\bSYNCS"), ("HMMA", r"\bHMMA"), ("IMMA", r"\bIMMA"), ("IDP.4A", r"\bIDP\.4A"), ("LDGSTS", r"\bLDGSTS"), ("MUFU.EX2", r"\bMUFU\.EX2"),
     ("ST.E(peer/global)", r"\bST\.E|\bSTG")])
