@@ -12,7 +12,12 @@
 // Integer arithmetic only, bit-identical to Pillow: 22-bit fixed-point taps computed on the host in fp64
 // (zv_host.cpp), int32 sums.
 //
-// Fast path (taps <= 37 per axis, 4-byte aligned image rows): the work is instruction-bound on the integer pipes
+// Main route (zv_k1_tc.cuh; crops inside the image, row pitch a multiple of 4): both passes run as ONE transposing
+// tcgen05 kernel (TMA -> kind::i8 UMMA -> TMEM epilogue), source -> T (transposed) -> U (the finished uint8 image), and a
+// small kernel turns U into normalised patches.  The kernels below serve what that route declines: boxes that leave the
+// image (zero fill), odd pitches, more than 45 taps per axis.
+//
+// Fallback fast path (taps <= 45 per axis, 4-byte aligned image rows): the work is instruction-bound on the integer pipes
 // (4 multiply-adds per source byte), so both passes run on dp4a.  Each 23-bit tap is split into three byte limbs
 // (k = l0 + 256 l1 + 65536 l2, l2 signed); the host emits, per output index, a word-aligned tap window whose limb
 // bytes are packed four taps to a word, so one dp4a does four taps of one limb and no per-thread realignment of the
