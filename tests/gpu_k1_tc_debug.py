@@ -1,7 +1,8 @@
-"""GPU diagnosis of K1's tensor-core route: a few crops through zv_resize_u8 / zv_preprocess against the oracle, with the
+"""(not a pytest file; lives under tests/ because it uses the oracle as its checker)
+GPU diagnosis of K1's tensor-core route: a few crops through zv_resize_u8 / zv_preprocess against the oracle, with the
 mismatches broken down by position so that a layout error (swizzle, lane mapping, digit order) shows its signature.
 
-    python tools/k1_tc_debug.py [--bench N]    # --bench: also time zv_preprocess alone on N 5000x5000 images
+    python tests/gpu_k1_tc_debug.py [--bench N]    # --bench: also time zv_preprocess alone on N 5000x5000 images
 """
 import argparse
 import ctypes as C
@@ -12,7 +13,7 @@ import sys
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # repo root
 from oracle import processor as OP, resample as OR   # noqa: E402  (checker only)
 from zoomearth_b200 import FusedImageProcessor, _lib   # noqa: E402
 

@@ -282,22 +282,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) k1_resample_tc(const RJob* __re
       for (int t = item.z; t < item.z + item.w; ++t, ++n_tile) {
         int v[3][EC];
         uint32_t word[EC];
+        // software pipeline over the four accumulator blocks: the TMEM loads of block q + 1 are in flight while block q's
+        // digit sums are folded (two register sets, statically alternated)
+        uint32_t acc[2][3][EC];
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(lq * 32) << 16) + tcol;
+        mbar_wait(dfull + 0, n_tile & 1);
+        tc_fence_after();
+        tmem_ld_x8(taddr0, acc[0][0]);
+        tmem_ld_x8(taddr0 + 16, acc[0][1]);
+        tmem_ld_x8(taddr0 + 32, acc[0][2]);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          mbar_wait(dfull + q, n_tile & 1);
-          tc_fence_after();
-          const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(q * kTcN) + tcol;
-          uint32_t a0[EC], a1[EC], a2[EC];
-          tmem_ld_x8(taddr, a0);
-          tmem_ld_x8(taddr + 16, a1);
-          tmem_ld_x8(taddr + 32, a2);
-          tmem_ld_wait();
+          tmem_ld_wait();                                            // block q is in registers
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(dempty + q);
+          if (q < 3) {
+            mbar_wait(dfull + q + 1, n_tile & 1);
+            tc_fence_after();
+            const uint32_t ta = taddr0 + (uint32_t)((q + 1) * kTcN);
+            tmem_ld_x8(ta, acc[(q + 1) & 1][0]);
+            tmem_ld_x8(ta + 16, acc[(q + 1) & 1][1]);
+            tmem_ld_x8(ta + 32, acc[(q + 1) & 1][2]);
+          }
 #pragma unroll
           for (int i = 0; i < EC; ++i) {
-            const int r = finish_raw((int)a0[i], (int)a1[i], (int)a2[i]);
+            const int r = finish_raw((int)acc[q & 1][0][i], (int)acc[q & 1][1][i], (int)acc[q & 1][2][i]);
             if (q < 3) v[q][i] = r; else word[i] = pack4_sat(v[0][i], v[1][i], v[2][i], r);
           }
         }
