@@ -66,7 +66,10 @@ constexpr int kTcMaxBBlocks = 8;            // variants x K blocks of one B buff
 __host__ __device__ constexpr int tc_smem_bytes(int stages, int b_blocks) {
   return 1024 + stages * kTcStageBytes + b_blocks * kTcBBlock + kTcBarBytes;
 }
-inline int tc_b_buffers(int nvar, int nkb) { return nvar * nkb <= kTcMaxBBlocks / 2 ? 2 : 1; }   // double-buffered while it fits 96 KB
+// Two B buffers only while they cost no A stage worth having: the pipeline is bound by the bytes the TMA ring keeps in
+// flight (ncu: DRAM 55-64 %, L2 49 %, tensor pipe 46 % busy, nothing saturated with 8 stages), and the builder holds an
+// item's taps in registers before it waits for the buffer, so a single buffer stalls the tensor core for ~1 000 clocks per item.
+inline int tc_b_buffers(int nvar, int nkb) { return nvar * nkb <= 2 ? 2 : 1; }
 inline int tc_stages(int b_blocks) {        // as many A stages as fit beside B (<= 12)
   const int room = 227 * 1024 - tc_smem_bytes(0, b_blocks);
   return std::min(12, room / kTcStageBytes);
@@ -212,36 +215,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) k1_resample_tc(const RJob* __re
     }
   } else if (warp < 4) {
     // ------------------------------------------------------------------ B builder (64 threads)
+    // The taps of an item are fetched into registers BEFORE the wait for the buffer (they do not depend on it), so that with
+    // a single B buffer the tensor core only waits for the zero fill + scatter, not for a global-memory round trip.
     const int tid = threadIdx.x - 64;
+    constexpr int kHold = 12;                                        // (column, tap) pairs a thread holds: 32 x 23 taps / 64 threads
     uint32_t n_item = 0;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++n_item) {
       const int4 item = __ldg(items + it);
       const RJob& j = jobs[item.x];
       const uint32_t buf = n_item % (uint32_t)nbuf;
-      mbar_wait(bempty + buf, ((n_item / (uint32_t)nbuf) & 1) ^ 1);
       uint8_t* B = sB + buf * b_buf_bytes;
-      const int nkb = j.nkb, ch = j.ch, ksize = j.ksize, nvar = j.nvar;
-      for (int v = 0; v < nvar; ++v) {
-        uint4* z = reinterpret_cast<uint4*>(B + v * nkb_max * kTcBBlock);
-        const int n16 = nkb * kTcBBlock / 16;
-        for (int i = tid; i < n16; i += 64) z[i] = make_uint4(0u, 0u, 0u, 0u);
-      }
-      asm volatile("bar.sync 1, 64;" ::: "memory");
+      const int nkb = j.nkb, ch = j.ch, ksize = j.ksize, nvar = j.nvar, origin = j.origin;
       const int wb0 = tc_chunk_wb0(j, coef, item.y);
       int slack[4];
 #pragma unroll
       for (int v = 0; v < 4; ++v) slack[v] = tc_slack(j, wb0, v);
-      const int n_bytes = j.n_out * ch;
-      for (int idx = tid; idx < kTcCols * ksize; idx += 64) {
-        const int c = idx / ksize, t = idx - c * ksize;
-        const int jb = kTcCols * item.y + c;                         // output byte
-        if (jb >= n_bytes) continue;
-        const int o = jb / ch, cc = jb - o * ch;
-        const int xmin = __ldg(coef + j.off_b + 2 * o), cnt = __ldg(coef + j.off_b + 2 * o + 1);
-        if (t >= cnt) continue;
+      const int n_bytes = j.n_out * ch, total = kTcCols * ksize;
+      const int32_t* __restrict__ cb = coef + j.off_b;
+      const int32_t* __restrict__ ck = coef + j.off_k;
+      // (column c, tap t) of pair idx -> output sample o, channel cc; false when the column is past the row's end
+      auto locate = [&](int idx, int& c, int& t, int& o, int& cc) -> bool {
+        c = idx / ksize; t = idx - c * ksize;
+        const int jb = kTcCols * item.y + c;
+        o = jb / ch; cc = jb - o * ch;
+        return idx < total && jb < n_bytes;
+      };
+      auto scatter = [&](int c, int t, int cc, int xmin, int cnt, int k) {
+        if (t >= cnt) return;
         int dg[3];
-        tc_digits(__ldg(coef + j.off_k + (int64_t)o * ksize + t), dg);
-        const int kwin = ch * (xmin - j.origin + t) + cc - wb0;       // input byte of this tap, from the window's first byte
+        tc_digits(k, dg);
+        const int kwin = ch * (xmin - origin + t) + cc - wb0;         // input byte of this tap, from the window's first byte
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
           if (v >= nvar) break;
@@ -249,13 +252,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) k1_resample_tc(const RJob* __re
           if (kbyte < 0 || kbyte >= 128 * nkb) continue;             // (never: the host sized nkb from the same tables)
           const int kb = kbyte >> 7, kin = kbyte & 127;
           uint8_t* blk = B + (v * nkb_max + kb) * kTcBBlock + (kin & 15);
-          const int ck = kin >> 4;
+          const int ckk = kin >> 4;
 #pragma unroll
           for (int l = 0; l < 3; ++l) {
             const int n = tc_b_row(c, l);
-            blk[(n >> 3) * 1024 + (n & 7) * 128 + ((ck ^ (n & 7)) << 4)] = (uint8_t)dg[l];   // 128B-swizzled K-major row
+            blk[(n >> 3) * 1024 + (n & 7) * 128 + ((ckk ^ (n & 7)) << 4)] = (uint8_t)dg[l];  // 128B-swizzled K-major row
           }
         }
+      };
+      int hx[kHold], hc[kHold], hk[kHold];
+#pragma unroll
+      for (int r = 0; r < kHold; ++r) {
+        int c, t, o, cc;
+        hx[r] = 0; hc[r] = 0; hk[r] = 0;
+        if (locate(tid + 64 * r, c, t, o, cc)) { hx[r] = __ldg(cb + 2 * o); hc[r] = __ldg(cb + 2 * o + 1); hk[r] = __ldg(ck + (int64_t)o * ksize + t); }
+      }
+      mbar_wait(bempty + buf, ((n_item / (uint32_t)nbuf) & 1) ^ 1);
+      for (int v = 0; v < nvar; ++v) {
+        uint4* z = reinterpret_cast<uint4*>(B + v * nkb_max * kTcBBlock);
+        const int n16 = nkb * kTcBBlock / 16;
+        for (int i = tid; i < n16; i += 64) z[i] = make_uint4(0u, 0u, 0u, 0u);
+      }
+      asm volatile("bar.sync 1, 64;" ::: "memory");
+#pragma unroll
+      for (int r = 0; r < kHold; ++r) {
+        int c, t, o, cc;
+        if (locate(tid + 64 * r, c, t, o, cc)) scatter(c, t, cc, hx[r], hc[r], hk[r]);
+      }
+      for (int idx = tid + 64 * kHold; idx < total; idx += 64) {     // more than 24 taps per column: the rest, fetched now
+        int c, t, o, cc;
+        if (locate(idx, c, t, o, cc)) scatter(c, t, cc, __ldg(cb + 2 * o), __ldg(cb + 2 * o + 1), __ldg(ck + (int64_t)o * ksize + t));
       }
       tc_fence_proxy_async();              // generic-proxy stores -> visible to the tensor core
       asm volatile("bar.sync 1, 64;" ::: "memory");
