@@ -66,10 +66,11 @@ constexpr int kTcMaxBBlocks = 8;            // variants x K blocks of one B buff
 __host__ __device__ constexpr int tc_smem_bytes(int stages, int b_blocks) {
   return 1024 + stages * kTcStageBytes + b_blocks * kTcBBlock + kTcBarBytes;
 }
-// Two B buffers only while they cost no A stage worth having: the pipeline is bound by the bytes the TMA ring keeps in
-// flight (ncu: DRAM 55-64 %, L2 49 %, tensor pipe 46 % busy, nothing saturated with 8 stages), and the builder holds an
-// item's taps in registers before it waits for the buffer, so a single buffer stalls the tensor core for ~1 000 clocks per item.
-inline int tc_b_buffers(int nvar, int nkb) { return nvar * nkb <= 2 ? 2 : 1; }
+// Two B buffers while both fit 96 KB.  (Measured: trading the second buffer for three more A stages - 8 -> 11 - changes
+// nothing, 1.02 -> 1.08 ms for pass 1 of 64 images: the pipeline is not short of bytes in flight.  Alone it runs at the
+// HBM rate, 5.9 TB/s; under the step's power-capped clock it is bound by the TMA unit's request rate: ~2.6 L2 requests per
+// 128-byte box row that starts on a 16-byte boundary, ~590 SM clocks per 16 KB box at either clock.)
+inline int tc_b_buffers(int nvar, int nkb) { return nvar * nkb <= kTcMaxBBlocks / 2 ? 2 : 1; }
 inline int tc_stages(int b_blocks) {        // as many A stages as fit beside B (<= 12)
   const int room = 227 * 1024 - tc_smem_bytes(0, b_blocks);
   return std::min(12, room / kTcStageBytes);
