@@ -4,12 +4,18 @@
 # compute-sanitizer (SAN_TESTS: test files).  Outputs under gpurun_out/.
 mkdir -p gpurun_out
 rc=0
+if [ "${TESTS:-files}" = "single" ]; then
+  # exactly what the driver runs at round end: every GPU test in ONE process
+  timeout 1500 python -m pytest tests/ -x -q -s -m gpu -p no:cacheprovider > gpurun_out/test_gpu_all.log 2>&1
+  r=$?; echo "== pytest tests/ -m gpu (one process) exit $r: $(grep -E 'passed|failed' gpurun_out/test_gpu_all.log | tail -n 1)"; [ $r -ne 0 ] && { rc=1; grep -E "^(FAILED|ERROR)|^E " gpurun_out/test_gpu_all.log | head -20; }
+else
 for f in tests/test_gpu_gemm.py tests/test_gpu_k1.py tests/test_gpu_attn.py tests/test_gpu_tower.py tests/test_gpu_configs.py tests/test_gpu_handoff.py tests/test_gpu_resize.py tests/test_gpu_ingest_plugin.py; do
   n=$(basename $f .py)
   timeout 900 python -m pytest $f -q -s -m gpu --timeout 600 -p no:cacheprovider > gpurun_out/$n.log 2>&1
   r=$?; echo "== $f exit $r: $(grep -E 'passed|failed' gpurun_out/$n.log | tail -n 1)"; [ $r -ne 0 ] && { rc=1; grep -E "^(FAILED|ERROR)|^E " gpurun_out/$n.log | head -20; }
 done
-grep -h PARITY gpurun_out/test_gpu_*.log > gpurun_out/parity.txt; wc -l gpurun_out/parity.txt
+fi
+grep -h PARITY gpurun_out/test_gpu_*.log | sed 's/^[.sx]*//' > gpurun_out/parity.txt; wc -l gpurun_out/parity.txt
 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit $?"; tail -1 gpurun_out/smoke.log
 timeout 1200 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"; tail -3 gpurun_out/bench.err
 python -c "
