@@ -20,6 +20,8 @@ SOURCES = ["zv_host.cpp", "zv_handoff.cpp", "zv_k1.cu", "zv_gemm.cu", "zv_attn.c
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-I", INCLUDE, "-I", CSRC,
           "-Xcompiler", "-fPIC,-fvisibility=hidden,-ffp-contract=off,-Wall,-Wno-unused-function"]
+# build-time only: extra nvcc flags for the compile-time debug variants (e.g. ZV_NVCC_EXTRA="-DZV_DEBUG_K1_NO_TC" for an A/B run)
+COMMON += os.environ.get("ZV_NVCC_EXTRA", "").split()
 
 
 def _deps():
