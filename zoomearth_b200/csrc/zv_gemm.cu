@@ -119,15 +119,6 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int m_blk, int n_b
     float ssp[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) ssp[i] = 0.f;
-    // the whole residual row segment of this thread's accumulator row (HALF fp32 values) is requested into L2 at once:
-    // the chunk-by-chunk loads below keep only 4 KB per warp in flight, which leaves the read-modify-write of X bound by
-    // DRAM latency (proj: 4.3 TB/s); the prefetch turns every chunk after the first into an L2 hit
-#ifndef ZV_DEBUG_NO_RESID_PREFETCH      // compile-time debug build for A/B runs
-    if (valid) {
-      const float* xp = static_cast<const float*>(g.out) + (int64_t)row * g.ldo + n_blk * BN + half * HALF;
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(xp), "r"(HALF * 4) : "memory");
-    }
-#endif
     load_x(0);
     wait_accumulator();
 #pragma unroll 1
