@@ -136,3 +136,18 @@ def test_tc_route_random_geometries(seed):
             else:
                 assert b[3] > (h // 4) * 4 or max((b[2] - b[0]) / ow, (b[3] - b[1]) / oh) > 4.0, (h, w, b, oh, ow)
     assert took_any >= 15
+
+
+def test_tc_route_window_order_rows():
+    """row_order = window: merge groups land at the tower's window position (closed form of argsort(window_index))"""
+    from oracle import tower as OT
+    img = _aligned(_img(9, 700, 1000))
+    box, ohw = (20, 40, 980, 680), (392, 588)                  # grid 28 x 42: 3.5 x 5.25 windows of 4 x 4 merge groups
+    got, took = _run([img], [0], [box], [ohw], patches=True, row_order=_lib.ORDER_WINDOW)
+    assert took.tolist() == [1]
+    r = OR.resize_u8(OR.crop_u8(img, box), ohw[1], ohw[0])
+    lut = OP.normalize_lut()
+    ref, grid = OP.patchify(np.stack([lut[c][r[:, :, c]] for c in range(3)], 0))
+    widx, _ = OT.window_index(np.asarray(grid).reshape(1, 3))
+    ref_w = ref.reshape(-1, 4, 1176)[np.asarray(widx)].reshape(-1, 1176)
+    assert np.array_equal(got, ref_w)
