@@ -733,7 +733,7 @@ inline int32_t mma_ksteps(int32_t in_size, int32_t out_size, int32_t ksize) {
 }
 struct Layout {
   int64_t off_desc = 0, off_lut = 0, off_coef = 0, off_lists = 0, off_tmp = 0, bytes = 0;
-  int64_t off_tmaps = 0, off_jobs = 0, off_pjobs = 0;     // tensor-core route: 2 tensor maps, 2 RJob and 1 PJob per crop
+  int64_t off_tmaps = 0, off_jobs = 0, off_pjobs = 0;     // tensor-core route: 3 tensor maps, 3 RJob and 1 PJob per crop
   std::vector<int64_t> u_off;                // per crop, relative to off_tmp: the finished uint8 image (zv_preprocess only)
   std::vector<int64_t> t_pitch;              // per crop: bytes per row of the transposed intermediate T
   int64_t item_cap_tc = 0;
@@ -919,7 +919,7 @@ int build_layout(int32_t n, const int32_t* crop_box, const int32_t* resized_hw, 
       tmp_bytes += align_up((int64_t)oh * ow * 3, 256);
     }
     const int64_t tiles1 = ((y_last + 3) / 4 - y_first / 4 + 127) / 128, tiles2 = ((3 * (int64_t)ow + 3) / 4 + 127) / 128;
-    L->item_cap_tc += ((3 * (int64_t)ow + kTcCols - 1) / kTcCols) * tiles1 + (((int64_t)oh + kTcCols - 1) / kTcCols) * tiles2;
+    L->item_cap_tc += ((3 * (int64_t)ow + kTcCols - 1) / kTcCols) * (tiles1 + 1) + (((int64_t)oh + kTcCols - 1) / kTcCols) * tiles2;   // + 1: the tail tile
   }
   // work-list sizing (geometry only, so that the workspace size does not depend on the tables)
   int64_t units_h = 0, units_v = 0;
@@ -947,8 +947,8 @@ int build_layout(int32_t n, const int32_t* crop_box, const int32_t* resized_hw, 
   // work lists of the fast kernels (int4 items) first, then, for the per-tap kernels, crop ids + block prefix per pass
   L->list_ints = 4 * (L->item_cap_h + L->item_cap_v + L->item_cap_tc) + 4 * ((int64_t)n + 16);
   L->off_lists = off; off = align_up(off + L->list_ints * (int64_t)sizeof(int32_t), 256);
-  L->off_tmaps = off; off = align_up(off + 2 * (int64_t)n * (int64_t)sizeof(CUtensorMap), 256);
-  L->off_jobs = off; off = align_up(off + 2 * (int64_t)n * (int64_t)sizeof(RJob), 256);
+  L->off_tmaps = off; off = align_up(off + 3 * (int64_t)n * (int64_t)sizeof(CUtensorMap), 256);
+  L->off_jobs = off; off = align_up(off + 3 * (int64_t)n * (int64_t)sizeof(RJob), 256);
   L->off_pjobs = off; off = align_up(off + (int64_t)n * (int64_t)sizeof(PJob), 256);
   L->off_tmp = off; off += tmp_bytes;
   L->bytes = off;
@@ -1009,6 +1009,19 @@ void launch_vpass(int nw, int count, cudaStream_t s, const K1Crop* d, const int3
     case 10: launch_vfast<10, OutT>(count, s, d, items, coef, ws, lut, out, row_order, wsz, tile_quads); break;
     default: launch_vfast<12, OutT>(count, s, d, items, coef, ws, lut, out, row_order, wsz, tile_quads); break;
   }
+}
+
+// Tensor-core route, pass 1: the image is read through super-rows of four rows counted from row 0, which cover rows
+// [0, 4 floor(H / 4)).  A crop that also needs the last H mod 4 rows gets a second job for its last row quads, read
+// through a tensor map whose super-rows are counted from row H mod 4 (so that they end with the image).  -> quads of the
+// first job, first image row of the second (rows_end when there is none); false when the split is impossible.
+inline bool tc_split_rows(int64_t row0, int64_t nrows, int64_t y_hi, int32_t src_h, int64_t* nq_a, int64_t* r_b) {
+  const int64_t nq = (nrows + 3) / 4, limit = (int64_t)(src_h / 4) * 4;
+  if (y_hi <= limit) { *nq_a = nq; *r_b = row0 + 4 * nq; return true; }
+  const int64_t k = row0 >= limit ? 0 : (limit - row0) / 4;
+  *nq_a = std::min(nq, k);
+  *r_b = row0 + 4 * *nq_a;
+  return *r_b >= (src_h & 3);
 }
 
 // Both device entry points: the two resample passes over n crops.  u8_dst == nullptr: patches (LUT + patchify) into out_dev;
@@ -1076,14 +1089,19 @@ int k1_run(const char* who, const zv_cfg* cfg, int32_t n, const uint8_t* const* 
     tq_v[i] = v.tile_quads;
     c.ybox0 = L.ybox0[i]; c.nrows = L.nrows[i];
     // Tensor-core route (k1_resample_tc): the crop lies inside the image (no zero fill needed), the row pitch is a
-    // multiple of 4 bytes (four image rows = one TMA row with a 16-byte-multiple stride), every row the pass reads lies in
-    // a complete group of four image rows, and a 32-byte chunk of either axis spans at most kTcMaxNkb K blocks (and its B variants fit 96 KB).  A base
+    // multiple of 4 bytes (four image rows = one TMA row with a 16-byte-multiple stride), the rows the pass reads lie in complete
+    // groups of four image rows counted from the top or from the bottom (tc_split_rows), and a 32-byte chunk of either axis spans at most kTcMaxNkb K blocks (and its B variants fit 96 KB).  A base
     // that is not 16-byte aligned (a cropped view) is rounded down and the difference added to the byte offset, which
     // works as long as the four-row group still fits its pitch.
     {
       const int64_t delta = (int64_t)(reinterpret_cast<uintptr_t>(c.src) & 15);
       const int64_t y_lo = (int64_t)c.y0 + (c.ybox0 & ~3), y_hi = (int64_t)c.y0 + c.ybox0 + c.nrows;
-      const bool inside = c.x0 >= 0 && c.x0 + c.cw <= c.src_w && y_lo >= 0 && y_hi <= (int64_t)(c.src_h / 4) * 4;
+      bool inside = c.x0 >= 0 && c.x0 + c.cw <= c.src_w && y_lo >= 0 && y_hi <= c.src_h;
+      if (inside && y_hi > (int64_t)(c.src_h / 4) * 4) {              // the last rows come through the end-aligned tensor map
+        int64_t nq_a, r_b;
+        const int64_t delta_b = (int64_t)((reinterpret_cast<uintptr_t>(c.src) + (uintptr_t)((c.src_h & 3) * c.pitch)) & 15);
+        inside = tc_split_rows(y_lo, y_hi - y_lo, y_hi, c.src_h, &nq_a, &r_b) && (delta_b == 0 || 3 * (int64_t)c.src_w + delta_b <= c.pitch);
+      }
       c.tc = (tc_enabled && inside && (c.pitch & 3) == 0 && (delta == 0 || 3 * (int64_t)c.src_w + delta <= c.pitch) &&
               4 * c.pitch < (int64_t)1 << 30 && h.nkb3 >= 1 && h.nkb3 <= kTcMaxNkb &&
               h.nkb3 * tc_variants(c.pitch) <= kTcMaxBBlocks && v.nkb1 >= 1 && v.nkb1 <= kTcMaxNkb) ? 1 : 0;
@@ -1192,19 +1210,33 @@ int k1_run(const char* who, const zv_cfg* cfg, int32_t n, const uint8_t* const* 
       const AxisTables& v = L.axis[{c.ch, c.oh}];
       const int64_t t_pitch = L.t_pitch[i];
       uint8_t* t_dev = ws_dev + c.tmp_off;
-      RJob& j1 = jobs[2 * i];
+      RJob& j1 = jobs[3 * i];
       const int64_t delta = (int64_t)(reinterpret_cast<uintptr_t>(c.src) & 15);
       j1.x_off = 3 * (int64_t)c.x0 + delta; j1.in_pitch = c.pitch; j1.out = t_dev; j1.out_pitch = t_pitch;
       j1.row0 = c.y0 + c.ybox0; j1.n_rows = c.nrows; j1.n_out = c.ow; j1.ch = 3;
-      j1.off_b = c.off_bh; j1.off_k = c.off_kh; j1.ksize = c.ksh; j1.origin = 0; j1.tmap = 2 * i; j1.nkb = h.nkb3;
+      j1.off_b = c.off_bh; j1.off_k = c.off_kh; j1.ksize = c.ksh; j1.origin = 0; j1.tmap = 3 * i; j1.nkb = h.nkb3;
       j1.in_base = c.src - delta; j1.in_dim0 = 3 * c.pitch + 3 * (int64_t)c.src_w + delta; j1.in_dim1 = c.src_h / 4;
       j1.nvar = tc_variants(c.pitch);
-      RJob& j2 = jobs[2 * i + 1];
+      // rows past the image's last multiple-of-4 row: a second job over the end-aligned tensor map (tc_split_rows)
+      RJob& j3 = jobs[3 * i + 2];
+      int64_t nq_a, r_b;
+      tc_split_rows(j1.row0, c.nrows, (int64_t)c.y0 + L.ybox0[i] + L.nrows[i], c.src_h, &nq_a, &r_b);
+      j3 = j1;
+      j3.n_rows = (int32_t)std::max<int64_t>(0, c.nrows - 4 * nq_a);  // 0: no tail job
+      j1.n_rows = (int32_t)std::min<int64_t>(c.nrows, 4 * nq_a);
+      if (j3.n_rows > 0) {
+        const int32_t sft = c.src_h & 3;
+        const uint8_t* base_b = c.src + (int64_t)sft * c.pitch;
+        const int64_t delta_b = (int64_t)(reinterpret_cast<uintptr_t>(base_b) & 15);
+        j3.x_off = 3 * (int64_t)c.x0 + delta_b; j3.row0 = (int32_t)(r_b - sft); j3.out = t_dev + 4 * nq_a; j3.tmap = 3 * i + 2;
+        j3.in_base = base_b - delta_b; j3.in_dim0 = 3 * c.pitch + 3 * (int64_t)c.src_w + delta_b; j3.in_dim1 = (c.src_h - sft) / 4;
+      }
+      RJob& j2 = jobs[3 * i + 1];
       j2.x_off = 0; j2.in_pitch = t_pitch;
       j2.out = u8_out ? c.dst : ws_dev + L.off_tmp + L.u_off[i];
       j2.out_pitch = u8_out ? c.dst_pitch : 3 * (int64_t)c.ow;
       j2.row0 = 0; j2.n_rows = 3 * c.ow; j2.n_out = c.oh; j2.ch = 1;
-      j2.off_b = c.off_bv; j2.off_k = c.off_kv; j2.ksize = c.ksv; j2.origin = c.ybox0; j2.tmap = 2 * i + 1; j2.nkb = v.nkb1;
+      j2.off_b = c.off_bv; j2.off_k = c.off_kv; j2.ksize = c.ksv; j2.origin = c.ybox0; j2.tmap = 3 * i + 1; j2.nkb = v.nkb1;
       j2.in_base = t_dev; j2.in_dim0 = 4 * t_pitch; j2.in_dim1 = (3 * c.ow + 3) / 4;
       j2.nvar = 1;                          // t_pitch is a multiple of 16
       TcLaunch& l1 = tcl[tc_class(j1.nvar)];
@@ -1214,10 +1246,15 @@ int k1_run(const char* who, const zv_cfg* cfg, int32_t n, const uint8_t* const* 
         CUtensorMap tm;
         rc = zv::make_tmap_u8(&tm, j1.in_base, (uint64_t)j1.in_dim0, (uint64_t)j1.in_dim1, 4 * (uint64_t)j1.in_pitch, 128, 128);
         if (rc) break;
-        std::memcpy(tmaps + (size_t)(2 * i) * sizeof(CUtensorMap), &tm, sizeof(tm));
+        std::memcpy(tmaps + (size_t)(3 * i) * sizeof(CUtensorMap), &tm, sizeof(tm));
         rc = zv::make_tmap_u8(&tm, j2.in_base, (uint64_t)j2.in_dim0, (uint64_t)j2.in_dim1, 4 * (uint64_t)j2.in_pitch, 128, 128);
         if (rc) break;
-        std::memcpy(tmaps + (size_t)(2 * i + 1) * sizeof(CUtensorMap), &tm, sizeof(tm));
+        std::memcpy(tmaps + (size_t)(3 * i + 1) * sizeof(CUtensorMap), &tm, sizeof(tm));
+        if (j3.n_rows > 0) {
+          rc = zv::make_tmap_u8(&tm, j3.in_base, (uint64_t)j3.in_dim0, (uint64_t)j3.in_dim1, 4 * (uint64_t)j3.in_pitch, 128, 128);
+          if (rc) break;
+          std::memcpy(tmaps + (size_t)(3 * i + 2) * sizeof(CUtensorMap), &tm, sizeof(tm));
+        }
       }
       if (!u8_out) {
         PJob& pj = pjobs[n_pjobs++];
@@ -1237,13 +1274,16 @@ int k1_run(const char* who, const zv_cfg* cfg, int32_t n, const uint8_t* const* 
       tl.list_off = cur;
       for (int32_t i = 0; i < n; ++i) {
         const K1Crop& c = d[i];
-        if (!c.tc || (!pass && tc_class(jobs[2 * i].nvar) != cls)) continue;
+        if (!c.tc || (!pass && tc_class(jobs[3 * i].nvar) != cls)) continue;
         const int chunks = pass ? (c.oh + kTcCols - 1) / kTcCols : (3 * c.ow + kTcCols - 1) / kTcCols;
-        const int tiles = pass ? ((3 * c.ow + 3) / 4 + 127) / 128 : ((c.nrows + 3) / 4 + 127) / 128;
-        for (int t0 = 0; t0 < tiles; t0 += per)
-          for (int ck = 0; ck < chunks; ++ck) {
-            lists[cur++] = 2 * i + pass; lists[cur++] = ck; lists[cur++] = t0; lists[cur++] = std::min(per, tiles - t0);
-          }
+        for (int part = 0; part < (pass ? 1 : 2); ++part) {           // pass 1: the job over the top-aligned map, then the tail job
+          const int job = pass ? 3 * i + 1 : 3 * i + 2 * part;
+          const int tiles = ((jobs[job].n_rows + 3) / 4 + 127) / 128;
+          for (int t0 = 0; t0 < tiles; t0 += per)
+            for (int ck = 0; ck < chunks; ++ck) {
+              lists[cur++] = job; lists[cur++] = ck; lists[cur++] = t0; lists[cur++] = std::min(per, tiles - t0);
+            }
+        }
       }
       tl.count = (cur - tl.list_off) / 4;
     }
