@@ -29,6 +29,8 @@ CASES = [
     (1500, 1500, None, 3136, 3136, "22x downscale, 89 taps"),
     (504, 700, None, 3136, 12845056, "vertical identity, horizontal resize only"),
     (640, 28, None, 3136, 12845056, "thin image"),
+    (1203, 1600, None, 3136, 1003520, "height not a multiple of 4: the last rows come through the end-aligned tensor map"),
+    (1203, 1600, (40, 700, 1500, 1203), 3136, 12845056, "crop that ends on the image's last row, height = 3 mod 4"),
 ]
 
 
