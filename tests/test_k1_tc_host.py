@@ -95,10 +95,25 @@ def test_tc_route_resize_u8_ragged_batch():
 
 
 def test_tc_route_declines_what_it_cannot_do():
-    img = _aligned(_img(3, 602, 800))
-    boxes = [(-5, 0, 400, 300), (0, 0, 800, 602), (0, 0, 800, 600)]           # the first leaves the image: zero fill, other kernels
-    _, took = _run([img], [0, 0, 0], boxes, [(280, 392), (280, 392), (280, 392)], patches=True)
-    assert took.tolist() == [0, 1, 1]
+    img = _aligned(_img(3, 602, 803))[:, :801]                               # row pitch 2409: not a multiple of 4
+    _, took = _run([img], [0], [(0, 0, 800, 600)], [(280, 392)], patches=True)
+    assert took.tolist() == [0]
+    img = _aligned(_img(3, 600, 4800))                                        # 12x horizontal downscale: more than four K blocks
+    _, took = _run([img], [0], [(0, 0, 4800, 600)], [(280, 392)], patches=True)
+    assert took.tolist() == [0]
+
+
+@pytest.mark.parametrize("box", [(-20, -30, 480, 470), (300, 200, 900, 640), (-7, 100, 810, 400), (100, -50, 500, 700),
+                                 (790, 590, 830, 630), (-60, -60, -10, -10), (0, 598, 800, 640)])
+def test_tc_route_boxes_that_leave_the_image(box):
+    """Image.crop's zero fill: rows above / below the image are zero-filled by the TMA unit, taps left / right of it are
+    left out of B; a box wholly outside gives the resize of a black image"""
+    img = _aligned(_img(5, 602, 800))
+    w, h = box[2] - box[0], box[3] - box[1]
+    ohw = (max(8, int(h / 1.7)), max(8, int(w / 1.3)))
+    outs, took = _run([img], [0], [box], [ohw], patches=False)
+    assert took.tolist() == [1]
+    assert np.array_equal(outs[0], OR.resize_u8(OR.crop_u8(img, box), ohw[1], ohw[0])), box
 
 
 @pytest.mark.parametrize("h", [601, 602, 603, 1203])

@@ -1017,7 +1017,7 @@ void launch_vpass(int nw, int count, cudaStream_t s, const K1Crop* d, const int3
 // first job, first image row of the second (rows_end when there is none); false when the split is impossible.
 inline bool tc_split_rows(int64_t row0, int64_t nrows, int64_t y_hi, int32_t src_h, int64_t* nq_a, int64_t* r_b) {
   const int64_t nq = (nrows + 3) / 4, limit = (int64_t)(src_h / 4) * 4;
-  if (y_hi <= limit) { *nq_a = nq; *r_b = row0 + 4 * nq; return true; }
+  if (y_hi <= limit || row0 >= src_h) { *nq_a = nq; *r_b = row0 + 4 * nq; return true; }   // (rows past the image are zero either way)
   const int64_t k = row0 >= limit ? 0 : (limit - row0) / 4;
   *nq_a = std::min(nq, k);
   *r_b = row0 + 4 * *nq_a;
@@ -1088,7 +1088,7 @@ int k1_run(const char* who, const zv_cfg* cfg, int32_t n, const uint8_t* const* 
     seg_h[i] = h.seg_words;
     tq_v[i] = v.tile_quads;
     c.ybox0 = L.ybox0[i]; c.nrows = L.nrows[i];
-    // Tensor-core route (k1_resample_tc): the crop lies inside the image (no zero fill needed), the row pitch is a
+    // Tensor-core route (k1_resample_tc): the row pitch is a
     // multiple of 4 bytes (four image rows = one TMA row with a 16-byte-multiple stride), the rows the pass reads lie in complete
     // groups of four image rows counted from the top or from the bottom (tc_split_rows), and a 32-byte chunk of either axis spans at most kTcMaxNkb K blocks (and its B variants fit 96 KB).  A base
     // that is not 16-byte aligned (a cropped view) is rounded down and the difference added to the byte offset, which
@@ -1096,8 +1096,10 @@ int k1_run(const char* who, const zv_cfg* cfg, int32_t n, const uint8_t* const* 
     {
       const int64_t delta = (int64_t)(reinterpret_cast<uintptr_t>(c.src) & 15);
       const int64_t y_lo = (int64_t)c.y0 + (c.ybox0 & ~3), y_hi = (int64_t)c.y0 + c.ybox0 + c.nrows;
-      bool inside = c.x0 >= 0 && c.x0 + c.cw <= c.src_w && y_lo >= 0 && y_hi <= c.src_h;
-      if (inside && y_hi > (int64_t)(c.src_h / 4) * 4) {              // the last rows come through the end-aligned tensor map
+      // (a box that leaves the image is fine: rows above / below are zero-filled by the TMA unit, taps left / right of the
+      // image are left out of B - Image.crop's zero fill)
+      bool inside = c.src_h >= 8;
+      if (inside && y_hi > (int64_t)(c.src_h / 4) * 4 && y_lo < c.src_h) {   // the last rows come through the end-aligned tensor map (tc_split_rows)
         int64_t nq_a, r_b;
         const int64_t delta_b = (int64_t)((reinterpret_cast<uintptr_t>(c.src) + (uintptr_t)((c.src_h & 3) * c.pitch)) & 15);
         inside = tc_split_rows(y_lo, y_hi - y_lo, y_hi, c.src_h, &nq_a, &r_b) && (delta_b == 0 || 3 * (int64_t)c.src_w + delta_b <= c.pitch);
@@ -1217,6 +1219,7 @@ int k1_run(const char* who, const zv_cfg* cfg, int32_t n, const uint8_t* const* 
       j1.off_b = c.off_bh; j1.off_k = c.off_kh; j1.ksize = c.ksh; j1.origin = 0; j1.tmap = 3 * i; j1.nkb = h.nkb3;
       j1.in_base = c.src - delta; j1.in_dim0 = 3 * c.pitch + 3 * (int64_t)c.src_w + delta; j1.in_dim1 = c.src_h / 4;
       j1.nvar = tc_variants(c.pitch);
+      j1.lo = -c.x0; j1.hi = c.src_w - c.x0;                          // crop columns that exist in the image
       // rows past the image's last multiple-of-4 row: a second job over the end-aligned tensor map (tc_split_rows)
       RJob& j3 = jobs[3 * i + 2];
       int64_t nq_a, r_b;
@@ -1239,6 +1242,7 @@ int k1_run(const char* who, const zv_cfg* cfg, int32_t n, const uint8_t* const* 
       j2.off_b = c.off_bv; j2.off_k = c.off_kv; j2.ksize = c.ksv; j2.origin = c.ybox0; j2.tmap = 3 * i + 1; j2.nkb = v.nkb1;
       j2.in_base = t_dev; j2.in_dim0 = 4 * t_pitch; j2.in_dim1 = (3 * c.ow + 3) / 4;
       j2.nvar = 1;                          // t_pitch is a multiple of 16
+      j2.lo = INT32_MIN / 2; j2.hi = INT32_MAX / 2;
       TcLaunch& l1 = tcl[tc_class(j1.nvar)];
       l1.nvar = j1.nvar; l1.nkb = std::max(l1.nkb, h.nkb3); tcl[3].nkb = std::max(tcl[3].nkb, v.nkb1);
       // source: super-rows of four image rows (the last image row's padding is not touched); T likewise

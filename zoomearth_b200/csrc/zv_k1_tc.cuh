@@ -49,7 +49,8 @@ struct RJob {                 // one resample pass over one crop
   int64_t in_dim0;            // device kernel reaches the input through TMA only
   int32_t in_dim1;
   int32_t nvar;               // B variants (1, 2 or 4): distinct box-start slacks of the four row phases
-};
+  int32_t lo, hi;             // table samples [lo, hi) exist in the input; taps outside multiply nothing (Image.crop's zero
+};                            // fill left / right of the image: the bytes the box holds there belong to a neighbouring row)
 
 constexpr int kTcCols = 32;                 // output bytes per chunk
 constexpr int kTcEpiWarps = 16;             // four per TMEM lane quarter, 8 output bytes each
@@ -241,8 +242,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k1_resample_tc(const RJob* __re
         o = jb / ch; cc = jb - o * ch;
         return idx < total && jb < n_bytes;
       };
+      const int s_lo = j.lo, s_hi = j.hi;
       auto scatter = [&](int c, int t, int cc, int xmin, int cnt, int k) {
-        if (t >= cnt) return;
+        if (t >= cnt || xmin + t < s_lo || xmin + t >= s_hi) return;
         int dg[3];
         tc_digits(k, dg);
         const int kwin = ch * (xmin - origin + t) + cc - wb0;         // input byte of this tap, from the window's first byte
@@ -443,6 +445,7 @@ inline void tc_emulate_resample(const RJob* jobs, const int4* items, int n_items
       const int o = jb / j.ch, cc = jb - o * j.ch;
       const int xmin = coef[j.off_b + 2 * o], cnt = coef[j.off_b + 2 * o + 1];
       for (int t = 0; t < cnt; ++t) {
+        if (xmin + t < j.lo || xmin + t >= j.hi) continue;
         int dg[3];
         tc_digits(coef[j.off_k + (int64_t)o * j.ksize + t], dg);
         const int kwin = j.ch * (xmin - j.origin + t) + cc - wb0;
