@@ -134,7 +134,7 @@ ZV_API int zv_resize_u8(int32_t n, const uint8_t* const* src_dev, const int32_t*
 
 /* Test hook (CPU, no GPU needed): runs the HOST side of zv_preprocess / zv_resize_u8 - descriptors, tap tables, work
  * lists of the tensor-core route (csrc/zv_k1_tc.cuh) - over HOST pointers and emulates that route's kernels lane by lane
- * on the CPU.  took_tc[i] = 1 for the crops the route accepts (inside the image, 16-byte aligned base, <= 4 K blocks);
+ * on the CPU.  took_tc[i] = 1 for the crops the route accepts (row pitch a multiple of 4 bytes, <= 4 K blocks per chunk);
  * only those are written.  u8_dst_host == NULL: fp32 patches into out_host (zv_preprocess), else uint8 images
  * (zv_resize_u8).  Checks everything but the hardware layouts (swizzle, descriptors, TMEM), which the GPU tests cover. */
 ZV_API int zv_debug_k1_tc_host(const zv_cfg* cfg, int32_t n, const uint8_t* const* src_host, const int32_t* src_hw,

@@ -12,10 +12,10 @@
 // Integer arithmetic only, bit-identical to Pillow: 22-bit fixed-point taps computed on the host in fp64
 // (zv_host.cpp), int32 sums.
 //
-// Main route (zv_k1_tc.cuh; crops inside the image, row pitch a multiple of 4): both passes run as ONE transposing
+// Main route (zv_k1_tc.cuh; row pitch a multiple of 4, downscales up to ~10x): both passes run as ONE transposing
 // tcgen05 kernel (TMA -> kind::i8 UMMA -> TMEM epilogue), source -> T (transposed) -> U (the finished uint8 image), and a
-// small kernel turns U into normalised patches.  The kernels below serve what that route declines: boxes that leave the
-// image (zero fill), odd pitches, more than 45 taps per axis.
+// small kernel turns U into normalised patches.  The kernels below serve what that route declines: other row pitches,
+// larger downscales.
 //
 // Fallback fast path (taps <= 45 per axis, 4-byte aligned image rows): the work is instruction-bound on the integer pipes
 // (4 multiply-adds per source byte), so both passes run on dp4a.  Each 23-bit tap is split into three byte limbs
