@@ -170,3 +170,22 @@ def test_k1_random_sweep_bitexact(cuda, seed):
         widx, _ = OT.window_index(np.concatenate(grids, 0))
         ref_w = torch.from_numpy(ref).view(-1, 4, 1176)[torch.from_numpy(widx)].reshape(-1, 1176).to(torch.bfloat16)
         assert torch.equal(pvw.cpu(), ref_w)
+
+
+def test_upload_pads_odd_widths_to_a_tensor_core_pitch(cuda):
+    """processor.upload_u8: a 701-pixel-wide image (row pitch 2103 bytes, which K1's tensor-core route cannot read) is
+    stored with padded rows and handed out as a view; pixels, patches and the device resize stay bit-exact"""
+    from zoomearth_b200 import FusedImageProcessor
+    from zoomearth_b200.processor import upload_u8
+    img = _img(77, 603, 701)
+    dev = upload_u8(torch.from_numpy(img), cuda)
+    assert dev.shape == (603, 701, 3) and dev.stride(0) % 16 == 0 and dev.stride(1) == 3
+    assert torch.equal(dev.cpu(), torch.from_numpy(img))
+    fp = FusedImageProcessor(min_pixels=3136, max_pixels=200704, device=cuda)
+    boxes = [(0, 0, 701, 603), (11, 7, 690, 603), (-9, -4, 400, 300)]
+    pv, grid, _ = fp.preprocess_crops([dev], boxes, torch.float32, image_index=[0, 0, 0])
+    refs, grids = zip(*[_oracle_crop(img, b, 3136, 200704) for b in boxes])
+    assert grid.tolist() == np.concatenate(grids, 0).tolist()
+    assert np.array_equal(pv.cpu().numpy(), np.concatenate(refs, 0))
+    out = fp.resize_u8([dev], [(3, 5, 699, 601)], [(233, 199)])[0]
+    assert np.array_equal(out.cpu().numpy(), OR.resize_u8(OR.crop_u8(img, (3, 5, 699, 601)), 233, 199))

@@ -57,12 +57,10 @@ class ImageStore:
         t = torch.from_numpy(arr)
         if self.device.type != "cuda":
             return t, None
-        t = t.pin_memory()
-        with torch.cuda.stream(self._copy_stream):
-            d = t.to(self.device, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(self._copy_stream)
-        d._zv_pinned_src = t                      # the pinned source must outlive the async copy
+        from .processor import upload_u8
+        d = upload_u8(t, self.device, stream=self._copy_stream)       # pinned, async, rows padded when 3 W is not a multiple of 4
+        ev = torch.cuda.Event()
+        ev.record(self._copy_stream)
         return d, ev
 
     def prefetch(self, paths):

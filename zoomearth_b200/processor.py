@@ -44,6 +44,27 @@ def _flatten(images):
     return [images]
 
 
+def upload_u8(t_host, device, stream=None):
+    """Host (H, W, 3) uint8 tensor -> resident CUDA image.  When the packed row pitch (3 W bytes) is not a multiple of 4 -
+    three widths out of four - the image is stored with its rows padded to a multiple of 16 pixels and returned as a
+    (H, W, 3) view of that buffer: K1's tensor-core route needs a row pitch that is a multiple of 4 bytes (zv_k1_tc.cuh),
+    and with a multiple of 16 it needs a single coefficient variant.  Every entry point takes row-pitched views."""
+    h, w = int(t_host.shape[0]), int(t_host.shape[1])
+    if t_host.device.type != "cpu":
+        return t_host
+    src = t_host if t_host.is_pinned() else t_host.pin_memory()
+    ctx = torch.cuda.stream(stream) if stream is not None else torch.cuda.device(device)
+    with ctx:
+        if w % 4 == 0:
+            d = src.to(device, non_blocking=True)
+        else:
+            buf = torch.empty((h, (w + 15) // 16 * 16, 3), dtype=torch.uint8, device=device)
+            d = buf[:, :w]
+            d.copy_(src, non_blocking=True)
+    d._zv_pinned_src = src                        # the pinned source must outlive the async copy
+    return d
+
+
 def _to_u8_hwc(image):
     """PIL / ndarray / tensor -> contiguous (H, W, 3) uint8 torch tensor on its current device."""
     if hasattr(image, "convert") and hasattr(image, "size"):          # PIL.Image
@@ -299,11 +320,7 @@ class FusedImageProcessor:
         imgs = [_to_u8_hwc(i) for i in _flatten(images)]
         if not imgs:
             raise ValueError("no images given")
-        dev_imgs = []
-        for t in imgs:
-            if t.device.type != "cuda":
-                t = t.pin_memory().to(device, non_blocking=True)
-            dev_imgs.append(t)
+        dev_imgs = [upload_u8(t, device) for t in imgs]
         pv, grid, _ = self.preprocess_crops(dev_imgs, None, torch.float32, False, min_pixels, max_pixels)
         if self.output_device == "cpu":
             pv = pv.cpu()

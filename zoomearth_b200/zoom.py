@@ -76,11 +76,8 @@ class ZoomEncoder:
 
     def upload(self, image):
         """PIL / (H, W, 3) uint8 array or tensor -> resident uint8 CUDA tensor (one H2D copy per image)."""
-        from .processor import _to_u8_hwc
-        t = _to_u8_hwc(image)
-        if t.device.type != "cuda":
-            t = t.pin_memory().to(self.visual.device, non_blocking=True)
-        return t
+        from .processor import _to_u8_hwc, upload_u8
+        return upload_u8(_to_u8_hwc(image), self.visual.device)     # rows padded when 3 W is not a multiple of 4 (a view comes back)
 
     @torch.no_grad()
     def encode(self, images_dev, boxes=None, image_index=None, apply_cut_image=True, return_patches=False,
