@@ -116,6 +116,7 @@ def test_k1_full_size_global_view_vs_pillow(cuda):
     fp = FusedImageProcessor(min_pixels=3136, max_pixels=1280 * 28 * 28, device=cuda)
     pv, grid, _ = fp.preprocess_crops([torch.from_numpy(img).to(cuda)], None, torch.float32)
     assert grid.tolist() == [[1, 70, 70]]
+    assert fp.last_launches == 3, "the bench shape must take the tensor-core route: two k1_resample_tc passes + k1_patchify_u8"
     r = np.asarray(Image.fromarray(img).resize((980, 980), Image.BICUBIC))
     lut = OP.normalize_lut()
     ref, _ = OP.patchify(np.stack([lut[c][r[:, :, c]] for c in range(3)], 0))
@@ -184,6 +185,7 @@ def test_upload_pads_odd_widths_to_a_tensor_core_pitch(cuda):
     fp = FusedImageProcessor(min_pixels=3136, max_pixels=200704, device=cuda)
     boxes = [(0, 0, 701, 603), (11, 7, 690, 603), (-9, -4, 400, 300)]
     pv, grid, _ = fp.preprocess_crops([dev], boxes, torch.float32, image_index=[0, 0, 0])
+    assert fp.last_launches == 3, "odd height, a box that leaves the image, a padded pitch: all on the tensor-core route"
     refs, grids = zip(*[_oracle_crop(img, b, 3136, 200704) for b in boxes])
     assert grid.tolist() == np.concatenate(grids, 0).tolist()
     assert np.array_equal(pv.cpu().numpy(), np.concatenate(refs, 0))
