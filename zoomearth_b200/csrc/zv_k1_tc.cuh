@@ -397,29 +397,16 @@ __global__ void __launch_bounds__(256) k1_patchify_u8(const PJob* __restrict__ j
   const int e0 = roff + (x0 / 14) * kPatchElems + (x0 % 14), e1 = roff + (x1 / 14) * kPatchElems + (x1 % 14);
   zv::ptx::pdl_wait();
   __syncthreads();
-  // a thread's 12 bytes of merge group g (the job index only moves forward: groups ascend)
-  int jn = 0;
-  auto fetch = [&](int g, uint32_t (&w)[3]) {
-    while (jn + 1 < n_jobs && __ldg(&jobs[jn + 1].blk0) <= g) ++jn;
-    const PJob& j = jobs[jn];
-    const int gl = g - j.blk0, my = gl / j.lw, mx = gl - my * j.lw;
-    const uint32_t* __restrict__ u = reinterpret_cast<const uint32_t*>(j.u + (int64_t)(my * 28 + yl) * j.u_pitch + mx * 84 + 12 * sg);
-    w[0] = u[0]; w[1] = u[1]; w[2] = u[2];               // R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
-  };
-  uint32_t cur[3] = {0u, 0u, 0u}, nxt[3] = {0u, 0u, 0u};
-  if (active && (int)blockIdx.x < n_groups) fetch(blockIdx.x, cur);
-  int jc = 0, buf = 0;
+  int jn = 0, buf = 0;
   for (int g = blockIdx.x; g < n_groups; g += gridDim.x, buf ^= 1) {
-    // the next group's pixels are requested before this group is converted: the global round trip hides under the work
-    const int gn = g + gridDim.x;
-    if (active && gn < n_groups) fetch(gn, nxt);
-    while (jc + 1 < n_jobs && __ldg(&jobs[jc + 1].blk0) <= g) ++jc;
-    const PJob& j = jobs[jc];
+    while (jn + 1 < n_jobs && __ldg(&jobs[jn + 1].blk0) <= g) ++jn;                // groups ascend: the job index only moves forward
+    const PJob& j = jobs[jn];
     const int gl = g - j.blk0, lw = j.lw;
     const int my = gl / lw, mx = gl - my * lw;
     OutT* st = stage[buf];
     if (active) {
-      const uint32_t w0 = cur[0], w1 = cur[1], w2 = cur[2];
+      const uint32_t* __restrict__ u = reinterpret_cast<const uint32_t*>(j.u + (int64_t)(my * 28 + yl) * j.u_pitch + mx * 84 + 12 * sg);
+      const uint32_t w0 = u[0], w1 = u[1], w2 = u[2];      // R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
       const float r0 = s_lut[w0 & 255], r1 = s_lut[w0 >> 24], r2 = s_lut[(w1 >> 16) & 255], r3 = s_lut[(w2 >> 8) & 255];
       const float g0 = s_lut[256 + ((w0 >> 8) & 255)], g1 = s_lut[256 + (w1 & 255)], g2 = s_lut[256 + (w1 >> 24)], g3 = s_lut[256 + ((w2 >> 16) & 255)];
       const float b0 = s_lut[512 + ((w0 >> 16) & 255)], b1 = s_lut[512 + ((w1 >> 8) & 255)], b2 = s_lut[512 + (w2 & 255)], b3 = s_lut[512 + (w2 >> 24)];
@@ -436,7 +423,6 @@ __global__ void __launch_bounds__(256) k1_patchify_u8(const PJob* __restrict__ j
     const uint4* srcv = reinterpret_cast<const uint4*>(st);
     constexpr int kVec = 4 * kPatchElems * (int)sizeof(OutT) / 16;
     for (int i = tid; i < kVec; i += 256) dst[i] = srcv[i];
-    cur[0] = nxt[0]; cur[1] = nxt[1]; cur[2] = nxt[2];
   }
 }
 
